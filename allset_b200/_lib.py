@@ -1,0 +1,261 @@
+"""ctypes binding of liballset_b200.so -- the C ABI declared in include/allset_b200.h.
+
+This is the ONLY way the Python host reaches the device code.  There is no CPU or PyTorch fallback:
+if the shared library is missing, `lib()` raises with the build command (`python -m allset_b200.build`).
+Every wrapper takes torch CUDA tensors, checks dtype/contiguity/device, and enqueues on
+`torch.cuda.current_stream()`; buffers (outputs and workspaces) are allocated by the caller-side
+PyTorch caching allocator, never by the library.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liballset_b200.so')
+ABI_VERSION = 1
+
+F32, BF16 = 0, 1
+SUM, MEAN = 0, 1
+
+_c = ctypes
+_p = _c.c_void_p
+_i32, _i64, _f32, _sz = _c.c_int32, _c.c_int64, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/allset_b200.h one to one
+SIGNATURES = {
+    'allset_version': (_c.c_int, []),
+    'allset_last_error': (_c.c_char_p, []),
+    'allset_csr_workspace_bytes': (_sz, [_i64, _i64]),
+    'allset_csr_from_coo': (_c.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
+    'allset_long_segments_workspace_bytes': (_sz, [_i64]),
+    'allset_long_segments': (_c.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
+    'allset_segreduce_fwd': (_c.c_int, [_p, _c.c_int, _i64, _i32, _p, _p, _p, _p, _i64, _c.c_int,
+                                        _p, _i32, _i32, _p, _p]),
+    'allset_segreduce_bwd_w': (_c.c_int, [_p, _p, _c.c_int, _i32, _p, _p, _p, _i64, _p, _p]),
+    'allset_pma_fwd': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
+                                  _p, _i32, _i32, _p, _p, _p]),
+    'allset_pma_alpha': (_c.c_int, [_p, _p, _i32, _f32, _p, _p, _i64, _p, _p]),
+    'allset_rowdot_heads': (_c.c_int, [_p, _p, _p, _c.c_int, _i64, _i32, _i32, _p, _p]),
+    'allset_pma_bwd': (_c.c_int, [_p, _p, _p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
+                                  _p, _i32, _i32, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            'allset_b200: %s not found. The aggregation path has no CPU fallback; build the sm_100a library '
+            'with `python -m allset_b200.build` (needs nvcc).' % LIB_PATH)
+    h = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(h, name)            # AttributeError here = header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    if h.allset_version() != ABI_VERSION:
+        raise RuntimeError('allset_b200: ABI version %d != expected %d; rebuild with `python -m allset_b200.build`'
+                           % (h.allset_version(), ABI_VERSION))
+    _lib = h
+    return h
+
+
+def _check(code: int, what: str) -> None:
+    if code != 0:
+        raise RuntimeError('%s failed (%d): %s' % (what, code, lib().allset_last_error().decode()))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError('allset_b200 kernels store features as float32 or bfloat16, got %s' % t.dtype)
+
+
+def _need(t: Optional[torch.Tensor], name: str, dtype=None, optional=False) -> None:
+    if t is None:
+        if optional:
+            return
+        raise ValueError('%s is required' % name)
+    if not t.is_cuda:
+        raise RuntimeError('%s must be a CUDA tensor: allset_b200 has no CPU path (got device %s)' % (name, t.device))
+    if not t.is_contiguous():
+        raise ValueError('%s must be contiguous' % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError('%s must be %s, got %s' % (name, dtype, t.dtype))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# incidence container
+# ----------------------------------------------------------------------------------------------------------
+def csr_from_coo(tgt: torch.Tensor, src: torch.Tensor, n_tgt: int):
+    """Stable sort of a COO incidence list by target -> (rowptr[n_tgt+1], col[nnz], perm[nnz]) int32."""
+    _need(tgt, 'tgt', torch.int64)
+    _need(src, 'src', torch.int64)
+    nnz = tgt.numel()
+    dev = tgt.device
+    with torch.cuda.device(dev):
+        rowptr = torch.empty(n_tgt + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        perm = torch.empty(nnz, dtype=torch.int32, device=dev)
+        ws_bytes = lib().allset_csr_workspace_bytes(nnz, n_tgt)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        _check(lib().allset_csr_from_coo(_ptr(tgt), _ptr(src), nnz, n_tgt, _ptr(rowptr), _ptr(col), _ptr(perm),
+                                         _ptr(ws), ws_bytes, _stream()), 'allset_csr_from_coo')
+    return rowptr, col, perm
+
+
+def long_segments(rowptr: torch.Tensor, n_tgt: int, threshold: int) -> Optional[torch.Tensor]:
+    """Row ids of segments longer than `threshold` (int32, ascending) or None.  Synchronises once (graph build)."""
+    _need(rowptr, 'rowptr', torch.int32)
+    dev = rowptr.device
+    if n_tgt == 0:
+        return None
+    with torch.cuda.device(dev):
+        ids = torch.empty(n_tgt, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws_bytes = lib().allset_long_segments_workspace_bytes(n_tgt)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        _check(lib().allset_long_segments(_ptr(rowptr), n_tgt, threshold, _ptr(ids), _ptr(cnt), _ptr(ws), ws_bytes,
+                                          _stream()), 'allset_long_segments')
+        n = int(cnt.item())
+    return ids[:n].clone() if n > 0 else None
+
+
+# ----------------------------------------------------------------------------------------------------------
+# AllDeepSets
+# ----------------------------------------------------------------------------------------------------------
+def segreduce_fwd(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, mean: bool,
+                  w: Optional[torch.Tensor] = None, src_scale: Optional[torch.Tensor] = None,
+                  long_ids: Optional[torch.Tensor] = None, long_threshold: int = 0,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(x, 'x')
+    _need(rowptr, 'rowptr', torch.int32)
+    _need(col, 'col', torch.int32)
+    _need(w, 'w', torch.float32, optional=True)
+    _need(src_scale, 'src_scale', torch.float32, optional=True)
+    if x.dim() != 2:
+        raise ValueError('x must be [n_src, d]')
+    n_src, d = x.shape
+    if rowptr.numel() < n_tgt + 1:
+        raise ValueError('rowptr has %d entries, need %d' % (rowptr.numel(), n_tgt + 1))
+    if w is not None and w.numel() != col.numel():
+        raise ValueError('w must have one entry per incidence')
+    if src_scale is not None and src_scale.numel() != n_src:
+        raise ValueError('src_scale must have one entry per source row')
+    if out is None:
+        out = torch.empty((n_tgt, d), dtype=x.dtype, device=x.device)
+    else:
+        _need(out, 'out', x.dtype)
+    if d == 0 or n_tgt == 0:
+        return out
+    n_long = 0 if long_ids is None else long_ids.numel()
+    with torch.cuda.device(x.device):
+        _check(lib().allset_segreduce_fwd(_ptr(x), _dtype_code(x), n_src, d, _ptr(rowptr), _ptr(col), _ptr(w),
+                                          _ptr(src_scale), n_tgt, MEAN if mean else SUM, _ptr(long_ids), n_long,
+                                          long_threshold, _ptr(out), _stream()), 'allset_segreduce_fwd')
+    return out
+
+
+def segreduce_bwd_w(x: torch.Tensor, grad_out: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int,
+                    tgt_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(x, 'x')
+    _need(grad_out, 'grad_out', x.dtype)
+    _need(tgt_scale, 'tgt_scale', torch.float32, optional=True)
+    gw = torch.empty(col.numel(), dtype=torch.float32, device=x.device)
+    if col.numel() == 0:
+        return gw
+    with torch.cuda.device(x.device):
+        _check(lib().allset_segreduce_bwd_w(_ptr(x), _ptr(grad_out), _dtype_code(x), x.shape[1], _ptr(rowptr), _ptr(col),
+                                            _ptr(tgt_scale), n_tgt, _ptr(gw), _stream()), 'allset_segreduce_bwd_w')
+    return gw
+
+
+# ----------------------------------------------------------------------------------------------------------
+# AllSetTransformer (PMA)
+# ----------------------------------------------------------------------------------------------------------
+def pma_fwd(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: int, C: int, slope: float,
+            rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, want_stats: bool = True,
+            long_ids: Optional[torch.Tensor] = None, long_threshold: int = 0):
+    """v [n_src, H*C], score [n_src, H] f32, seed [H*C] f32 -> (out [n_tgt, H*C], stats [n_tgt, H, 2] | None)."""
+    _need(v, 'v')
+    _need(score, 'score', torch.float32)
+    _need(seed, 'seed', torch.float32)
+    _need(rowptr, 'rowptr', torch.int32)
+    _need(col, 'col', torch.int32)
+    if v.dim() != 2 or v.shape[1] != H * C or score.shape != (v.shape[0], H) or seed.numel() != H * C:
+        raise ValueError('pma_fwd: shape mismatch v%s score%s seed%s H=%d C=%d'
+                         % (tuple(v.shape), tuple(score.shape), tuple(seed.shape), H, C))
+    out = torch.empty((n_tgt, H * C), dtype=v.dtype, device=v.device)
+    stats = torch.empty((n_tgt, H, 2), dtype=torch.float32, device=v.device) if want_stats else None
+    if n_tgt == 0:
+        return out, stats
+    n_long = 0 if long_ids is None else long_ids.numel()
+    with torch.cuda.device(v.device):
+        _check(lib().allset_pma_fwd(_ptr(v), _ptr(score), _ptr(seed), _dtype_code(v), H, C, float(slope), _ptr(rowptr),
+                                    _ptr(col), n_tgt, _ptr(long_ids), n_long, long_threshold, _ptr(out), _ptr(stats),
+                                    _stream()), 'allset_pma_fwd')
+    return out, stats
+
+
+def pma_alpha(score: torch.Tensor, stats: torch.Tensor, H: int, slope: float, rowptr: torch.Tensor,
+              col: torch.Tensor, n_tgt: int) -> torch.Tensor:
+    _need(score, 'score', torch.float32)
+    _need(stats, 'stats', torch.float32)
+    alpha = torch.empty((col.numel(), H), dtype=torch.float32, device=score.device)
+    if col.numel() == 0:
+        return alpha
+    with torch.cuda.device(score.device):
+        _check(lib().allset_pma_alpha(_ptr(score), _ptr(stats), H, float(slope), _ptr(rowptr), _ptr(col), n_tgt,
+                                      _ptr(alpha), _stream()), 'allset_pma_alpha')
+    return alpha
+
+
+def rowdot_heads(a: torch.Tensor, b: torch.Tensor, sub: Optional[torch.Tensor], H: int, C: int) -> torch.Tensor:
+    _need(a, 'a')
+    _need(b, 'b', a.dtype)
+    _need(sub, 'sub', torch.float32, optional=True)
+    n = a.shape[0]
+    out = torch.empty((n, H), dtype=torch.float32, device=a.device)
+    if n == 0:
+        return out
+    with torch.cuda.device(a.device):
+        _check(lib().allset_rowdot_heads(_ptr(a), _ptr(b), _ptr(sub), _dtype_code(a), n, H, C, _ptr(out), _stream()),
+               'allset_rowdot_heads')
+    return out
+
+
+def pma_bwd(grad_out: torch.Tensor, v: torch.Tensor, score: torch.Tensor, stats: torch.Tensor, D: torch.Tensor,
+            H: int, C: int, slope: float, rowptrT: torch.Tensor, colT: torch.Tensor, n_src: int,
+            long_ids: Optional[torch.Tensor] = None, long_threshold: int = 0):
+    _need(grad_out, 'grad_out', v.dtype)
+    _need(v, 'v')
+    _need(score, 'score', torch.float32)
+    _need(stats, 'stats', torch.float32)
+    _need(D, 'D', torch.float32)
+    grad_v = torch.empty_like(v)
+    grad_score = torch.empty_like(score)
+    if n_src == 0:
+        return grad_v, grad_score
+    n_long = 0 if long_ids is None else long_ids.numel()
+    with torch.cuda.device(v.device):
+        _check(lib().allset_pma_bwd(_ptr(grad_out), _ptr(v), _ptr(score), _ptr(stats), _ptr(D), _dtype_code(v), H, C,
+                                    float(slope), _ptr(rowptrT), _ptr(colT), n_src, _ptr(long_ids), n_long,
+                                    long_threshold, _ptr(grad_v), _ptr(grad_score), _stream()), 'allset_pma_bwd')
+    return grad_v, grad_score

@@ -1,0 +1,1082 @@
+// allset_kernels.cu -- sm_100a kernels + C ABI for AllSet's V->E / E->V multiset aggregation.
+//
+// Replaces, per direction, the reference's index_select -> norm*x_j -> torch_scatter.scatter chain
+// (reference src/layers.py:633,638-639,656) and PMA's gather -> leaky_relu -> segment softmax ->
+// weight -> scatter-add chain (src/layers.py:145-153,168-194) with ONE launch over a CSR-by-target
+// incidence list.  See include/allset_b200.h for the contract of each entry point and DESIGN.md
+// for the data layout and the roofline each kernel is bounded by (HBM bandwidth for all of them).
+//
+// Work decomposition (common to all gather kernels)
+//   * a feature row is cut into 16-byte chunks (8 bf16 / 4 fp32); lane `gl` of a lane GROUP of
+//     G = 2^k <= 32 lanes owns chunk gl of the row, so one row load is a single coalesced
+//     128-bit-per-lane request (d=128 bf16: G=16, two segments per warp; d=128 fp32: G=32);
+//   * one group owns one target segment: it reads G column indices with one coalesced load,
+//     broadcasts them with group-masked shuffles, and issues U=8 independent row loads
+//     (ld.global.nc.L1::no_allocate.v4) before the first use -- the memory-level parallelism
+//     that hides HBM latency on 256-byte random rows;
+//   * accumulation is fp32 in registers in CSR (= caller's COO) order, so fp32 sums are
+//     bit-identical to the reference's sequential CPU scatter_add_; no atomics anywhere;
+//   * segments longer than `long_threshold` are skipped by the group kernel and handled by a
+//     CTA-per-segment kernel (8 warps stride over the segment, shared-memory tree at the end);
+//   * rows wider than 32 chunks are processed as independent 32-chunk slabs (blockIdx.y).
+// Rows whose byte width or base address is not 16-byte aligned take the same kernels with
+// 1-element chunks (scalar path) -- still CUDA, never a host fallback.
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cub/cub.cuh>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "allset_b200.h"
+
+namespace {
+
+thread_local char g_err[512] = {0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ALLSET_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  return ALLSET_OK;
+}
+
+constexpr int kThreads = 256;   // 8 warps per CTA
+constexpr int kUnroll = 8;      // independent row loads in flight per lane
+
+// ---------------------------------------------------------------------------------------------
+// chunk access: VECTOR = one 16-byte chunk per lane; otherwise one element per lane
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_nc_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+template <typename T, bool VECTOR>
+struct Chunk;
+
+template <>
+struct Chunk<float, true> {
+  static constexpr int N = 4;
+  using Raw = uint4;
+  __device__ static __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  __device__ static __forceinline__ Raw load(const float* p) { return ld_nc_16(p); }
+  __device__ static __forceinline__ void unpack(const Raw& r, float (&f)[N]) {
+    f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y);
+    f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&f)[N]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+
+template <>
+struct Chunk<__nv_bfloat16, true> {
+  static constexpr int N = 8;
+  using Raw = uint4;
+  __device__ static __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  __device__ static __forceinline__ Raw load(const __nv_bfloat16* p) { return ld_nc_16(p); }
+  __device__ static __forceinline__ void unpack(const Raw& r, float (&f)[N]) {
+    // bf16 -> fp32 is a 16-bit shift: exact
+    f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+    f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+    f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
+    f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&f)[N]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]);
+    __nv_bfloat162 e = __floats2bfloat162_rn(f[6], f[7]);
+    uint4 o;
+    o.x = *reinterpret_cast<unsigned*>(&a); o.y = *reinterpret_cast<unsigned*>(&b);
+    o.z = *reinterpret_cast<unsigned*>(&c); o.w = *reinterpret_cast<unsigned*>(&e);
+    *reinterpret_cast<uint4*>(p) = o;
+  }
+};
+
+template <>
+struct Chunk<float, false> {
+  static constexpr int N = 1;
+  using Raw = float;
+  __device__ static __forceinline__ Raw zero() { return 0.f; }
+  __device__ static __forceinline__ Raw load(const float* p) { return __ldg(p); }
+  __device__ static __forceinline__ void unpack(const Raw& r, float (&f)[N]) { f[0] = r; }
+  __device__ static __forceinline__ void store(float* p, const float (&f)[N]) { *p = f[0]; }
+};
+
+template <>
+struct Chunk<__nv_bfloat16, false> {
+  static constexpr int N = 1;
+  using Raw = unsigned short;
+  __device__ static __forceinline__ Raw zero() { return 0; }
+  __device__ static __forceinline__ Raw load(const __nv_bfloat16* p) {
+    return __ldg(reinterpret_cast<const unsigned short*>(p));
+  }
+  __device__ static __forceinline__ void unpack(const Raw& r, float (&f)[N]) {
+    f[0] = __uint_as_float(static_cast<unsigned>(r) << 16);
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&f)[N]) {
+    *p = __float2bfloat16_rn(f[0]);
+  }
+};
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+  if constexpr (G == 32) {
+    return 0xffffffffu;
+  } else {
+    return ((1u << G) - 1u) << (lane & ~(G - 1));
+  }
+}
+
+__device__ __forceinline__ float leaky(float s, float slope) { return s > 0.f ? s : s * slope; }
+
+// Sum `val` over the lanes that own the same head.  lph = lanes per head inside the group
+// (>= G means the whole group is one head).  All lanes of the group call this together.
+template <int G>
+__device__ __forceinline__ float head_reduce(float val, unsigned gmask, int lph, int gl) {
+  if (lph >= G) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) val += __shfl_xor_sync(gmask, val, o, G);
+    return val;
+  }
+  if ((lph & (lph - 1)) == 0) {
+    for (int o = lph >> 1; o > 0; o >>= 1) val += __shfl_xor_sync(gmask, val, o, G);
+    return val;
+  }
+  const int myhead = gl / lph;
+  float s = 0.f;
+  for (int k = 0; k < G; ++k) {
+    const float o = __shfl_sync(gmask, val, k, G);
+    if (k / lph == myhead) s += o;
+  }
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AllDeepSets: segmented sum / mean
+// ---------------------------------------------------------------------------------------------
+// Accumulate rows [first, end) of one segment, `stride` slots between successive batches of G.
+template <typename T, bool VECTOR, int G, bool WEIGHTED>
+__device__ __forceinline__ void accumulate_rows(const T* __restrict__ x, const int* __restrict__ col,
+                                                const float* __restrict__ w,
+                                                const float* __restrict__ sscale, int first, int end,
+                                                int stride, int d, int feat, bool active, int gl,
+                                                unsigned gmask,
+                                                float (&acc)[Chunk<T, VECTOR>::N]) {
+  using CH = Chunk<T, VECTOR>;
+  constexpr int N = CH::N;
+  constexpr int U = G < kUnroll ? G : kUnroll;
+  for (int base = first; base < end; base += stride) {
+    const int n = min(G, end - base);
+    int myidx = 0;
+    float myw = 1.f;
+    if (gl < n) {
+      myidx = __ldg(col + base + gl);
+      if (WEIGHTED) {
+        if (w != nullptr) myw = __ldg(w + base + gl);
+        if (sscale != nullptr) myw *= __ldg(sscale + myidx);
+      }
+    }
+#pragma unroll 1
+    for (int u = 0; u < n; u += U) {
+      typename CH::Raw raw[U];
+      float wk[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int idx = __shfl_sync(gmask, myidx, u + k, G);
+        if (WEIGHTED) wk[k] = __shfl_sync(gmask, myw, u + k, G);
+        raw[k] = CH::zero();
+        if (u + k < n && active) raw[k] = CH::load(x + (size_t)idx * (size_t)d + feat);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        float f[N];
+        CH::unpack(raw[k], f);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          // mul then add, each rounded: the reference materialises norm*x_j before the scatter
+          acc[i] = WEIGHTED ? __fadd_rn(acc[i], __fmul_rn(wk[k], f[i])) : __fadd_rn(acc[i], f[i]);
+        }
+      }
+    }
+  }
+}
+
+template <typename T, bool VECTOR, int G, bool WEIGHTED>
+__global__ void __launch_bounds__(kThreads)
+segreduce_group_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
+                       const int* __restrict__ col, const float* __restrict__ w,
+                       const float* __restrict__ sscale, long long n_tgt, int d, int mean,
+                       int skip_over, T* __restrict__ out) {
+  using CH = Chunk<T, VECTOR>;
+  constexpr int N = CH::N;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const unsigned gmask = group_mask<G>(lane);
+  const long long seg = ((long long)blockIdx.x * kThreads + threadIdx.x) / G;
+  if (seg >= n_tgt) return;
+  const int feat = (blockIdx.y * 32 + gl) * N;
+  const bool active = feat < d;
+  const int beg = __ldg(rowptr + seg), end = __ldg(rowptr + seg + 1);
+  if (end - beg > skip_over) return;
+  float acc[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) acc[i] = 0.f;
+  accumulate_rows<T, VECTOR, G, WEIGHTED>(x, col, w, sscale, beg, end, G, d, feat, active, gl, gmask, acc);
+  if (mean) {
+    const float cnt = (float)max(end - beg, 1);
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = __fdiv_rn(acc[i], cnt);
+  }
+  if (active) CH::store(out + (size_t)seg * (size_t)d + feat, acc);
+}
+
+template <typename T, bool VECTOR, int G, bool WEIGHTED>
+__global__ void __launch_bounds__(kThreads)
+segreduce_cta_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
+                     const int* __restrict__ col, const float* __restrict__ w,
+                     const float* __restrict__ sscale, const int* __restrict__ long_ids, int d,
+                     int mean, T* __restrict__ out) {
+  using CH = Chunk<T, VECTOR>;
+  constexpr int N = CH::N;
+  constexpr int NG = kThreads / G;
+  __shared__ float red[kThreads * N];
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const int grp = threadIdx.x / G;
+  const unsigned gmask = group_mask<G>(lane);
+  const long long seg = long_ids[blockIdx.x];
+  const int feat = (blockIdx.y * 32 + gl) * N;
+  const bool active = feat < d;
+  const int beg = __ldg(rowptr + seg), end = __ldg(rowptr + seg + 1);
+  float acc[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) acc[i] = 0.f;
+  accumulate_rows<T, VECTOR, G, WEIGHTED>(x, col, w, sscale, beg + grp * G, end, NG * G, d, feat, active,
+                                          gl, gmask, acc);
+#pragma unroll
+  for (int i = 0; i < N; ++i) red[threadIdx.x * N + i] = acc[i];
+  __syncthreads();
+  if (grp == 0) {
+    for (int g = 1; g < NG; ++g) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[i] += red[(g * G + gl) * N + i];
+    }
+    if (mean) {
+      const float cnt = (float)max(end - beg, 1);
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[i] = __fdiv_rn(acc[i], cnt);
+    }
+    if (active) CH::store(out + (size_t)seg * (size_t)d + feat, acc);
+  }
+}
+
+// grad_w[k] = tgt_scale[t] * <x[col[k]], grad_out[t]>; one warp per segment (LearnMask only).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+segreduce_bwd_w_kernel(const T* __restrict__ x, const T* __restrict__ go,
+                       const int* __restrict__ rowptr, const int* __restrict__ col,
+                       const float* __restrict__ tscale, long long n_tgt, int d,
+                       float* __restrict__ gw) {
+  const int lane = threadIdx.x & 31;
+  const long long seg = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  if (seg >= n_tgt) return;
+  const int beg = __ldg(rowptr + seg), end = __ldg(rowptr + seg + 1);
+  const float sc = tscale != nullptr ? __ldg(tscale + seg) : 1.f;
+  const T* grow = go + (size_t)seg * (size_t)d;
+  for (int k = beg; k < end; ++k) {
+    const T* xrow = x + (size_t)__ldg(col + k) * (size_t)d;
+    float s = 0.f;
+    for (int f = lane; f < d; f += 32) s += (float)xrow[f] * (float)grow[f];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) gw[k] = s * sc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AllSetTransformer: PMA forward (online segment softmax fused with the weighted row sum)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool VECTOR, int G>
+__device__ __forceinline__ void pma_accumulate(const T* __restrict__ v, const float* __restrict__ score,
+                                               const int* __restrict__ col, int first, int end,
+                                               int stride, int d, int H, int h, float slope, int feat,
+                                               bool active, int gl, unsigned gmask, float& m, float& l,
+                                               float (&acc)[Chunk<T, VECTOR>::N]) {
+  using CH = Chunk<T, VECTOR>;
+  constexpr int N = CH::N;
+  constexpr int U = G < kUnroll ? G : kUnroll;
+  for (int base = first; base < end; base += stride) {
+    const int n = min(G, end - base);
+    int myidx = 0;
+    if (gl < n) myidx = __ldg(col + base + gl);
+#pragma unroll 1
+    for (int u = 0; u < n; u += U) {
+      typename CH::Raw raw[U];
+      float a[U];
+      float bm = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int idx = __shfl_sync(gmask, myidx, u + k, G);
+        raw[k] = CH::zero();
+        a[k] = -INFINITY;
+        if (u + k < n && active) {
+          a[k] = __ldg(score + (size_t)idx * (size_t)H + h);
+          raw[k] = CH::load(v + (size_t)idx * (size_t)d + feat);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        a[k] = leaky(a[k], slope);   // leaky(-inf) stays -inf (slope > 0)
+        bm = fmaxf(bm, a[k]);
+      }
+      const float m_new = fmaxf(m, bm);
+      const float c = (m == -INFINITY) ? 0.f : expf(m - m_new);
+      l *= c;
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[i] *= c;
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const float p = (a[k] == -INFINITY) ? 0.f : expf(a[k] - m_new);
+        l += p;
+        float f[N];
+        CH::unpack(raw[k], f);
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] = fmaf(p, f[i], acc[i]);
+      }
+      m = m_new;
+    }
+  }
+}
+
+template <typename T, bool VECTOR, int N>
+__device__ __forceinline__ void pma_finish(float m, float l, float (&acc)[N], const float* __restrict__ seed,
+                                           int feat, int C, int h, bool active, long long seg, int d,
+                                           int H, T* __restrict__ out, float* __restrict__ stats) {
+  using CH = Chunk<T, VECTOR>;
+  if (!active) return;
+  const float denom = l + 1e-16f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) acc[i] = acc[i] / denom + __ldg(seed + feat + i);
+  CH::store(out + (size_t)seg * (size_t)d + feat, acc);
+  if (stats != nullptr && feat == h * C) {
+    stats[((size_t)seg * H + h) * 2 + 0] = m;
+    stats[((size_t)seg * H + h) * 2 + 1] = denom;
+  }
+}
+
+template <typename T, bool VECTOR, int G>
+__global__ void __launch_bounds__(kThreads)
+pma_fwd_group_kernel(const T* __restrict__ v, const float* __restrict__ score,
+                     const float* __restrict__ seed, const int* __restrict__ rowptr,
+                     const int* __restrict__ col, long long n_tgt, int H, int C, float slope,
+                     int skip_over, T* __restrict__ out, float* __restrict__ stats) {
+  using CH = Chunk<T, VECTOR>;
+  constexpr int N = CH::N;
+  const int d = H * C;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const unsigned gmask = group_mask<G>(lane);
+  const long long seg = ((long long)blockIdx.x * kThreads + threadIdx.x) / G;
+  if (seg >= n_tgt) return;
+  const int feat = (blockIdx.y * 32 + gl) * N;
+  const bool active = feat < d;
+  const int h = active ? feat / C : 0;
+  const int beg = __ldg(rowptr + seg), end = __ldg(rowptr + seg + 1);
+  if (end - beg > skip_over) return;
+  float m = -INFINITY, l = 0.f;
+  float acc[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) acc[i] = 0.f;
+  pma_accumulate<T, VECTOR, G>(v, score, col, beg, end, G, d, H, h, slope, feat, active, gl, gmask, m, l, acc);
+  pma_finish<T, VECTOR, N>(m, l, acc, seed, feat, C, h, active, seg, d, H, out, stats);
+}
+
+template <typename T, bool VECTOR, int G>
+__global__ void __launch_bounds__(kThreads)
+pma_fwd_cta_kernel(const T* __restrict__ v, const float* __restrict__ score,
+                   const float* __restrict__ seed, const int* __restrict__ rowptr,
+                   const int* __restrict__ col, const int* __restrict__ long_ids, int H, int C,
+                   float slope, T* __restrict__ out, float* __restrict__ stats) {
+  using CH = Chunk<T, VECTOR>;
+  constexpr int N = CH::N;
+  constexpr int NG = kThreads / G;
+  __shared__ float red[kThreads * N];
+  __shared__ float red_m[kThreads];
+  __shared__ float red_l[kThreads];
+  const int d = H * C;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const int grp = threadIdx.x / G;
+  const unsigned gmask = group_mask<G>(lane);
+  const long long seg = long_ids[blockIdx.x];
+  const int feat = (blockIdx.y * 32 + gl) * N;
+  const bool active = feat < d;
+  const int h = active ? feat / C : 0;
+  const int beg = __ldg(rowptr + seg), end = __ldg(rowptr + seg + 1);
+  float m = -INFINITY, l = 0.f;
+  float acc[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) acc[i] = 0.f;
+  pma_accumulate<T, VECTOR, G>(v, score, col, beg + grp * G, end, NG * G, d, H, h, slope, feat, active, gl,
+                               gmask, m, l, acc);
+  red_m[threadIdx.x] = m;
+  red_l[threadIdx.x] = l;
+#pragma unroll
+  for (int i = 0; i < N; ++i) red[threadIdx.x * N + i] = acc[i];
+  __syncthreads();
+  if (grp == 0) {
+    float mt = m;
+    for (int g = 1; g < NG; ++g) mt = fmaxf(mt, red_m[g * G + gl]);
+    float lt = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.f;
+    for (int g = 0; g < NG; ++g) {
+      const float mg = red_m[g * G + gl];
+      const float c = (mg == -INFINITY) ? 0.f : expf(mg - mt);
+      lt += red_l[g * G + gl] * c;
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[i] = fmaf(red[(g * G + gl) * N + i], c, acc[i]);
+    }
+    pma_finish<T, VECTOR, N>(mt, lt, acc, seed, feat, C, h, active, seg, d, H, out, stats);
+  }
+}
+
+// alpha[k,h] in CSR order; one warp per segment (only when attention weights are requested)
+__global__ void __launch_bounds__(kThreads)
+pma_alpha_kernel(const float* __restrict__ score, const float* __restrict__ stats,
+                 const int* __restrict__ rowptr, const int* __restrict__ col, long long n_tgt, int H,
+                 float slope, float* __restrict__ alpha) {
+  const int lane = threadIdx.x & 31;
+  const long long seg = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  if (seg >= n_tgt) return;
+  const int beg = __ldg(rowptr + seg), end = __ldg(rowptr + seg + 1);
+  const long long total = (long long)(end - beg) * H;
+  for (long long i = lane; i < total; i += 32) {
+    const int k = beg + (int)(i / H), h = (int)(i % H);
+    const float a = leaky(__ldg(score + (size_t)__ldg(col + k) * H + h), slope);
+    const float m = stats[((size_t)seg * H + h) * 2], den = stats[((size_t)seg * H + h) * 2 + 1];
+    alpha[(size_t)k * H + h] = expf(a - m) / den;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-row per-head dot: out[r,h] = sum_c a[r,h,c] * (b[r,h,c] - sub[h,c])
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool VECTOR, int G>
+__global__ void __launch_bounds__(kThreads)
+rowdot_group_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ sub,
+                    long long n_rows, int H, int C, float* __restrict__ out) {
+  using CH = Chunk<T, VECTOR>;
+  constexpr int N = CH::N;
+  const int d = H * C;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const unsigned gmask = group_mask<G>(lane);
+  const long long row = ((long long)blockIdx.x * kThreads + threadIdx.x) / G;
+  if (row >= n_rows) return;
+  const int feat = gl * N;
+  const bool active = feat < d;
+  float s = 0.f;
+  if (active) {
+    float fa[N], fb[N];
+    CH::unpack(CH::load(a + (size_t)row * d + feat), fa);
+    CH::unpack(CH::load(b + (size_t)row * d + feat), fb);
+#pragma unroll
+    for (int i = 0; i < N; ++i) s = fmaf(fa[i], sub != nullptr ? fb[i] - __ldg(sub + feat + i) : fb[i], s);
+  }
+  const int lph = C / N;
+  s = head_reduce<G>(s, gmask, lph, gl);
+  if (active && feat % C == 0) out[(size_t)row * H + feat / C] = s;
+}
+
+// generic fallback: one thread per (row, head)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+rowdot_thread_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ sub,
+                     long long n_rows, int H, int C, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n_rows * H) return;
+  const int h = (int)(i % H);
+  const size_t off = (size_t)(i / H) * H * C + (size_t)h * C;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float bv = (float)b[off + c] - (sub != nullptr ? sub[h * C + c] : 0.f);
+    s = fmaf((float)a[off + c], bv, s);
+  }
+  out[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PMA backward over the transposed CSR (segments = source rows)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool VECTOR, int G>
+__device__ __forceinline__ void pma_bwd_accumulate(const T* __restrict__ go, const float* __restrict__ stats,
+                                                   const float* __restrict__ D, const int* __restrict__ col,
+                                                   int first, int end, int stride, int d, int H, int h,
+                                                   float a_s, int feat, bool active, int gl, unsigned gmask,
+                                                   float& sD, float (&gv)[Chunk<T, VECTOR>::N]) {
+  using CH = Chunk<T, VECTOR>;
+  constexpr int N = CH::N;
+  constexpr int U = G < kUnroll ? G : kUnroll;
+  for (int base = first; base < end; base += stride) {
+    const int n = min(G, end - base);
+    int myidx = 0;
+    if (gl < n) myidx = __ldg(col + base + gl);
+#pragma unroll 1
+    for (int u = 0; u < n; u += U) {
+      typename CH::Raw raw[U];
+      float2 st[U];
+      float dd[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int idx = __shfl_sync(gmask, myidx, u + k, G);
+        raw[k] = CH::zero();
+        st[k] = make_float2(INFINITY, 1.f);   // alpha = exp(-inf) = 0 for empty slots
+        dd[k] = 0.f;
+        if (u + k < n && active) {
+          st[k] = __ldg(reinterpret_cast<const float2*>(stats) + (size_t)idx * H + h);
+          dd[k] = __ldg(D + (size_t)idx * H + h);
+          raw[k] = CH::load(go + (size_t)idx * (size_t)d + feat);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const float alpha = expf(a_s - st[k].x) / st[k].y;
+        sD = fmaf(alpha, dd[k], sD);
+        float f[N];
+        CH::unpack(raw[k], f);
+#pragma unroll
+        for (int i = 0; i < N; ++i) gv[i] = fmaf(alpha, f[i], gv[i]);
+      }
+    }
+  }
+}
+
+// FUSED: the whole row fits one slab, so <grad_v, v> is reduced in-register and grad_score is final.
+// Otherwise grad_score receives S = sum_k alpha_k D[t_k,h] and pma_score_finish_kernel completes it.
+template <typename T, bool VECTOR, int G, bool FUSED>
+__global__ void __launch_bounds__(kThreads)
+pma_bwd_group_kernel(const T* __restrict__ go, const T* __restrict__ v, const float* __restrict__ score,
+                     const float* __restrict__ stats, const float* __restrict__ D,
+                     const int* __restrict__ rowptr, const int* __restrict__ col, long long n_src, int H,
+                     int C, float slope, int skip_over, T* __restrict__ gvout, float* __restrict__ gscore) {
+  using CH = Chunk<T, VECTOR>;
+  constexpr int N = CH::N;
+  const int d = H * C;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const unsigned gmask = group_mask<G>(lane);
+  const long long seg = ((long long)blockIdx.x * kThreads + threadIdx.x) / G;
+  if (seg >= n_src) return;
+  const int feat = (blockIdx.y * 32 + gl) * N;
+  const bool active = feat < d;
+  const int h = active ? feat / C : 0;
+  const int beg = __ldg(rowptr + seg), end = __ldg(rowptr + seg + 1);
+  if (end - beg > skip_over) return;
+  const float s_raw = active ? __ldg(score + (size_t)seg * H + h) : 0.f;
+  const float a_s = leaky(s_raw, slope);
+  float sD = 0.f;
+  float gv[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) gv[i] = 0.f;
+  pma_bwd_accumulate<T, VECTOR, G>(go, stats, D, col, beg, end, G, d, H, h, a_s, feat, active, gl, gmask, sD, gv);
+  if (active) CH::store(gvout + (size_t)seg * (size_t)d + feat, gv);
+  if (FUSED) {
+    float dot = 0.f;
+    if (active) {
+      float fv[N];
+      CH::unpack(CH::load(v + (size_t)seg * (size_t)d + feat), fv);
+#pragma unroll
+      for (int i = 0; i < N; ++i) dot = fmaf(gv[i], fv[i], dot);
+    }
+    dot = head_reduce<G>(dot, gmask, C / N, gl);
+    if (active && feat % C == 0) gscore[(size_t)seg * H + h] = (s_raw > 0.f ? 1.f : slope) * (dot - sD);
+  } else {
+    if (active && feat % C == 0) gscore[(size_t)seg * H + h] = sD;
+  }
+}
+
+template <typename T, bool VECTOR, int G, bool FUSED>
+__global__ void __launch_bounds__(kThreads)
+pma_bwd_cta_kernel(const T* __restrict__ go, const T* __restrict__ v, const float* __restrict__ score,
+                   const float* __restrict__ stats, const float* __restrict__ D,
+                   const int* __restrict__ rowptr, const int* __restrict__ col,
+                   const int* __restrict__ long_ids, int H, int C, float slope, T* __restrict__ gvout,
+                   float* __restrict__ gscore) {
+  using CH = Chunk<T, VECTOR>;
+  constexpr int N = CH::N;
+  constexpr int NG = kThreads / G;
+  __shared__ float red[kThreads * N];
+  __shared__ float red_s[kThreads];
+  const int d = H * C;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const int grp = threadIdx.x / G;
+  const unsigned gmask = group_mask<G>(lane);
+  const long long seg = long_ids[blockIdx.x];
+  const int feat = (blockIdx.y * 32 + gl) * N;
+  const bool active = feat < d;
+  const int h = active ? feat / C : 0;
+  const int beg = __ldg(rowptr + seg), end = __ldg(rowptr + seg + 1);
+  const float s_raw = active ? __ldg(score + (size_t)seg * H + h) : 0.f;
+  const float a_s = leaky(s_raw, slope);
+  float sD = 0.f;
+  float gv[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) gv[i] = 0.f;
+  pma_bwd_accumulate<T, VECTOR, G>(go, stats, D, col, beg + grp * G, end, NG * G, d, H, h, a_s, feat, active,
+                                   gl, gmask, sD, gv);
+  red_s[threadIdx.x] = sD;
+#pragma unroll
+  for (int i = 0; i < N; ++i) red[threadIdx.x * N + i] = gv[i];
+  __syncthreads();
+  if (grp == 0) {   // G >= 32 or a whole number of groups per warp: warp 0 (or part of it) is uniform here
+    for (int g = 1; g < NG; ++g) {
+      sD += red_s[g * G + gl];
+#pragma unroll
+      for (int i = 0; i < N; ++i) gv[i] += red[(g * G + gl) * N + i];
+    }
+    if (active) CH::store(gvout + (size_t)seg * (size_t)d + feat, gv);
+    if (FUSED) {
+      float dot = 0.f;
+      if (active) {
+        float fv[N];
+        CH::unpack(CH::load(v + (size_t)seg * (size_t)d + feat), fv);
+#pragma unroll
+        for (int i = 0; i < N; ++i) dot = fmaf(gv[i], fv[i], dot);
+      }
+      dot = head_reduce<G>(dot, gmask, C / N, gl);
+      if (active && feat % C == 0) gscore[(size_t)seg * H + h] = (s_raw > 0.f ? 1.f : slope) * (dot - sD);
+    } else {
+      if (active && feat % C == 0) gscore[(size_t)seg * H + h] = sD;
+    }
+  }
+}
+
+// multi-slab rows: grad_score[s,h] = leaky'(score) * (<grad_v[s,h,:], v[s,h,:]> - S[s,h])
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pma_score_finish_kernel(const T* __restrict__ gv, const T* __restrict__ v, const float* __restrict__ score,
+                        long long n_src, int H, int C, float slope, float* __restrict__ gscore) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n_src * H) return;
+  const size_t off = (size_t)(i / H) * H * C + (size_t)(i % H) * C;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s = fmaf((float)gv[off + c], (float)v[off + c], s);
+  gscore[i] = (score[i] > 0.f ? 1.f : slope) * (s - gscore[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR construction
+// ---------------------------------------------------------------------------------------------
+__global__ void csr_keys_kernel(const long long* __restrict__ tgt, long long nnz, int* __restrict__ keys,
+                                int* __restrict__ pos) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnz) {
+    keys[i] = (int)tgt[i];
+    pos[i] = (int)i;
+  }
+}
+
+// rowptr[k] = first sorted slot whose key >= k; col[i] = src[perm[i]]
+__global__ void csr_fill_kernel(const int* __restrict__ keys_sorted, const int* __restrict__ perm,
+                                const long long* __restrict__ src, long long nnz, long long n_tgt,
+                                int* __restrict__ rowptr, int* __restrict__ col) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nnz) return;
+  if (i < nnz) col[i] = (int)src[perm[i]];
+  const long long lo = (i == 0) ? 0 : (long long)keys_sorted[i - 1] + 1;
+  const long long hi = (i == nnz) ? n_tgt : (long long)keys_sorted[i];
+  for (long long k = lo; k <= hi && k <= n_tgt; ++k) rowptr[k] = (int)i;
+}
+
+struct LongSegment {
+  const int* rowptr;
+  int threshold;
+  __host__ __device__ bool operator()(int r) const { return rowptr[r + 1] - rowptr[r] > threshold; }
+};
+
+int bits_for(long long n) {
+  int b = 1;
+  while (b < 31 && (1LL << b) < n) ++b;
+  return b;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+struct Shape {
+  bool vector;   // 16-byte chunk path
+  int G;         // lanes per group
+  int slabs;     // gridDim.y
+};
+
+Shape plan(int d, int elem_bytes, const void* p0, const void* p1, const void* p2 = nullptr) {
+  Shape s;
+  const int per = 16 / elem_bytes;
+  const uintptr_t bits = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2;
+  s.vector = (d % per == 0) && (bits % 16 == 0);
+  const int nch = s.vector ? d / per : d;
+  int g = 1;
+  while (g < 32 && g < nch) g <<= 1;
+  s.G = g;
+  s.slabs = (nch + 31) / 32;
+  return s;
+}
+
+unsigned blocks_for(long long units, int G) {
+  const long long per = kThreads / G;
+  return (unsigned)((units + per - 1) / per);
+}
+
+#define ALLSET_DISPATCH_G(G_, ...)                 \
+  switch (G_) {                                    \
+    case 1: { constexpr int G = 1; __VA_ARGS__; break; }   \
+    case 2: { constexpr int G = 2; __VA_ARGS__; break; }   \
+    case 4: { constexpr int G = 4; __VA_ARGS__; break; }   \
+    case 8: { constexpr int G = 8; __VA_ARGS__; break; }   \
+    case 16: { constexpr int G = 16; __VA_ARGS__; break; } \
+    default: { constexpr int G = 32; __VA_ARGS__; break; } \
+  }
+
+template <typename T, bool VECTOR, bool WEIGHTED>
+void launch_segreduce(const Shape& sh, const T* x, const int* rowptr, const int* col, const float* w,
+                      const float* sscale, long long n_tgt, int d, int mean, const int* long_ids,
+                      int n_long, int long_threshold, T* out, cudaStream_t st) {
+  const int skip = n_long > 0 ? long_threshold : INT32_MAX;
+  ALLSET_DISPATCH_G(sh.G, {
+    dim3 grid(blocks_for(n_tgt, G), sh.slabs);
+    segreduce_group_kernel<T, VECTOR, G, WEIGHTED><<<grid, kThreads, 0, st>>>(x, rowptr, col, w, sscale, n_tgt,
+                                                                           d, mean, skip, out);
+    if (n_long > 0) {
+      dim3 lgrid(n_long, sh.slabs);
+      segreduce_cta_kernel<T, VECTOR, G, WEIGHTED><<<lgrid, kThreads, 0, st>>>(x, rowptr, col, w, sscale,
+                                                                            long_ids, d, mean, out);
+    }
+  });
+}
+
+template <typename T>
+void segreduce_typed(const Shape& sh, const void* x, const int* rowptr, const int* col, const float* w,
+                     const float* sscale, long long n_tgt, int d, int mean, const int* long_ids, int n_long,
+                     int long_threshold, void* out, cudaStream_t st) {
+  const bool weighted = (w != nullptr) || (sscale != nullptr);
+  const T* xi = static_cast<const T*>(x);
+  T* oi = static_cast<T*>(out);
+  if (sh.vector) {
+    if (weighted) launch_segreduce<T, true, true>(sh, xi, rowptr, col, w, sscale, n_tgt, d, mean, long_ids, n_long, long_threshold, oi, st);
+    else launch_segreduce<T, true, false>(sh, xi, rowptr, col, w, sscale, n_tgt, d, mean, long_ids, n_long, long_threshold, oi, st);
+  } else {
+    if (weighted) launch_segreduce<T, false, true>(sh, xi, rowptr, col, w, sscale, n_tgt, d, mean, long_ids, n_long, long_threshold, oi, st);
+    else launch_segreduce<T, false, false>(sh, xi, rowptr, col, w, sscale, n_tgt, d, mean, long_ids, n_long, long_threshold, oi, st);
+  }
+}
+
+template <typename T, bool VECTOR>
+void launch_pma_fwd(const Shape& sh, const T* v, const float* score, const float* seed, const int* rowptr,
+                    const int* col, long long n_tgt, int H, int C, float slope, const int* long_ids, int n_long,
+                    int long_threshold, T* out, float* stats, cudaStream_t st) {
+  const int skip = n_long > 0 ? long_threshold : INT32_MAX;
+  ALLSET_DISPATCH_G(sh.G, {
+    dim3 grid(blocks_for(n_tgt, G), sh.slabs);
+    pma_fwd_group_kernel<T, VECTOR, G><<<grid, kThreads, 0, st>>>(v, score, seed, rowptr, col, n_tgt, H, C, slope,
+                                                                 skip, out, stats);
+    if (n_long > 0) {
+      dim3 lgrid(n_long, sh.slabs);
+      pma_fwd_cta_kernel<T, VECTOR, G><<<lgrid, kThreads, 0, st>>>(v, score, seed, rowptr, col, long_ids, H, C,
+                                                                  slope, out, stats);
+    }
+  });
+}
+
+template <typename T, bool VECTOR, bool FUSED>
+void launch_pma_bwd(const Shape& sh, const T* go, const T* v, const float* score, const float* stats,
+                    const float* D, const int* rowptr, const int* col, long long n_src, int H, int C, float slope,
+                    const int* long_ids, int n_long, int long_threshold, T* gv, float* gscore, cudaStream_t st) {
+  const int skip = n_long > 0 ? long_threshold : INT32_MAX;
+  ALLSET_DISPATCH_G(sh.G, {
+    dim3 grid(blocks_for(n_src, G), sh.slabs);
+    pma_bwd_group_kernel<T, VECTOR, G, FUSED><<<grid, kThreads, 0, st>>>(go, v, score, stats, D, rowptr, col, n_src,
+                                                                        H, C, slope, skip, gv, gscore);
+    if (n_long > 0) {
+      dim3 lgrid(n_long, sh.slabs);
+      pma_bwd_cta_kernel<T, VECTOR, G, FUSED><<<lgrid, kThreads, 0, st>>>(go, v, score, stats, D, rowptr, col,
+                                                                         long_ids, H, C, slope, gv, gscore);
+    }
+  });
+  if (!FUSED) {
+    const long long total = n_src * H;
+    pma_score_finish_kernel<T><<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+        gv, v, score, n_src, H, C, slope, gscore);
+  }
+}
+
+template <typename T>
+void pma_bwd_typed(const Shape& sh, bool fused, const void* go, const void* v, const float* score,
+                   const float* stats, const float* D, const int* rowptr, const int* col, long long n_src, int H,
+                   int C, float slope, const int* long_ids, int n_long, int long_threshold, void* gv,
+                   float* gscore, cudaStream_t st) {
+  const T* g = static_cast<const T*>(go);
+  const T* vv = static_cast<const T*>(v);
+  T* o = static_cast<T*>(gv);
+  if (sh.vector) {
+    if (fused) launch_pma_bwd<T, true, true>(sh, g, vv, score, stats, D, rowptr, col, n_src, H, C, slope, long_ids, n_long, long_threshold, o, gscore, st);
+    else launch_pma_bwd<T, true, false>(sh, g, vv, score, stats, D, rowptr, col, n_src, H, C, slope, long_ids, n_long, long_threshold, o, gscore, st);
+  } else {
+    if (fused) launch_pma_bwd<T, false, true>(sh, g, vv, score, stats, D, rowptr, col, n_src, H, C, slope, long_ids, n_long, long_threshold, o, gscore, st);
+    else launch_pma_bwd<T, false, false>(sh, g, vv, score, stats, D, rowptr, col, n_src, H, C, slope, long_ids, n_long, long_threshold, o, gscore, st);
+  }
+}
+
+bool bad_dtype(int dtype) { return dtype != ALLSET_F32 && dtype != ALLSET_BF16; }
+int elem_bytes(int dtype) { return dtype == ALLSET_F32 ? 4 : 2; }
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int allset_version(void) { return ALLSET_ABI_VERSION; }
+
+const char* allset_last_error(void) { return g_err; }
+
+size_t allset_csr_workspace_bytes(int64_t nnz, int64_t n_tgt) {
+  if (nnz < 0 || n_tgt < 0 || nnz >= INT32_MAX || n_tgt >= INT32_MAX) return 0;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr,
+                                  (int*)nullptr, (int)nnz, 0, bits_for(n_tgt));
+  const size_t arr = align_up((size_t)nnz * sizeof(int), 256);
+  return 3 * arr + align_up(cub_bytes, 256) + 256;
+}
+
+int allset_csr_from_coo(const int64_t* tgt, const int64_t* src, int64_t nnz, int64_t n_tgt, int32_t* rowptr,
+                        int32_t* col, int32_t* perm, void* workspace, size_t workspace_bytes, void* stream) {
+  if (nnz < 0 || n_tgt < 0) return fail(ALLSET_EINVAL, "csr_from_coo: negative size");
+  if (nnz >= INT32_MAX || n_tgt >= INT32_MAX)
+    return fail(ALLSET_ERANGE, "csr_from_coo: nnz=%lld / n_tgt=%lld do not fit int32", (long long)nnz,
+                (long long)n_tgt);
+  if (rowptr == nullptr || (nnz > 0 && (tgt == nullptr || src == nullptr || col == nullptr || perm == nullptr)))
+    return fail(ALLSET_EINVAL, "csr_from_coo: null pointer");
+  const size_t need = allset_csr_workspace_bytes(nnz, n_tgt);
+  if (workspace_bytes < need || (workspace == nullptr && need > 0))
+    return fail(ALLSET_EWORKSPACE, "csr_from_coo: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t arr = align_up((size_t)nnz * sizeof(int), 256);
+  char* ws = static_cast<char*>(workspace);
+  int* keys = reinterpret_cast<int*>(ws);
+  int* keys_sorted = reinterpret_cast<int*>(ws + arr);
+  int* pos = reinterpret_cast<int*>(ws + 2 * arr);
+  void* cub_ws = ws + 3 * arr;
+  size_t cub_bytes = workspace_bytes - 3 * arr;
+  const unsigned blocks = (unsigned)((nnz + 1 + 255) / 256);
+  if (nnz > 0) {
+    csr_keys_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(tgt), nnz, keys, pos);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys, keys_sorted, pos, perm, (int)nnz, 0,
+                                                    bits_for(n_tgt), st);
+    if (e != cudaSuccess) return fail(ALLSET_ECUDA, "csr_from_coo: radix sort: %s", cudaGetErrorString(e));
+  }
+  csr_fill_kernel<<<blocks, 256, 0, st>>>(keys_sorted, perm, reinterpret_cast<const long long*>(src), nnz, n_tgt,
+                                          rowptr, col);
+  return check_launch("csr_from_coo");
+}
+
+size_t allset_long_segments_workspace_bytes(int64_t n_tgt) {
+  if (n_tgt < 0 || n_tgt >= INT32_MAX) return 0;
+  size_t bytes = 0;
+  cub::CountingInputIterator<int> it(0);
+  LongSegment pred{nullptr, 0};
+  cub::DeviceSelect::If(nullptr, bytes, it, (int*)nullptr, (int*)nullptr, (int)n_tgt, pred);
+  return align_up(bytes, 256) + 256;
+}
+
+int allset_long_segments(const int32_t* rowptr, int64_t n_tgt, int32_t threshold, int32_t* long_ids,
+                         int32_t* n_long, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_tgt < 0 || n_tgt >= INT32_MAX) return fail(ALLSET_ERANGE, "long_segments: n_tgt out of range");
+  if (rowptr == nullptr || n_long == nullptr || (n_tgt > 0 && long_ids == nullptr))
+    return fail(ALLSET_EINVAL, "long_segments: null pointer");
+  const size_t need = allset_long_segments_workspace_bytes(n_tgt);
+  if (workspace_bytes < need || workspace == nullptr)
+    return fail(ALLSET_EWORKSPACE, "long_segments: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cub::CountingInputIterator<int> it(0);
+  LongSegment pred{rowptr, threshold};
+  size_t bytes = workspace_bytes;
+  cudaError_t e = cub::DeviceSelect::If(workspace, bytes, it, long_ids, n_long, (int)n_tgt, pred, st);
+  if (e != cudaSuccess) return fail(ALLSET_ECUDA, "long_segments: %s", cudaGetErrorString(e));
+  return check_launch("long_segments");
+}
+
+int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d, const int32_t* rowptr,
+                         const int32_t* col, const float* w, const float* src_scale, int64_t n_tgt, int op,
+                         const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out,
+                         void* stream) {
+  if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "segreduce_fwd: unknown dtype %d", dtype);
+  if (op != ALLSET_SUM && op != ALLSET_MEAN) return fail(ALLSET_EINVAL, "segreduce_fwd: unknown op %d", op);
+  if (d <= 0 || n_tgt < 0 || n_src < 0 || n_long < 0) return fail(ALLSET_EINVAL, "segreduce_fwd: bad size");
+  if (n_tgt >= INT32_MAX || n_src >= INT32_MAX) return fail(ALLSET_ERANGE, "segreduce_fwd: rows do not fit int32");
+  if (n_tgt == 0) return ALLSET_OK;
+  if (rowptr == nullptr || out == nullptr || (n_long > 0 && long_ids == nullptr))
+    return fail(ALLSET_EINVAL, "segreduce_fwd: null pointer");
+  if (x == nullptr || col == nullptr) {
+    // legal only for an incidence list without entries; rowptr is then all zero and nothing is read
+    if (n_src != 0) return fail(ALLSET_EINVAL, "segreduce_fwd: null x/col with n_src > 0");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Shape sh = plan(d, elem_bytes(dtype), x, out);
+  if (dtype == ALLSET_F32)
+    segreduce_typed<float>(sh, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, long_ids, n_long,
+                           long_threshold, out, st);
+  else
+    segreduce_typed<__nv_bfloat16>(sh, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, long_ids, n_long,
+                                   long_threshold, out, st);
+  return check_launch("segreduce_fwd");
+}
+
+int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32_t d, const int32_t* rowptr,
+                           const int32_t* col, const float* tgt_scale, int64_t n_tgt, float* grad_w,
+                           void* stream) {
+  if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "segreduce_bwd_w: unknown dtype %d", dtype);
+  if (d <= 0 || n_tgt < 0) return fail(ALLSET_EINVAL, "segreduce_bwd_w: bad size");
+  if (n_tgt == 0) return ALLSET_OK;
+  if (x == nullptr || grad_out == nullptr || rowptr == nullptr || col == nullptr || grad_w == nullptr)
+    return fail(ALLSET_EINVAL, "segreduce_bwd_w: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = blocks_for(n_tgt, 32);
+  if (dtype == ALLSET_F32)
+    segreduce_bwd_w_kernel<float><<<blocks, kThreads, 0, st>>>(static_cast<const float*>(x),
+                                                              static_cast<const float*>(grad_out), rowptr, col,
+                                                              tgt_scale, n_tgt, d, grad_w);
+  else
+    segreduce_bwd_w_kernel<__nv_bfloat16><<<blocks, kThreads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(grad_out), rowptr, col, tgt_scale,
+        n_tgt, d, grad_w);
+  return check_launch("segreduce_bwd_w");
+}
+
+int allset_pma_fwd(const void* v, const float* score, const float* seed, int dtype, int32_t H, int32_t C,
+                   float slope, const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
+                   const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out, float* stats,
+                   void* stream) {
+  if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "pma_fwd: unknown dtype %d", dtype);
+  if (H <= 0 || C <= 0 || n_tgt < 0 || n_long < 0) return fail(ALLSET_EINVAL, "pma_fwd: bad size");
+  if (!(slope > 0.f)) return fail(ALLSET_EINVAL, "pma_fwd: negative_slope must be > 0");
+  if (n_tgt >= INT32_MAX) return fail(ALLSET_ERANGE, "pma_fwd: rows do not fit int32");
+  if (n_tgt == 0) return ALLSET_OK;
+  if (seed == nullptr || rowptr == nullptr || out == nullptr || (n_long > 0 && long_ids == nullptr))
+    return fail(ALLSET_EINVAL, "pma_fwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = H * C;
+  Shape sh = plan(d, elem_bytes(dtype), v, out);
+  if (sh.vector && C % (16 / elem_bytes(dtype)) != 0) {   // a 16-byte chunk would straddle two heads
+    sh.vector = false;
+    sh.G = 1;
+    while (sh.G < 32 && sh.G < d) sh.G <<= 1;
+    sh.slabs = (d + 31) / 32;
+  }
+  if (dtype == ALLSET_F32) {
+    const float* vi = static_cast<const float*>(v);
+    float* oi = static_cast<float*>(out);
+    if (sh.vector) launch_pma_fwd<float, true>(sh, vi, score, seed, rowptr, col, n_tgt, H, C, slope, long_ids, n_long, long_threshold, oi, stats, st);
+    else launch_pma_fwd<float, false>(sh, vi, score, seed, rowptr, col, n_tgt, H, C, slope, long_ids, n_long, long_threshold, oi, stats, st);
+  } else {
+    const __nv_bfloat16* vi = static_cast<const __nv_bfloat16*>(v);
+    __nv_bfloat16* oi = static_cast<__nv_bfloat16*>(out);
+    if (sh.vector) launch_pma_fwd<__nv_bfloat16, true>(sh, vi, score, seed, rowptr, col, n_tgt, H, C, slope, long_ids, n_long, long_threshold, oi, stats, st);
+    else launch_pma_fwd<__nv_bfloat16, false>(sh, vi, score, seed, rowptr, col, n_tgt, H, C, slope, long_ids, n_long, long_threshold, oi, stats, st);
+  }
+  return check_launch("pma_fwd");
+}
+
+int allset_pma_alpha(const float* score, const float* stats, int32_t H, float slope, const int32_t* rowptr,
+                     const int32_t* col, int64_t n_tgt, float* alpha, void* stream) {
+  if (H <= 0 || n_tgt < 0) return fail(ALLSET_EINVAL, "pma_alpha: bad size");
+  if (n_tgt == 0) return ALLSET_OK;
+  if (stats == nullptr || rowptr == nullptr) return fail(ALLSET_EINVAL, "pma_alpha: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pma_alpha_kernel<<<blocks_for(n_tgt, 32), kThreads, 0, st>>>(score, stats, rowptr, col, n_tgt, H, slope, alpha);
+  return check_launch("pma_alpha");
+}
+
+int allset_rowdot_heads(const void* a, const void* b, const float* sub, int dtype, int64_t n_rows, int32_t H,
+                        int32_t C, float* out, void* stream) {
+  if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "rowdot_heads: unknown dtype %d", dtype);
+  if (H <= 0 || C <= 0 || n_rows < 0) return fail(ALLSET_EINVAL, "rowdot_heads: bad size");
+  if (n_rows == 0) return ALLSET_OK;
+  if (a == nullptr || b == nullptr || out == nullptr) return fail(ALLSET_EINVAL, "rowdot_heads: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = H * C;
+  const Shape sh = plan(d, elem_bytes(dtype), a, b);
+  const bool grouped = sh.vector && sh.slabs == 1 && C % (16 / elem_bytes(dtype)) == 0;
+  if (grouped) {
+    ALLSET_DISPATCH_G(sh.G, {
+      if (dtype == ALLSET_F32)
+        rowdot_group_kernel<float, true, G><<<blocks_for(n_rows, G), kThreads, 0, st>>>(
+            static_cast<const float*>(a), static_cast<const float*>(b), sub, n_rows, H, C, out);
+      else
+        rowdot_group_kernel<__nv_bfloat16, true, G><<<blocks_for(n_rows, G), kThreads, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), sub, n_rows, H, C, out);
+    });
+  } else {
+    const long long total = n_rows * H;
+    const unsigned blocks = (unsigned)((total + kThreads - 1) / kThreads);
+    if (dtype == ALLSET_F32)
+      rowdot_thread_kernel<float><<<blocks, kThreads, 0, st>>>(static_cast<const float*>(a),
+                                                              static_cast<const float*>(b), sub, n_rows, H, C, out);
+    else
+      rowdot_thread_kernel<__nv_bfloat16><<<blocks, kThreads, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), sub, n_rows, H, C, out);
+  }
+  return check_launch("rowdot_heads");
+}
+
+int allset_pma_bwd(const void* grad_out, const void* v, const float* score, const float* stats, const float* D,
+                   int dtype, int32_t H, int32_t C, float slope, const int32_t* rowptrT, const int32_t* colT,
+                   int64_t n_src, const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* grad_v,
+                   float* grad_score, void* stream) {
+  if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "pma_bwd: unknown dtype %d", dtype);
+  if (H <= 0 || C <= 0 || n_src < 0 || n_long < 0) return fail(ALLSET_EINVAL, "pma_bwd: bad size");
+  if (n_src >= INT32_MAX) return fail(ALLSET_ERANGE, "pma_bwd: rows do not fit int32");
+  if (n_src == 0) return ALLSET_OK;
+  if (v == nullptr || score == nullptr || rowptrT == nullptr || grad_v == nullptr || grad_score == nullptr ||
+      (n_long > 0 && long_ids == nullptr))
+    return fail(ALLSET_EINVAL, "pma_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = H * C;
+  Shape sh = plan(d, elem_bytes(dtype), grad_out, v, grad_v);
+  if (sh.vector && C % (16 / elem_bytes(dtype)) != 0) {
+    sh.vector = false;
+    sh.G = 1;
+    while (sh.G < 32 && sh.G < d) sh.G <<= 1;
+    sh.slabs = (d + 31) / 32;
+  }
+  const bool fused = sh.slabs == 1;
+  if (dtype == ALLSET_F32)
+    pma_bwd_typed<float>(sh, fused, grad_out, v, score, stats, D, rowptrT, colT, n_src, H, C, slope, long_ids, n_long,
+                         long_threshold, grad_v, grad_score, st);
+  else
+    pma_bwd_typed<__nv_bfloat16>(sh, fused, grad_out, v, score, stats, D, rowptrT, colT, n_src, H, C, slope, long_ids,
+                                 n_long, long_threshold, grad_v, grad_score, st);
+  return check_launch("pma_bwd");
+}
+
+}  // extern "C"

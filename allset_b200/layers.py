@@ -1,0 +1,192 @@
+"""B200-native `MLP`, `PMA` and `HalfNLHconv` with the reference's constructor signatures, attribute names,
+initialisation and `state_dict` keys (reference src/layers.py: PMA :42-199, MLP :496-579, HalfNLHconv :582-656),
+so reference checkpoints load and reference `train.py` drives them unchanged.
+
+What differs is below the module API: instead of PyG `MessagePassing.propagate` + torch_scatter (gather ->
+materialised [nnz, d] messages -> atomic scatter, ~20 launches for PMA) each half layer issues ONE fused CUDA
+kernel over a cached CSR (allset_b200/ops.py).  The dense parts (Linear / LayerNorm) stay on cuBLAS / ATen.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+from torch.nn import Linear, Parameter
+
+from . import ops
+from .graph import Incidence, incidence_of
+
+__all__ = ['MLP', 'PMA', 'HalfNLHconv', 'glorot', 'zeros']
+
+
+def glorot(tensor):
+    """Uniform(-a, a), a = sqrt(6 / (fan_in + fan_out)) over the last two dims (reference src/layers.py:31-34)."""
+    if tensor is not None:
+        bound = math.sqrt(6.0 / (tensor.size(-2) + tensor.size(-1)))
+        tensor.data.uniform_(-bound, bound)
+
+
+def zeros(tensor):
+    if tensor is not None:
+        tensor.data.fill_(0)
+
+
+class MLP(nn.Module):
+    """norm0 -> [Linear -> ReLU -> norm -> dropout] x (num_layers-1) -> Linear   (reference src/layers.py:496-579).
+
+    `normalizations[0]` is a real norm only when `InputNorm`; Normalization 'None' makes every norm Identity."""
+
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers,
+                 dropout=.5, Normalization='bn', InputNorm=False):
+        super().__init__()
+        assert Normalization in ['bn', 'ln', 'None']
+        self.InputNorm = InputNorm
+        self.dropout = dropout
+        make = {'bn': nn.BatchNorm1d, 'ln': nn.LayerNorm, 'None': lambda width: nn.Identity()}[Normalization]
+        # the reference's ctor builds in->hid, (num_layers-2) x hid->hid, hid->out for every num_layers != 1
+        # (so num_layers <= 0 still yields two Linears)
+        depth = 1 if num_layers == 1 else max(num_layers, 2)
+        widths = [in_channels] + [hidden_channels] * (depth - 1) + [out_channels]
+        self.lins = nn.ModuleList(nn.Linear(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        norms = [make(in_channels) if (InputNorm and Normalization != 'None') else nn.Identity()]
+        norms += [make(hidden_channels) for _ in range(depth - 1)]
+        self.normalizations = nn.ModuleList(norms)
+
+    def reset_parameters(self):
+        for lin in self.lins:
+            lin.reset_parameters()
+        for norm in self.normalizations:
+            if not isinstance(norm, nn.Identity):
+                norm.reset_parameters()
+
+    def forward(self, x):
+        x = self.normalizations[0](x)
+        for i, lin in enumerate(self.lins[:-1]):
+            x = F.relu(lin(x), inplace=True)
+            x = self.normalizations[i + 1](x)
+            x = F.dropout(x, p=self.dropout, training=self.training)
+        return self.lins[-1](x)
+
+
+def _resolve(edge_index, n_src: int) -> Incidence:
+    if isinstance(edge_index, Incidence):
+        return edge_index
+    if not isinstance(edge_index, Tensor):
+        raise TypeError('edge_index must be a [2, nnz] tensor or an allset_b200.Incidence')
+    if not edge_index.is_cuda:
+        raise RuntimeError('allset_b200 layers run on CUDA only (no CPU fallback): edge_index is on %s'
+                           % edge_index.device)
+    return incidence_of(edge_index, n_src)
+
+
+class PMA(nn.Module):
+    """Pooling by multi-head attention with ONE learned seed per head (reference src/layers.py:42-199).
+
+    forward: K = lin_K(x), V = lin_V(x), score = <K_h, att_r_h> per source row; per target segment a softmax of
+    leaky_relu(score) weights the V rows; + seed; LN0; LN1(out + relu(rFF(out))).  The segment part (everything
+    the reference does inside `propagate`, plus the seed residual) is one CUDA kernel."""
+
+    def __init__(self, in_channels, hid_dim, out_channels, num_layers, heads=1, concat=True,
+                 negative_slope=0.2, dropout=0.0, bias=False, **kwargs):
+        super().__init__()
+        self.in_channels = in_channels
+        self.hidden = hid_dim // heads
+        self.out_channels = out_channels
+        self.heads = heads
+        self.concat = concat
+        self.negative_slope = negative_slope
+        self.dropout = 0.          # the reference hard-wires attention dropout off (src/layers.py:63)
+        self.aggr = 'add'
+        self.lin_K = Linear(in_channels, self.heads * self.hidden)
+        self.lin_V = Linear(in_channels, self.heads * self.hidden)
+        self.att_r = Parameter(torch.Tensor(1, heads, self.hidden))      # seed
+        self.rFF = MLP(in_channels=self.heads * self.hidden, hidden_channels=self.heads * self.hidden,
+                       out_channels=out_channels, num_layers=num_layers, dropout=.0, Normalization='None')
+        self.ln0 = nn.LayerNorm(self.heads * self.hidden)
+        self.ln1 = nn.LayerNorm(self.heads * self.hidden)
+        self.register_parameter('bias', None)
+        self.agg_dtype: Optional[torch.dtype] = None   # storage dtype of the gathered rows (None = x.dtype)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot(self.lin_K.weight)       # biases keep their construction-time values, as in the reference
+        glorot(self.lin_V.weight)
+        self.rFF.reset_parameters()
+        self.ln0.reset_parameters()
+        self.ln1.reset_parameters()
+        nn.init.xavier_uniform_(self.att_r)
+
+    def forward(self, x, edge_index, size=None, return_attention_weights=None):
+        assert x.dim() == 2, 'Static graphs not supported in `GATConv`.'
+        H, C = self.heads, self.hidden
+        inc = _resolve(edge_index, x.size(0))
+        x_K = self.lin_K(x).view(-1, H, C)
+        x_V = self.lin_V(x)
+        score = (x_K * self.att_r).sum(dim=-1)                          # [n_src, H], no 1/sqrt(C)
+        v = x_V if self.agg_dtype is None else x_V.to(self.agg_dtype)
+        want_alpha = isinstance(return_attention_weights, bool)
+        out, alpha = ops.pma_aggregate(v, score, self.att_r, inc, H, self.negative_slope, return_alpha=want_alpha)
+        out = out.to(x_V.dtype)                                          # [n_tgt, H*C], seed already added
+        out = self.ln0(out)
+        out = self.ln1(out + F.relu(self.rFF(out)))
+        if want_alpha:
+            return out, (edge_index, alpha)
+        return out
+
+    def __repr__(self):
+        return '{}({}, {}, heads={})'.format(self.__class__.__name__, self.in_channels, self.out_channels, self.heads)
+
+
+class HalfNLHconv(nn.Module):
+    """One half layer, V->E or E->V (reference src/layers.py:582-656).
+
+    attention=True : PMA.   attention=False : relu(f_enc(x)) -> dropout -> segmented sum/mean of norm_e * x[src_e]
+    -> relu(f_dec(.)).  `edge_index` row 0 = source rows, row 1 = target rows; output rows = max(target)+1."""
+
+    def __init__(self, in_dim, hid_dim, out_dim, num_layers, dropout, Normalization='bn', InputNorm=False,
+                 heads=1, attention=True):
+        super().__init__()
+        self.attention = attention
+        self.dropout = dropout
+        self.agg_dtype: Optional[torch.dtype] = None
+        if self.attention:
+            self.prop = PMA(in_dim, hid_dim, out_dim, num_layers, heads=heads)
+        elif num_layers > 0:
+            self.f_enc = MLP(in_dim, hid_dim, hid_dim, num_layers, dropout, Normalization, InputNorm)
+            self.f_dec = MLP(hid_dim, hid_dim, out_dim, num_layers, dropout, Normalization, InputNorm)
+        else:
+            self.f_enc = nn.Identity()
+            self.f_dec = nn.Identity()
+
+    def reset_parameters(self):
+        if self.attention:
+            self.prop.reset_parameters()
+        else:
+            for f in (self.f_enc, self.f_dec):
+                if not isinstance(f, nn.Identity):
+                    f.reset_parameters()
+
+    def set_agg_dtype(self, dtype: Optional[torch.dtype]):
+        self.agg_dtype = dtype
+        if self.attention:
+            self.prop.agg_dtype = dtype
+
+    def forward(self, x, edge_index, norm, aggr='add'):
+        if self.attention:
+            return self.prop(x, edge_index)              # norm and aggr are ignored, as in the reference
+        if aggr is None:
+            raise ValueError('aggr was not passed!')
+        x = F.relu(self.f_enc(x))
+        x = F.dropout(x, p=self.dropout, training=self.training)
+        inc = _resolve(edge_index, x.size(0))
+        weight = None
+        if norm is not None and not (not norm.requires_grad and inc.weights_all_one(norm)):
+            weight = norm
+        xs = x if self.agg_dtype is None else x.to(self.agg_dtype)
+        x = ops.segment_reduce(xs, inc, weight, aggr).to(x.dtype)
+        x = F.relu(self.f_dec(x))
+        return x

@@ -1,0 +1,143 @@
+"""`SetGNN` with the reference's module API (reference src/models.py:295-484): same constructor (`args`
+namespace, optional `norm`), attribute / `state_dict` names (V2EConvs, E2VConvs, bnV2Es, bnE2Vs, classifier, MLP,
+GPRweights, Importance), `reset_parameters()` and `forward(data) -> [N, num_classes]`, including its side effect
+of zero-basing `data.edge_index[1]` in place.  Drop-in for reference src/train.py:28-42,437,462,478.
+
+Below the API the V->E / E->V aggregations run as fused sm_100a kernels over an `Incidence` that is sorted once per
+graph and cached on `data.edge_index` (the reference re-derives sizes with a device->host sync in every scatter).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import Linear, Parameter
+
+from .graph import Incidence, attach
+from .layers import MLP, HalfNLHconv
+
+__all__ = ['SetGNN']
+
+_ATTR = '_allset_setgnn_graph'
+
+
+class SetGNN(nn.Module):
+    def __init__(self, args, norm=None, agg_dtype: Optional[torch.dtype] = None):
+        """args: namespace with All_num_layers, dropout, aggregate, normalization, deepset_input_norm, GPR, LearnMask,
+        num_features, MLP_hidden, MLP_num_layers, heads, PMA, Classifier_hidden, Classifier_num_layers, num_classes
+        (reference src/train.py:221-289).  agg_dtype (extension): storage dtype of the rows the aggregation kernels
+        gather, e.g. torch.bfloat16; None keeps the module dtype (fp32 = reference numerics)."""
+        super().__init__()
+        self.All_num_layers = args.All_num_layers
+        self.dropout = args.dropout
+        self.aggr = args.aggregate
+        self.NormLayer = args.normalization
+        self.InputNorm = args.deepset_input_norm
+        self.GPR = args.GPR
+        self.LearnMask = args.LearnMask
+        self.V2EConvs = nn.ModuleList()
+        self.E2VConvs = nn.ModuleList()
+        self.bnV2Es = nn.ModuleList()      # created, reset and saved but never applied -- as in the reference
+        self.bnE2Vs = nn.ModuleList()
+
+        if self.LearnMask:
+            self.Importance = Parameter(torch.ones(norm.size()))
+
+        def classifier(in_channels):
+            return MLP(in_channels=in_channels, hidden_channels=args.Classifier_hidden, out_channels=args.num_classes,
+                       num_layers=args.Classifier_num_layers, dropout=self.dropout, Normalization=self.NormLayer,
+                       InputNorm=False)
+
+        def half(in_dim):
+            return HalfNLHconv(in_dim=in_dim, hid_dim=args.MLP_hidden, out_dim=args.MLP_hidden,
+                               num_layers=args.MLP_num_layers, dropout=self.dropout, Normalization=self.NormLayer,
+                               InputNorm=self.InputNorm, heads=args.heads, attention=args.PMA)
+
+        if self.All_num_layers == 0:
+            self.classifier = classifier(args.num_features)
+        else:
+            for i in range(self.All_num_layers):
+                self.V2EConvs.append(half(args.num_features if i == 0 else args.MLP_hidden))
+                self.bnV2Es.append(nn.BatchNorm1d(args.MLP_hidden))
+                self.E2VConvs.append(half(args.MLP_hidden))
+                self.bnE2Vs.append(nn.BatchNorm1d(args.MLP_hidden))
+            if self.GPR:
+                self.MLP = MLP(in_channels=args.num_features, hidden_channels=args.MLP_hidden,
+                               out_channels=args.MLP_hidden, num_layers=args.MLP_num_layers, dropout=self.dropout,
+                               Normalization=self.NormLayer, InputNorm=False)
+                self.GPRweights = Linear(self.All_num_layers + 1, 1, bias=False)
+            self.classifier = classifier(args.MLP_hidden)
+        self.set_agg_dtype(agg_dtype)
+
+    def set_agg_dtype(self, dtype: Optional[torch.dtype]):
+        self.agg_dtype = dtype
+        for conv in list(self.V2EConvs) + list(self.E2VConvs):
+            conv.set_agg_dtype(dtype)
+
+    def reset_parameters(self):
+        for group in (self.V2EConvs, self.E2VConvs, self.bnV2Es, self.bnE2Vs):
+            for layer in group:
+                layer.reset_parameters()
+        self.classifier.reset_parameters()
+        if self.GPR:
+            self.MLP.reset_parameters()
+            self.GPRweights.reset_parameters()
+        if self.LearnMask:
+            nn.init.ones_(self.Importance)
+
+    # ------------------------------------------------------------------------------------------------------
+    def _graph(self, edge_index: torch.Tensor, n_nodes: int):
+        """(V->E incidence, E->V incidence) for data.edge_index, built on first sight and cached on the tensor.
+
+        Reproduces reference src/models.py:453-454: hyperedge ids are zero-based IN PLACE (cidx = row1.min();
+        row1 -= cidx).  The reference repeats the subtraction every forward (a no-op after the first); here the
+        shift happens when the graph is (re)built, and later forwards reuse the cache with no device->host sync."""
+        if not edge_index.is_cuda:
+            raise RuntimeError('allset_b200.SetGNN runs on CUDA only (no CPU fallback): data.edge_index is on %s'
+                               % edge_index.device)
+        tagged = getattr(edge_index, _ATTR, None)
+        if tagged is not None and tagged[0] == edge_index._version and tagged[1] == n_nodes:
+            return tagged[2], tagged[3]
+        if edge_index.numel() > 0:
+            cidx = edge_index[1].min()
+            edge_index[1] -= cidx
+        v2e = Incidence.from_coo(edge_index[0], edge_index[1], n_src=n_nodes)          # rows out: max(he)+1
+        n_v_out = int(edge_index[0].max()) + 1 if edge_index.numel() > 0 else 0        # rows out of E->V: max(node)+1
+        e2v = v2e.reversed(n_tgt=n_v_out)
+        setattr(edge_index, _ATTR, (edge_index._version, n_nodes, v2e, e2v))
+        return v2e, e2v
+
+    def forward(self, data):
+        """data.x [N, F]; data.edge_index [2, nnz] int64 (row 0 node id, row 1 hyperedge id, any base);
+        data.norm [nnz] per-incidence weights (int64 ones by default).  Returns node logits [N, num_classes]."""
+        x, edge_index, norm = data.x, data.edge_index, data.norm
+        if self.All_num_layers == 0:
+            # only the classifier exists (src/models.py:339-346); the reference still zero-bases the hyperedge ids
+            if edge_index.numel() > 0:
+                edge_index[1] -= edge_index[1].min()
+            return self.classifier(F.dropout(x, p=0.2, training=self.training))
+        if self.LearnMask:
+            norm = self.Importance * norm
+        v2e, e2v = self._graph(edge_index, x.size(0))
+        if self.GPR:
+            xs = [F.relu(self.MLP(x))]
+            for i, _ in enumerate(self.V2EConvs):
+                x = F.relu(self.V2EConvs[i](x, v2e, norm, self.aggr))
+                x = F.dropout(x, p=self.dropout, training=self.training)
+                x = F.relu(self.E2VConvs[i](x, e2v, norm, self.aggr))
+                xs.append(x)
+                x = F.dropout(x, p=self.dropout, training=self.training)
+            x = torch.stack(xs, dim=-1)
+            x = self.GPRweights(x).squeeze()
+            x = self.classifier(x)
+        else:
+            x = F.dropout(x, p=0.2, training=self.training)     # input dropout, hard-coded in the reference
+            for i, _ in enumerate(self.V2EConvs):
+                x = F.relu(self.V2EConvs[i](x, v2e, norm, self.aggr))
+                x = F.dropout(x, p=self.dropout, training=self.training)
+                x = F.relu(self.E2VConvs[i](x, e2v, norm, self.aggr))
+                x = F.dropout(x, p=self.dropout, training=self.training)
+            x = self.classifier(x)
+        return x

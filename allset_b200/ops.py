@@ -1,0 +1,138 @@
+"""Differentiable operators over an `Incidence`: the two aggregations of the AllSet layer.
+
+    segment_reduce  == propagate of HalfNLHconv       (reference src/layers.py:633, message :638-639, aggregate :641-656)
+    pma_aggregate   == propagate of PMA + seed add    (reference src/layers.py:145-153, message :168-177, aggregate :179-194)
+
+Forward and backward are each ONE launch of a hand-written sm_100a kernel through the C ABI (allset_b200/_lib.py);
+the backward w.r.t. the gathered rows is the same gather kernel on the transposed CSR, so nothing here uses
+atomics and results are run-to-run deterministic.  No CPU path: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .graph import Incidence
+
+
+def _storage(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError('aggregation kernels store rows as float32 or bfloat16, got %s' % x.dtype)
+    return x.contiguous()
+
+
+class _SegReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, inc: Incidence, mean: bool):
+        t = inc.by_tgt
+        x = _storage(x)
+        w_csr = None
+        if weight is not None:
+            w_csr = weight.detach().float().index_select(0, t.perm64)
+        out = _lib.segreduce_fwd(x, t.rowptr, t.col, t.n_tgt, mean, w=w_csr, long_ids=t.long_ids,
+                                 long_threshold=t.long_threshold)
+        ctx.inc, ctx.mean = inc, mean
+        ctx.has_weight = weight is not None
+        ctx.weight_dtype = None if weight is None else weight.dtype
+        ctx.save_for_backward(x if (weight is not None and ctx.needs_input_grad[1]) else None,
+                              weight.detach() if weight is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        inc, mean = ctx.inc, ctx.mean
+        x, weight = ctx.saved_tensors
+        t, s = inc.by_tgt, inc.by_src
+        grad_out = _storage(grad_out)
+        grad_x = grad_w = None
+        if ctx.needs_input_grad[0]:
+            # d out[t] / d x[s] = w_e (/ count_t): the same gather-reduce over the transposed CSR
+            w_T = None if weight is None else weight.float().index_select(0, s.perm64)
+            grad_x = _lib.segreduce_fwd(grad_out, s.rowptr, s.col, s.n_tgt, False, w=w_T,
+                                        src_scale=t.inv_count if mean else None,
+                                        long_ids=s.long_ids, long_threshold=s.long_threshold)
+        if ctx.has_weight and ctx.needs_input_grad[1]:
+            gw_csr = _lib.segreduce_bwd_w(x, grad_out, t.rowptr, t.col, t.n_tgt,
+                                          tgt_scale=t.inv_count if mean else None)
+            grad_w = torch.empty_like(gw_csr)
+            grad_w.index_copy_(0, t.perm64, gw_csr)           # CSR slot k came from COO position perm[k]
+            grad_w = grad_w.to(ctx.weight_dtype)
+        return grad_x, grad_w, None, None
+
+
+def segment_reduce(x: torch.Tensor, inc: Incidence, weight: Optional[torch.Tensor] = None,
+                   reduce: str = 'sum') -> torch.Tensor:
+    """out[t] = reduce_{e: tgt(e)=t} weight[e] * x[src(e)]  with out.shape[0] == inc.n_tgt.
+
+    x [n_src, d] float32 | bfloat16 (CUDA); weight [nnz] in the caller's COO order or None (= all ones);
+    reduce in {'sum', 'add', 'mean'} (torch_scatter spellings reachable from reference src/train.py:38,245)."""
+    if reduce not in ('sum', 'add', 'mean'):
+        raise ValueError("reduce must be 'sum', 'add' or 'mean', got %r" % (reduce,))
+    if not x.is_cuda:
+        raise RuntimeError('allset_b200.segment_reduce: CUDA tensors only (no CPU fallback); got %s' % x.device)
+    if x.dim() != 2 or x.shape[0] != inc.n_src:
+        raise ValueError('x must be [n_src=%d, d], got %s' % (inc.n_src, tuple(x.shape)))
+    if weight is not None and weight.numel() != inc.nnz:
+        raise ValueError('weight must have one entry per incidence (%d), got %d' % (inc.nnz, weight.numel()))
+    return _SegReduce.apply(x, weight, inc, reduce == 'mean')
+
+
+class _PMA(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, score, seed, inc: Incidence, H: int, C: int, slope: float):
+        t = inc.by_tgt
+        v = _storage(v)
+        score = score.float().contiguous()
+        seed_f = seed.detach().float().reshape(-1).contiguous()
+        out, stats = _lib.pma_fwd(v, score, seed_f, H, C, slope, t.rowptr, t.col, t.n_tgt, want_stats=True,
+                                  long_ids=t.long_ids, long_threshold=t.long_threshold)
+        ctx.inc, ctx.H, ctx.C, ctx.slope = inc, H, C, slope
+        ctx.seed_shape, ctx.seed_dtype, ctx.score_dtype = seed.shape, seed.dtype, score.dtype
+        ctx.save_for_backward(v, score, seed_f, out, stats)
+        ctx.mark_non_differentiable(stats)
+        return out, stats
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_stats):
+        v, score, seed_f, out, stats = ctx.saved_tensors
+        inc, H, C, slope = ctx.inc, ctx.H, ctx.C, ctx.slope
+        s = inc.by_src
+        grad_out = _storage(grad_out)
+        grad_v = grad_score = grad_seed = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            # softmax backward needs D[t,h] = sum_k alpha_k <g_t, v_k> = <g_t, out_t - seed>
+            D = _lib.rowdot_heads(grad_out, out, seed_f, H, C)
+            grad_v, grad_score = _lib.pma_bwd(grad_out, v, score, stats, D, H, C, slope, s.rowptr, s.col, s.n_tgt,
+                                              long_ids=s.long_ids, long_threshold=s.long_threshold)
+        if ctx.needs_input_grad[2]:
+            grad_seed = grad_out.float().sum(dim=0).reshape(ctx.seed_shape).to(ctx.seed_dtype)
+        return grad_v, grad_score, grad_seed, None, None, None, None
+
+
+def pma_aggregate(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, inc: Incidence, heads: int,
+                  negative_slope: float = 0.2, return_alpha: bool = False
+                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Per target segment t and head h:  out[t,h,:] = sum_e softmax_t(leaky_relu(score[src(e),h])) * v[src(e),h,:] + seed[h,:]
+
+    v [n_src, H*C] (or [n_src, H, C]); score [n_src, H]; seed [1, H, C] (PMA.att_r).  Returns (out [n_tgt, H*C],
+    alpha [nnz, H] in the caller's COO order if `return_alpha` else None)."""
+    if not v.is_cuda:
+        raise RuntimeError('allset_b200.pma_aggregate: CUDA tensors only (no CPU fallback); got %s' % v.device)
+    v2 = v.reshape(v.shape[0], -1)
+    d = v2.shape[1]
+    if d % heads != 0:
+        raise ValueError('feature width %d is not divisible by heads=%d' % (d, heads))
+    C = d // heads
+    if v2.shape[0] != inc.n_src or tuple(score.shape) != (inc.n_src, heads) or seed.numel() != d:
+        raise ValueError('pma_aggregate: shape mismatch v%s score%s seed%s n_src=%d'
+                         % (tuple(v.shape), tuple(score.shape), tuple(seed.shape), inc.n_src))
+    out, stats = _PMA.apply(v2, score.float(), seed, inc, heads, C, float(negative_slope))
+    alpha = None
+    if return_alpha:
+        t = inc.by_tgt
+        a_csr = _lib.pma_alpha(score.detach().float().contiguous(), stats, heads, negative_slope, t.rowptr, t.col, t.n_tgt)
+        alpha = torch.empty_like(a_csr)
+        alpha.index_copy_(0, t.perm64, a_csr)
+    return out, alpha

@@ -1,0 +1,142 @@
+/* allset_b200.h -- C ABI of liballset_b200.so (sm_100a).
+ *
+ * The drop-in boundary for AllSet's V->E / E->V multiset-aggregation path.  The reference
+ * (jianhao2016/AllSet) has no FFI layer of its own: the path bottoms out in three third-party
+ * Python entry points.  Each function below names the reference call it replaces
+ * (paths relative to the reference tree):
+ *
+ *   torch_scatter.scatter(src, index, dim, reduce)    src/layers.py:656 (HalfNLHconv.aggregate)
+ *                                                     src/layers.py:194 (PMA.aggregate)
+ *   MessagePassing.propagate -> index_select gather   src/layers.py:633, :145
+ *   norm.view(-1,1) * x_j                             src/layers.py:638-639 (HalfNLHconv.message)
+ *   torch_geometric.utils.softmax(alpha, index, ...)  src/layers.py:168-177 (PMA.message)
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Every pointer is a DEVICE pointer owned by the caller
+ *     (PyTorch's caching allocator in the Python host); the library never allocates, frees or
+ *     retains memory.  Workspace sizes are queried first and passed in.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation, no host reads of device data.
+ *   - Return value: 0 on success, a negative ALLSET_E* code otherwise; the message is available
+ *     from allset_last_error() (thread-local).  No C++ exception crosses the boundary.
+ *   - Incidence lists are CSR by TARGET row: rowptr[n_tgt+1] (int32), col[nnz] (int32 source row
+ *     of each incidence), in the stable order of the caller's COO list, so per-segment summation
+ *     order equals the reference's CPU scatter_add_ order.
+ *   - dtype: ALLSET_F32 or ALLSET_BF16 is the STORAGE type of feature rows; accumulation is
+ *     always fp32.  Scores, weights and statistics are fp32.
+ */
+#ifndef ALLSET_B200_H_
+#define ALLSET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALLSET_ABI_VERSION 1
+
+enum { ALLSET_F32 = 0, ALLSET_BF16 = 1 };
+enum { ALLSET_SUM = 0, ALLSET_MEAN = 1 };
+enum {
+  ALLSET_OK = 0,
+  ALLSET_EINVAL = -1,   /* bad argument (null pointer, negative size, unknown enum) */
+  ALLSET_ERANGE = -2,   /* size does not fit the int32 CSR (nnz or rows >= 2^31) */
+  ALLSET_EWORKSPACE = -3, /* workspace too small */
+  ALLSET_ECUDA = -4     /* CUDA launch / runtime error (text in allset_last_error) */
+};
+
+/* ABI version of the loaded library (== ALLSET_ABI_VERSION it was built with). */
+int allset_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char* allset_last_error(void);
+
+/* --- incidence container ------------------------------------------------------------------
+ * Replaces the implicit work torch_scatter does on every call (unsorted COO index + a
+ * D2H `index.max()` to size the output, src/layers.py:656): the COO list is sorted ONCE per
+ * graph into CSR-by-target.  `perm[k]` = position in the caller's COO list of CSR slot k
+ * (needed to carry per-incidence tensors -- data.norm, SetGNN.Importance, PMA's returned
+ * alpha -- between the two orders).  Stable: equal targets keep COO order. */
+size_t allset_csr_workspace_bytes(int64_t nnz, int64_t n_tgt);
+int allset_csr_from_coo(const int64_t* tgt, const int64_t* src, int64_t nnz, int64_t n_tgt,
+                        int32_t* rowptr, int32_t* col, int32_t* perm,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Segments longer than `threshold` get a CTA each instead of a lane group.  Writes their row
+ * ids (ascending) to long_ids[capacity] and their count to *n_long (device int32). */
+size_t allset_long_segments_workspace_bytes(int64_t n_tgt);
+int allset_long_segments(const int32_t* rowptr, int64_t n_tgt, int32_t threshold,
+                         int32_t* long_ids, int32_t* n_long,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* --- AllDeepSets: gather + weight + segmented sum / mean -----------------------------------
+ * out[t, :] = reduce_{k in [rowptr[t], rowptr[t+1])} w[k] * src_scale[col[k]] * x[col[k], :]
+ * Replaces propagate -> message -> aggregate of HalfNLHconv (src/layers.py:633,638-639,641-656)
+ * i.e. index_select + norm*x_j + torch_scatter.scatter(reduce='add'|'sum'|'mean') in ONE launch.
+ *   x         [n_src, d]  feature rows (dtype)          out  [n_tgt, d] (dtype), fully written
+ *   w         [nnz] fp32 in CSR order, or NULL (= data.norm all ones, preprocessing.py:454)
+ *   src_scale [n_src] fp32 or NULL (used by the backward of 'mean': 1/max(count,1) of the row)
+ *   op        ALLSET_SUM | ALLSET_MEAN (mean divides by max(segment length, 1): torch_scatter)
+ *   long_ids / n_long / long_threshold: output of allset_long_segments (n_long may be 0, then
+ *   long_ids may be NULL).
+ * The gradient w.r.t. x is this same function on the transposed CSR. */
+int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d,
+                         const int32_t* rowptr, const int32_t* col,
+                         const float* w, const float* src_scale,
+                         int64_t n_tgt, int op,
+                         const int32_t* long_ids, int32_t n_long, int32_t long_threshold,
+                         void* out, void* stream);
+
+/* Gradient w.r.t. the per-incidence weights (SetGNN.LearnMask, src/models.py:451-452):
+ * grad_w[k] = tgt_scale[t] * <x[col[k], :], grad_out[t, :]>  for k in segment t (CSR order).
+ * tgt_scale [n_tgt] fp32 or NULL (mean: 1/max(count,1)). */
+int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32_t d,
+                           const int32_t* rowptr, const int32_t* col, const float* tgt_scale,
+                           int64_t n_tgt, float* grad_w, void* stream);
+
+/* --- AllSetTransformer: per-segment multi-head PMA -----------------------------------------
+ * One seed query per head, so per target segment t and head h:
+ *   a_k   = leaky_relu(score[col[k], h], slope)
+ *   alpha = exp(a_k - max_k a_k) / (sum_k exp(a_k - max) + 1e-16)      (PyG softmax)
+ *   out[t, h, :] = sum_k alpha_k * v[col[k], h, :] + seed[h, :]
+ * Replaces PMA.propagate/message/aggregate + the seed residual (src/layers.py:145-153,168-194):
+ * index_select x2, leaky_relu, the 6-kernel segment softmax, the weighting and the scatter-add.
+ *   v     [n_src, H*C] (dtype)     score [n_src, H] fp32     seed [H*C] fp32
+ *   out   [n_tgt, H*C] (dtype)     stats [n_tgt, H, 2] fp32 = (max, sum + 1e-16), or NULL
+ * Empty segments yield out = seed (the reference's zero row + att_r). */
+int allset_pma_fwd(const void* v, const float* score, const float* seed, int dtype,
+                   int32_t H, int32_t C, float slope,
+                   const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
+                   const int32_t* long_ids, int32_t n_long, int32_t long_threshold,
+                   void* out, float* stats, void* stream);
+
+/* Attention weights per incidence in CSR order (PMA.forward(return_attention_weights=True),
+ * src/layers.py:159-166): alpha[k, h] for k in segment t from score and stats. */
+int allset_pma_alpha(const float* score, const float* stats, int32_t H, float slope,
+                     const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
+                     float* alpha, void* stream);
+
+/* Per-row, per-head dot product  out[r, h] = sum_c a[r,h,c] * (b[r,h,c] - sub[h,c])
+ * (sub may be NULL).  Used for the softmax-backward term D = <grad_out, out - seed>. */
+int allset_rowdot_heads(const void* a, const void* b, const float* sub, int dtype,
+                        int64_t n_rows, int32_t H, int32_t C, float* out, void* stream);
+
+/* Backward of allset_pma_fwd, run over the TRANSPOSED CSR (segments = source rows s,
+ * colT[k] = target row of the incidence):
+ *   alpha_k       = exp(leaky_relu(score[s,h]) - stats[t,h,0]) / stats[t,h,1]
+ *   grad_v[s,h,:] = sum_k alpha_k * grad_out[t_k, h, :]
+ *   grad_score[s,h] = leaky_relu'(score[s,h]) * (<grad_v[s,h,:], v[s,h,:]> - sum_k alpha_k * D[t_k,h])
+ * D [n_tgt, H] from allset_rowdot_heads(grad_out, out, seed).  (grad_seed = column sums of
+ * grad_out is left to the host framework.) */
+int allset_pma_bwd(const void* grad_out, const void* v, const float* score, const float* stats,
+                   const float* D, int dtype, int32_t H, int32_t C, float slope,
+                   const int32_t* rowptrT, const int32_t* colT, int64_t n_src,
+                   const int32_t* long_ids, int32_t n_long, int32_t long_threshold,
+                   void* grad_v, float* grad_score, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALLSET_B200_H_ */
