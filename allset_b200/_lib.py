@@ -163,6 +163,8 @@ def segreduce_fwd(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tg
         out = torch.empty((n_tgt, d), dtype=x.dtype, device=x.device)
     else:
         _need(out, 'out', x.dtype)
+        if tuple(out.shape) != (n_tgt, d):
+            raise ValueError('out must be [n_tgt, d]')
     if d == 0 or n_tgt == 0:
         return out
     n_long = 0 if long_ids is None else long_ids.numel()
@@ -192,7 +194,7 @@ def segreduce_bwd_w(x: torch.Tensor, grad_out: torch.Tensor, rowptr: torch.Tenso
 # ----------------------------------------------------------------------------------------------------------
 def pma_fwd(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: int, C: int, slope: float,
             rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, want_stats: bool = True,
-            long_ids: Optional[torch.Tensor] = None, long_threshold: int = 0):
+            long_ids: Optional[torch.Tensor] = None, long_threshold: int = 0, out: Optional[torch.Tensor] = None):
     """v [n_src, H*C], score [n_src, H] f32, seed [H*C] f32 -> (out [n_tgt, H*C], stats [n_tgt, H, 2] | None)."""
     _need(v, 'v')
     _need(score, 'score', torch.float32)
@@ -202,7 +204,12 @@ def pma_fwd(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: int, C:
     if v.dim() != 2 or v.shape[1] != H * C or score.shape != (v.shape[0], H) or seed.numel() != H * C:
         raise ValueError('pma_fwd: shape mismatch v%s score%s seed%s H=%d C=%d'
                          % (tuple(v.shape), tuple(score.shape), tuple(seed.shape), H, C))
-    out = torch.empty((n_tgt, H * C), dtype=v.dtype, device=v.device)
+    if out is None:
+        out = torch.empty((n_tgt, H * C), dtype=v.dtype, device=v.device)
+    else:
+        _need(out, 'out', v.dtype)
+        if tuple(out.shape) != (n_tgt, H * C):
+            raise ValueError('out must be [n_tgt, H*C]')
     stats = torch.empty((n_tgt, H, 2), dtype=torch.float32, device=v.device) if want_stats else None
     if n_tgt == 0:
         return out, stats

@@ -1,0 +1,177 @@
+"""Multi-GPU partition of the V->E / E->V path: one process per GPU, target segments split into contiguous ranges.
+
+The reference is single-device; this is the B200 scale-out named by BASELINE.json:north_star.
+Each direction shards naturally BY TARGET SEGMENT: hyperedges are independent units of V->E given
+read access to the replicated vertex rows, vertices are independent units of E->V given the hyperedge rows.  So
+
+    V->E : rank r reduces hyperedges [e_lo, e_hi) from the replicated X_v           (no collective inside)
+    exch : all-gather of X_e rows   (small: |E| d s bytes)
+    E->V : rank r reduces vertices   [v_lo, v_hi) from the gathered X_e             (no collective inside)
+    exch : all-gather of the updated X_v rows -- THE all-gather of north_star, |V| d s bytes over NVLink
+
+Ranges are contiguous in the CSR-by-target, so a shard is a slice of (rowptr, col): no re-sort, no copy of `col`.
+Boundaries balance the number of INCIDENCES (bytes gathered), not the number of rows, which matters for the
+power-law config.  Pure index arithmetic: works on any device (the gloo tests run it on CPU tensors).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+
+
+def balanced_ranges(rowptr: torch.Tensor, parts: int, row_weight: int = 0) -> List[Tuple[int, int]]:
+    """Split rows [0, n) of a CSR into `parts` contiguous ranges of (nearly) equal cost, where the cost of row t is
+    (rowptr[t+1] - rowptr[t]) + row_weight  -- incidences gathered plus `row_weight` incidence-equivalents for
+    writing the output row.  Returns [(lo, hi)] * parts covering [0, n) in order; ranges may be empty."""
+    n = int(rowptr.numel()) - 1
+    if parts <= 0:
+        raise ValueError('parts must be positive')
+    if n <= 0:
+        return [(0, 0)] * parts
+    cost = rowptr.to(torch.int64) + row_weight * torch.arange(n + 1, device=rowptr.device, dtype=torch.int64)
+    total = int(cost[-1])
+    targets = torch.tensor([(total * k) // parts for k in range(1, parts)], device=rowptr.device, dtype=torch.int64)
+    cuts = torch.searchsorted(cost, targets, right=False).clamp_(max=n).tolist() if parts > 1 else []
+    bounds = [0] + cuts + [n]
+    for i in range(1, len(bounds)):                        # monotone (searchsorted already is; guard the clamp)
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return [(bounds[i], bounds[i + 1]) for i in range(parts)]
+
+
+def slice_csr(rowptr: torch.Tensor, col: torch.Tensor, lo: int, hi: int) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """Rows [lo, hi) of a CSR as (rowptr_local [hi-lo+1] starting at 0, col_local view, first incidence offset)."""
+    if not (0 <= lo <= hi <= rowptr.numel() - 1):
+        raise ValueError('bad range [%d, %d) for %d rows' % (lo, hi, rowptr.numel() - 1))
+    p0, p1 = int(rowptr[lo]), int(rowptr[hi])
+    return (rowptr[lo:hi + 1] - rowptr[lo]).contiguous(), col[p0:p1], p0
+
+
+def row_views(full: torch.Tensor, ranges: Sequence[Tuple[int, int]]) -> List[torch.Tensor]:
+    """Views of the replicated [rows, d] buffer, one per rank's range -- the receive list of the uneven all-gather."""
+    return [full[lo:hi] for lo, hi in ranges]
+
+
+def allgather_rows(full: torch.Tensor, ranges: Sequence[Tuple[int, int]], rank: int, group=None, async_op=False):
+    """All-gather row ranges IN PLACE into the replicated buffer: rank r owns full[ranges[r]] (already written by its
+    kernel) and receives every other range.  Equal-sized ranges take the single-kernel all_gather_into_tensor path;
+    ragged ones one broadcast per non-empty range (what NCCL's uneven all-gather decomposes into; also the only
+    form gloo accepts).  With async_op the returned handle(s) must be waited on by the caller."""
+    import torch.distributed as dist
+    sizes = {hi - lo for lo, hi in ranges}
+    mine = full[ranges[rank][0]:ranges[rank][1]]
+    contiguous_cover = all(ranges[i][1] == ranges[i + 1][0] for i in range(len(ranges) - 1))
+    if len(sizes) == 1 and contiguous_cover and ranges[0][0] == 0:
+        rows = ranges[-1][1]
+        return dist.all_gather_into_tensor(full[:rows], mine, group=group, async_op=async_op)
+    works = []
+    for r, view in enumerate(row_views(full, ranges)):
+        if view.shape[0] > 0:
+            src = r if group is None else dist.get_global_rank(group, r)
+            works.append(dist.broadcast(view, src=src, group=group, async_op=async_op))
+    return works if async_op else None
+
+
+def equal_ranges(n: int, parts: int) -> List[Tuple[int, int]]:
+    """ceil(n / parts) rows per rank (the last ranges may be shorter or empty)."""
+    per = (n + parts - 1) // parts
+    return [(min(n, r * per), min(n, (r + 1) * per)) for r in range(parts)]
+
+
+def choose_ranges(rowptr: torch.Tensor, parts: int, row_weight: int = 0, tolerance: float = 0.02
+                  ) -> List[Tuple[int, int]]:
+    """Equal row counts when that is also cost-balanced to within `tolerance` (random graphs: law of large numbers;
+    it keeps the exchange on the one-kernel all_gather_into_tensor path), cost-balanced ragged ranges otherwise."""
+    n = int(rowptr.numel()) - 1
+    if parts == 1 or n == 0:
+        return [(0, n)] + [(n, n)] * (parts - 1)
+    if n % parts == 0:
+        eq = equal_ranges(n, parts)
+        b = torch.tensor([lo for lo, _ in eq] + [n], device=rowptr.device)
+        cost = (rowptr[b].to(torch.int64) + row_weight * b.to(torch.int64)).tolist()
+        per = [cost[i + 1] - cost[i] for i in range(parts)]
+        mean = sum(per) / parts
+        if mean == 0 or max(per) <= (1.0 + tolerance) * mean:
+            return eq
+    return balanced_ranges(rowptr, parts, row_weight)
+
+
+class ShardedIncidence(object):
+    """One rank's share of a hypergraph: the hyperedge range it reduces in V->E and the vertex range it reduces in
+    E->V, as slices of the two CSRs of a full `Incidence` (every rank holds the full index; features are what is
+    big).  world == 1 degenerates to the single-GPU path with no collective.
+
+        sh = ShardedIncidence(v2e, rank, world)
+        sh.v2e_reduce(x_v, x_e)      # writes rows [e_lo, e_hi) of the replicated x_e
+        sh.gather_e(x_e)             # all-gather of hyperedge rows
+        sh.e2v_reduce(x_e, x_v_new)  # writes rows [v_lo, v_hi)
+        sh.gather_v(x_v_new)         # all-gather of the updated vertex rows (north_star's one big collective)
+    """
+
+    def __init__(self, v2e, rank: int = 0, world: int = 1, group=None, row_weight: int = 1):
+        from .graph import Csr
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.n_v, self.n_e, self.nnz = v2e.n_src, v2e.n_tgt, v2e.nnz
+        t, s = v2e.by_tgt, v2e.by_src
+        self.e_ranges = choose_ranges(t.rowptr, world, row_weight)
+        self.v_ranges = choose_ranges(s.rowptr, world, row_weight)
+        self.e_lo, self.e_hi = self.e_ranges[rank]
+        self.v_lo, self.v_hi = self.v_ranges[rank]
+        if world == 1:
+            self.e_csr, self.v_csr = t, s
+        else:
+            rp, col, p0 = slice_csr(t.rowptr, t.col, self.e_lo, self.e_hi)
+            self.e_csr = Csr(rp, col, t.perm[p0:p0 + col.numel()], self.e_hi - self.e_lo, self.n_v)
+            rp, col, p0 = slice_csr(s.rowptr, s.col, self.v_lo, self.v_hi)
+            self.v_csr = Csr(rp, col, s.perm[p0:p0 + col.numel()], self.v_hi - self.v_lo, self.n_e)
+
+    # -- AllDeepSets ------------------------------------------------------------------------------------------
+    def _reduce(self, csr, x_src, out_full, lo, hi, mean):
+        from . import _lib
+        _lib.segreduce_fwd(x_src, csr.rowptr, csr.col, csr.n_tgt, mean, long_ids=csr.long_ids,
+                           long_threshold=csr.long_threshold, out=out_full[lo:hi])
+
+    def v2e_reduce(self, x_v, x_e_full, mean: bool = False):
+        self._reduce(self.e_csr, x_v, x_e_full, self.e_lo, self.e_hi, mean)
+
+    def e2v_reduce(self, x_e, x_v_full, mean: bool = False):
+        self._reduce(self.v_csr, x_e, x_v_full, self.v_lo, self.v_hi, mean)
+
+    # -- AllSetTransformer ------------------------------------------------------------------------------------
+    def _pma(self, csr, v, score, seed, heads, out_full, lo, hi, slope):
+        from . import _lib
+        _lib.pma_fwd(v, score, seed, heads, v.shape[1] // heads, slope, csr.rowptr, csr.col, csr.n_tgt,
+                     want_stats=False, long_ids=csr.long_ids, long_threshold=csr.long_threshold, out=out_full[lo:hi])
+
+    def v2e_pma(self, v_v, score_v, seed, heads, out_e_full, slope: float = 0.2):
+        self._pma(self.e_csr, v_v, score_v, seed, heads, out_e_full, self.e_lo, self.e_hi, slope)
+
+    def e2v_pma(self, v_e, score_e, seed, heads, out_v_full, slope: float = 0.2):
+        self._pma(self.v_csr, v_e, score_e, seed, heads, out_v_full, self.v_lo, self.v_hi, slope)
+
+    # -- exchanges --------------------------------------------------------------------------------------------
+    def gather_e(self, x_e_full):
+        if self.world > 1:
+            allgather_rows(x_e_full, self.e_ranges, self.rank, self.group)
+
+    def gather_v(self, x_v_full):
+        if self.world > 1:
+            allgather_rows(x_v_full, self.v_ranges, self.rank, self.group)
+
+    def launches_per_pair(self) -> int:
+        """Kernels of this library launched by one V->E + E->V pair on this rank."""
+        return 2 + (self.e_csr.long_ids is not None) + (self.v_csr.long_ids is not None)
+
+    def layer_pair_sum(self, x_v, x_e_full, x_v_new_full, mean: bool = False):
+        self.v2e_reduce(x_v, x_e_full, mean)
+        self.gather_e(x_e_full)
+        self.e2v_reduce(x_e_full, x_v_new_full, mean)
+        self.gather_v(x_v_new_full)
+        return x_v_new_full
+
+    def layer_pair_pma(self, v_v, score_v, score_e, seed, heads, out_e_full, out_v_full):
+        self.v2e_pma(v_v, score_v, seed, heads, out_e_full)
+        self.gather_e(out_e_full)
+        self.e2v_pma(out_e_full, score_e, seed, heads, out_v_full)
+        self.gather_v(out_v_full)
+        return out_v_full

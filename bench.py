@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- hyperedge-aggregations/sec (V->E + E->V) at d=128 on B200, with HBM roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over the named graph: the V->E segmented reduce over every hyperedge followed
+by the E->V segmented reduce over every vertex (AllDeepSets, aggregate='add' as reference src/train.py:36-38 forces),
+d=128, bf16 rows / fp32 accumulate.  Workload = BASELINE.json configs[3]'s graph (synthetic |V|=10M, |E|=2M,
+hyperedge size 1+Poisson(29), nnz~60M, seed 1234) -- the 10M-vertex / 2M-hyperedge synthetic the north_star target
+is quoted on; it fits one B200.  With N > 1 the SAME graph is hyperedge-sharded (V->E) / vertex-sharded (E->V) over
+N ranks with an all-gather of X_e and of the updated X_v inside every step (strong scaling).
+
+JSON line (rank 0): value = |E| * K / t (device-timed, inputs resident in HBM, max over ranks); e2e = same metric
+through the public API with the vertex features starting in pinned HOST memory and the result read back to the host
+every step; roofline = the segmented-reduce kernel's algorithmic bytes / its CUDA-event duration against
+MEASURED_PEAKS.json; cpu_baseline = the reference's CPU op sequence (oracle port: index_select -> norm*x_j ->
+scatter_add_, fp32) on a bounded sample of the same graph distribution on this box's host cores.
+
+--impl reference times that CPU path alone (the reference has no GPU kernel of its own).
+Only the cpu_baseline / --impl reference legs import oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'hyperedge-aggregations/sec (V->E+E->V) at d=128'
+UNIT = 'hyperedges/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--nodes', type=int, default=10_000_000, help='|V|')
+    ap.add_argument('--hyperedges', type=int, default=2_000_000, help='|E|')
+    ap.add_argument('--mean-size', type=float, default=30.0)
+    ap.add_argument('--d', type=int, default=128)
+    ap.add_argument('--heads', type=int, default=8)
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+    ap.add_argument('--seed', type=int, default=1234)
+    ap.add_argument('--cpu-scale', type=int, default=20, help='CPU legs run on a 1/scale graph of the same distribution')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-pma', action='store_true')
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ('synthetic |V|=%s |E|=%s mean-deg=%g AllDeepSets(sum) V->E+E->V d=%d %s'
+            % (_si(a.nodes), _si(a.hyperedges), a.mean_size, a.d, a.dtype))
+
+
+def _si(n):
+    for div, suf in ((1_000_000, 'M'), (1_000, 'K')):
+        if n >= div and n % (div // 10) == 0:
+            v = n / div
+            return ('%d%s' % (v, suf)) if v == int(v) else ('%g%s' % (v, suf))
+    return str(n)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------------------------
+_REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+            0x80: 'hw_power_brake_slowdown', 0x2: 'applications_clocks_setting', 0x10: 'sync_boost'}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + clock-event reasons of one GPU through NVML every `period` seconds while running."""
+
+    def __init__(self, device_index: int, period: float = 0.01):
+        super().__init__(daemon=True)
+        self.period, self.samples, self.reasons, self.sm_max = period, [], set(), None
+        self._halt = threading.Event()
+        self.handle = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = 'GPU-' + str(torch.cuda.get_device_properties(device_index).uuid)
+                try:
+                    self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+                except Exception:
+                    self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa
+            self.error = repr(e)
+            self.handle = None
+
+    def run(self):
+        if self.handle is None:
+            return
+        nv = self.nv
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+        while not self._halt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                bits = int(get_reasons(self.handle))
+                for bit, name in _REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        out = {'sm_mhz': (statistics.median(self.samples) if self.samples else None), 'sm_max_mhz': self.sm_max,
+               'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+        if self.handle is None:
+            out['error'] = getattr(self, 'error', 'nvml unavailable')
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only code in this file that touches oracle/)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sample_graph(a):
+    import torch
+    from allset_b200 import synthetic
+    n, m = max(a.nodes // a.cpu_scale, 1000), max(a.hyperedges // a.cpu_scale, 200)
+    ei = synthetic.poisson_hypergraph(n, m, a.mean_size, seed=a.seed, device='cpu')
+    node, he = ei[0], ei[1] - n
+    x = torch.randn(n, a.d, generator=torch.Generator().manual_seed(a.seed))
+    norm = torch.ones(ei.shape[1], dtype=torch.int64)        # data.norm = ones_like(edge_index[0]) (int64), preprocessing.py:454
+    desc = ('1/%d-scale graph of the same distribution (|V|=%d |E|=%d nnz=%d, d=%d), fp32, reference op sequence '
+            'index_select -> norm*x_j -> scatter_add_ per direction' % (a.cpu_scale, n, m, ei.shape[1], a.d))
+    return n, m, node, he, x, norm, desc
+
+
+def cpu_time_pairs(a, steps, warmup, budget_s=None):
+    """Times `steps` V->E + E->V pairs of the oracle's reference op sequence; returns (hyperedges/s, cores, desc, ms/step, steps)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import allset_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n, m, node, he, x, norm, desc = cpu_sample_graph(a)
+    for _ in range(warmup):
+        O.layer_pair_sum(x, node, he, norm, 'sum')
+    done, t0 = 0, time.perf_counter()
+    for _ in range(steps):
+        O.layer_pair_sum(x, node, he, norm, 'sum')
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return m * done / dt, cores, desc, dt / done * 1e3, done
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    value, cores, desc, ms, done = cpu_time_pairs(a, a.steps, a.warmup)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': done,
+        'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(a), 'sample': desc, 'l2': 'inputs larger than L2'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import allset_b200
+    from allset_b200 import _lib, sharding, synthetic
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py --impl b200 needs a CUDA device (allset_b200 has no CPU path)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    if world != a.gpus and rank == 0:
+        sys.stderr.write('warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE\n' % (a.gpus, world))
+    _lib.lib()                                            # fail loudly here if the CUDA library is missing
+
+    dtype = torch.bfloat16 if a.dtype == 'bf16' else torch.float32
+    es = 2 if a.dtype == 'bf16' else 4
+    Nv, Me, d, H = a.nodes, a.hyperedges, a.d, a.heads
+
+    # ---- graph (resident; built once like the reference's data.to(device)) ------------------------------------
+    ei = synthetic.poisson_hypergraph(Nv, Me, a.mean_size, seed=a.seed, device=dev)
+    he = ei[1] - Nv
+    v2e = allset_b200.Incidence.from_coo(ei[0], he, n_src=Nv, n_tgt=Me)
+    nnz = v2e.nnz
+    del ei, he
+    sh = sharding.ShardedIncidence(v2e, rank, world)
+    torch.cuda.empty_cache()
+
+    x_v = synthetic.features(Nv, d, dtype, seed=a.seed, device=dev)
+    x_e = torch.empty((Me, d), dtype=dtype, device=dev)
+    x_v2 = torch.empty((Nv, d), dtype=dtype, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    # ---- device-resident timing: K steps, per-phase events inside ---------------------------------------------
+    def timed_steps(step_fn, n_phases, steps, warmup):
+        for _ in range(warmup):
+            step_fn(None)
+        barrier()
+        marks = [[ev() for _ in range(n_phases + 1)] for _ in range(steps)]
+        start, end = ev(), ev()
+        start.record()
+        for k in range(steps):
+            step_fn(marks[k])
+        end.record()
+        barrier()
+        total_ms = max_over_ranks(start.elapsed_time(end))
+        phases = [max_over_ranks(sum(m[i].elapsed_time(m[i + 1]) for m in marks) / steps) for i in range(n_phases)]
+        return total_ms, phases
+
+    def sum_step(marks):
+        if marks: marks[0].record()
+        sh.v2e_reduce(x_v, x_e)
+        if marks: marks[1].record()
+        sh.gather_e(x_e)
+        if marks: marks[2].record()
+        sh.e2v_reduce(x_e, x_v2)
+        if marks: marks[3].record()
+        sh.gather_v(x_v2)
+        if marks: marks[4].record()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, ph = timed_steps(sum_step, 4, a.steps, a.warmup)
+    ms_per_step = total_ms / a.steps
+    value = Me / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API: host-resident features in, result read back, every step -------------
+    e2e = None
+    if not a.no_e2e:
+        x_host = torch.empty((Nv, d), dtype=dtype).pin_memory()
+        x_host.copy_(x_v)
+        out_rows = sh.v_hi - sh.v_lo
+        out_host = torch.empty((out_rows, d), dtype=dtype).pin_memory()
+        x_in = torch.empty_like(x_v)
+        inc_v2e, inc_e2v = v2e, v2e.reversed()
+
+        def e2e_step(_marks):
+            x_in.copy_(x_host, non_blocking=True)                            # H2D of this step's input
+            if world == 1:
+                xe = allset_b200.segment_reduce(x_in, inc_v2e, None, 'sum')   # the call a user makes
+                xv = allset_b200.segment_reduce(xe, inc_e2v, None, 'sum')
+                out_host.copy_(xv, non_blocking=True)                        # D2H of the result
+            else:
+                sh.layer_pair_sum(x_in, x_e, x_v2)
+                out_host.copy_(x_v2[sh.v_lo:sh.v_hi], non_blocking=True)     # each rank reads back the rows it owns
+
+        e2e_steps = max(3, min(a.steps, 20))
+        e2e_ms, _ = timed_steps(e2e_step, 0, e2e_steps, 2)
+        e2e = {'value': Me / (e2e_ms / e2e_steps * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': int(Nv * d * es) * world, 'd2h_bytes_per_step': int(Nv * d * es),
+               'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
+               'api': 'allset_b200.segment_reduce(x, Incidence, None, "sum") x2' if world == 1
+                      else 'allset_b200.sharding.ShardedIncidence.layer_pair_sum'}
+        del x_host, out_host, x_in
+    clocks = sampler.stop()
+
+    # ---- AllSetTransformer (PMA, heads=H) on the same graph: reported beside the headline -----------------------
+    pma = None
+    if not a.no_pma:
+        g = torch.Generator(device=dev)
+        g.manual_seed(a.seed + 1)
+        score_v = torch.randn(Nv, H, device=dev, generator=g)
+        score_e = torch.randn(Me, H, device=dev, generator=g)
+        seed = torch.randn(H * (d // H), device=dev, generator=g)
+
+        def pma_step(marks):
+            if marks: marks[0].record()
+            sh.v2e_pma(x_v, score_v, seed, H, x_e)
+            if marks: marks[1].record()
+            sh.gather_e(x_e)
+            if marks: marks[2].record()
+            sh.e2v_pma(x_e, score_e, seed, H, x_v2)
+            if marks: marks[3].record()
+            sh.gather_v(x_v2)
+            if marks: marks[4].record()
+
+        p_ms, pph = timed_steps(pma_step, 4, a.steps, a.warmup)
+        nnz_e = int(sh.e_csr.nnz)
+        nnz_v = int(sh.v_csr.nnz)
+        b_ve = synthetic.algorithmic_bytes(nnz_e, sh.e_hi - sh.e_lo, d, es, heads=H)
+        b_ev = synthetic.algorithmic_bytes(nnz_v, sh.v_hi - sh.v_lo, d, es, heads=H)
+        pma = {'value': Me / (p_ms / a.steps * 1e-3), 'unit': UNIT, 'heads': H, 'ms_per_step': p_ms / a.steps,
+               'v2e_ms': pph[0], 'e2v_ms': pph[2], 'gather_e_ms': pph[1], 'gather_v_ms': pph[3],
+               'v2e_gbs': b_ve / (pph[0] * 1e-3) / 1e9, 'e2v_gbs': b_ev / (pph[2] * 1e-3) / 1e9}
+        del score_v, score_e
+
+    # ---- roofline of the dominant kernel (the segmented-reduce gather kernel; both directions launch it) --------
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    nnz_e, nnz_v = int(sh.e_csr.nnz), int(sh.v_csr.nnz)
+    b_ve = synthetic.algorithmic_bytes(nnz_e, sh.e_hi - sh.e_lo, d, es)
+    b_ev = synthetic.algorithmic_bytes(nnz_v, sh.v_hi - sh.v_lo, d, es)
+    t_ve, t_ge, t_ev, t_gv = ph
+    achieved = (b_ve + b_ev) / ((t_ve + t_ev) * 1e-3) / 1e9
+    roofline = {
+        'bound': 'hbm', 'kernel': 'segreduce_group_kernel<bf16,16B chunks>' if a.dtype == 'bf16' else 'segreduce_group_kernel<f32>',
+        'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+        'peak_source': peak_src,
+        'bytes_per_launch': (b_ve + b_ev) / 2, 'avg_launch_ms': (t_ve + t_ev) / 2,
+        'v2e': {'bytes': b_ve, 'ms': t_ve, 'gbs': b_ve / (t_ve * 1e-3) / 1e9, 'frac': b_ve / (t_ve * 1e-3) / 1e9 / peak},
+        'e2v': {'bytes': b_ev, 'ms': t_ev, 'gbs': b_ev / (t_ev * 1e-3) / 1e9, 'frac': b_ev / (t_ev * 1e-3) / 1e9 / peak},
+    }
+    traffic_path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if world == 1 and os.path.isfile(traffic_path):
+        try:
+            tr = json.load(open(traffic_path))
+            if tr.get('workload') == workload_name(a):
+                roofline['traffic'] = tr.get('dram_bytes_per_launch')
+                roofline['traffic_source'] = tr.get('source')
+        except Exception:
+            pass
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only) -----------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, cores, desc, ms, done = cpu_time_pairs(a, steps=8, warmup=1, budget_s=20.0)
+        cpu_baseline = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc,
+                        'ms_per_step_on_sample': ms, 'steps': done}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': a.dtype, 'data': 'synthetic',
+            'config': {'workload': workload_name(a), 'nodes': Nv, 'hyperedges': Me, 'nnz': nnz, 'd': d,
+                       'seed': a.seed, 'parallelism': 'single GPU' if world == 1 else
+                       'hyperedge-sharded V->E / vertex-sharded E->V x%d, NCCL all-gather of X_e and X_v per step' % world,
+                       'l2': 'inputs larger than L2 (X_v %.2f GB, col %.2f GB per step; no flush)'
+                             % (Nv * d * es / 1e9, nnz * 4 / 1e9)},
+            'clocks': clocks,
+            'e2e': e2e,
+            'gpu_launches': sh.launches_per_pair() * a.steps,
+            'roofline': roofline,
+            'cpu_baseline': cpu_baseline,
+            'phases_ms': {'v2e': t_ve, 'allgather_x_e': t_ge, 'e2v': t_ev, 'allgather_x_v': t_gv},
+            'incidence_visits_per_s': 2 * nnz / (ms_per_step * 1e-3),
+            'pma': pma,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == '__main__':
+    main()

@@ -214,8 +214,10 @@ def setgnn(params, x: Tensor, edge_index: Tensor, norm: Optional[Tensor], *, PMA
 
 
 def _count_layers(params) -> int:
+    # bnV2Es.i exists for every layer (models.py:357,378) even when the convs themselves hold no parameters
+    # (MLP_num_layers == 0 -> Identity f_enc / f_dec, layers.py:605-607)
     n = 0
-    while any(k.startswith('V2EConvs.%d.' % n) for k in params):
+    while any(k.startswith('V2EConvs.%d.' % n) or k.startswith('bnV2Es.%d.' % n) for k in params):
         n += 1
     return n
 

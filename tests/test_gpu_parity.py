@@ -1,0 +1,383 @@
+"""GPU parity: the CUDA path (through the C ABI, allset_b200/_lib.py -> liballset_b200.so) against
+  * the golden vectors recorded from the reference's own modules (tests/golden/, oracle/make_golden.py),
+  * the CPU oracle (oracle/allset_oracle.py) on seeded random inputs incl. the edge cases the domain has
+    (empty / interior-empty / singleton / very long segments, ragged widths, empty graph),
+  * size-independent properties at BASELINE.json's full sizes (checksums, linearity, constant rows).
+Tolerances (north_star): 1e-4 for fp32 storage, 1e-2 for bf16 storage.  Index work (CSR build) is bit-exact.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import allset_oracle as O
+from conftest import golden_x, load_golden
+
+pytestmark = pytest.mark.gpu
+
+FP32 = dict(rtol=1e-4, atol=1e-4)
+BF16 = dict(rtol=1e-2, atol=1e-2)
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def ab():
+    import allset_b200
+    return allset_b200
+
+
+def _ns(d):
+    from types import SimpleNamespace
+    return SimpleNamespace(**d)
+
+
+class _Data(object):
+    pass
+
+
+def _build(rec, agg_dtype=None):
+    args = _ns(rec['args'])
+    norm = rec['norm']
+    model = ab().SetGNN(args, norm, agg_dtype=agg_dtype) if args.LearnMask else ab().SetGNN(args, agg_dtype=agg_dtype)
+    missing = model.load_state_dict(rec['state_dict'], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model.to(dev()).eval()
+    data = _Data()
+    data.x = golden_x(rec).to(dev())
+    data.edge_index = rec['edge_index'].clone().to(dev())
+    data.norm = norm.to(dev())
+    return model, data
+
+
+def _taps(model):
+    taps, hooks = [], []
+    for i in range(len(model.V2EConvs)):
+        for conv in (model.V2EConvs[i], model.E2VConvs[i]):
+            hooks.append(conv.register_forward_hook(lambda m, inp, out: taps.append(out.detach().float().cpu())))
+    return taps, hooks
+
+
+# ------------------------------------------------------------------------------------------------------------
+# SetGNN against reference outputs (configs[0], configs[1] and the variants)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['cora_alldeepsets.pt', 'citeseer_allsettransformer.pt'])
+def test_setgnn_real_fp32(name):
+    rec = load_golden(name)
+    model, data = _build(rec)
+    taps, hooks = _taps(model)
+    data.x.requires_grad_(True)
+    out = model(data)
+    for h in hooks:
+        h.remove()
+    torch.testing.assert_close(out.detach().cpu(), rec['logits'], **FP32)
+    s = rec['tap_stride']
+    for mine, ref in zip(taps, rec['taps']):
+        torch.testing.assert_close(mine[::s], ref, **FP32)
+    # side effect of the reference forward: hyperedge ids zero-based in place (models.py:453-454)
+    assert torch.equal(data.edge_index.cpu(), rec['edge_index_after'])
+    (out * rec['grad_logits'].to(dev())).sum().backward()
+    torch.testing.assert_close(data.x.grad.sum(dim=1).cpu(), rec['grad_x_rowsum'], rtol=1e-3, atol=1e-4)
+    grads = dict((k, p.grad) for k, p in model.named_parameters() if p.grad is not None)
+    for k, g in rec['grads'].items():
+        torch.testing.assert_close(grads[k].cpu(), g, rtol=1e-3, atol=1e-4, msg=lambda m: k + ': ' + m)
+    # second forward reuses the cached incidence and gives the same answer
+    out2 = model(data)
+    assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize('name', ['cora_alldeepsets.pt', 'citeseer_allsettransformer.pt'])
+def test_setgnn_real_bf16_storage(name):
+    """bf16 rows in the aggregation kernels (fp32 accumulate), everything else fp32: <= 1e-2 of the reference."""
+    rec = load_golden(name)
+    model, data = _build(rec, agg_dtype=torch.bfloat16)
+    taps, hooks = _taps(model)
+    out = model(data)
+    for h in hooks:
+        h.remove()
+    s = rec['tap_stride']
+    # first aggregation output: single bf16 rounding of inputs + outputs
+    torch.testing.assert_close(taps[0][::s], rec['taps'][0], rtol=2e-2, atol=2e-2)
+    err = (out.detach().cpu() - rec['logits']).abs().max().item()
+    scale = rec['logits'].abs().max().item()
+    assert err <= 1e-2 * max(scale, 1.0) * 2, (err, scale)
+
+
+@pytest.mark.parametrize('idx', range(12))
+def test_setgnn_variants(idx):
+    rec = load_golden('setgnn_variants.pt')[idx]
+    model, data = _build(rec)
+    data.x.requires_grad_(True)
+    taps, hooks = _taps(model)
+    out = model(data)
+    for h in hooks:
+        h.remove()
+    torch.testing.assert_close(out.detach().cpu(), rec['logits'], **FP32)
+    for mine, ref in zip(taps, rec['taps']):
+        torch.testing.assert_close(mine, ref, **FP32)
+    (out * rec['grad_logits'].to(dev())).sum().backward()
+    torch.testing.assert_close(data.x.grad.sum(dim=1).cpu(), rec['grad_x_rowsum'], rtol=1e-3, atol=1e-4)
+    grads = dict((k, p.grad) for k, p in model.named_parameters() if p.grad is not None)
+    assert set(rec['grads']) <= set(grads)
+    for k, g in rec['grads'].items():
+        torch.testing.assert_close(grads[k].cpu(), g, rtol=1e-3, atol=1e-4, msg=lambda m: k + ': ' + m)
+
+
+@pytest.mark.parametrize('idx', range(12))
+def test_layers(idx):
+    rec = load_golden('layers_small.pt')[idx]
+    e = rec['extra']
+    if rec['kind'] == 'pma':
+        m = ab().PMA(e['in_channels'], e['hid_dim'], e['out_channels'], e['num_layers'], heads=e['heads'])
+    else:
+        m = ab().HalfNLHconv(e['in_dim'], e['hid_dim'], e['out_dim'], e['num_layers'], 0.3, e['Normalization'],
+                             e['InputNorm'], heads=1, attention=False)
+    m.load_state_dict(rec['state_dict'], strict=True)
+    m.to(dev()).eval()
+    x = rec['x'].to(dev()).requires_grad_(True)
+    ei = rec['edge_index'].to(dev())
+    if rec['kind'] == 'pma':
+        out, (ei_back, alpha) = m(x, ei, return_attention_weights=True)
+        assert ei_back is ei
+        torch.testing.assert_close(alpha.cpu(), rec['alpha'], **FP32)     # caller's COO order
+    else:
+        out = m(x, ei, rec['norm'].to(dev()), rec['aggr'])
+    assert out.shape[0] == e['n_tgt']
+    torch.testing.assert_close(out.detach().cpu(), rec['out'], **FP32)
+    (out * rec['grad_out'].to(dev())).sum().backward()
+    torch.testing.assert_close(x.grad.cpu(), rec['grad_x'], rtol=1e-3, atol=1e-4)
+    grads = dict((k, p.grad) for k, p in m.named_parameters() if p.grad is not None)
+    for k, g in rec['grads'].items():
+        torch.testing.assert_close(grads[k].cpu(), g, rtol=1e-3, atol=1e-4, msg=lambda m_: k + ': ' + m_)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# raw operators through the C ABI against the oracle
+# ------------------------------------------------------------------------------------------------------------
+def _graph(n_src, n_tgt, nnz, seed, long_seg=0, empty=()):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n_src, (nnz,), generator=g)
+    allowed = torch.tensor([t for t in range(n_tgt) if t not in set(empty)])
+    tgt = allowed[torch.randint(0, allowed.numel(), (nnz,), generator=g)]
+    if long_seg:                              # one very long segment (CTA-per-segment path) in the middle
+        tgt[:long_seg] = int(allowed[allowed.numel() // 2])
+    tgt[-1] = n_tgt - 1
+    src[-1] = n_src - 1
+    p = torch.randperm(nnz, generator=g)
+    return src[p].contiguous(), tgt[p].contiguous(), g
+
+
+def test_csr_build_bit_exact():
+    from allset_b200 import _lib
+    src, tgt, g = _graph(1000, 300, 20000, 0, long_seg=2000, empty=(0, 7, 299 - 1))
+    rowptr, col, perm = _lib.csr_from_coo(tgt.to(dev()), src.to(dev()), 300)
+    order = torch.argsort(tgt, stable=True)
+    assert torch.equal(perm.cpu().long(), order)
+    assert torch.equal(col.cpu().long(), src[order])
+    counts = torch.bincount(tgt, minlength=300)
+    ref_ptr = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+    assert torch.equal(rowptr.cpu().long(), ref_ptr)
+    # degenerate: no incidences
+    rowptr, col, perm = _lib.csr_from_coo(tgt[:0].to(dev()), src[:0].to(dev()), 5)
+    assert rowptr.cpu().tolist() == [0] * 6 and col.numel() == 0
+
+
+@pytest.mark.parametrize('d', [1, 3, 8, 20, 64, 128, 130, 256, 264, 512, 1000])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_segment_reduce_widths(d, dtype):
+    src, tgt, g = _graph(300, 90, 4000, d, long_seg=1500, empty=(0, 11))
+    inc = ab().Incidence.from_coo(src.to(dev()), tgt.to(dev()))
+    assert inc.n_tgt == 90 and inc.by_tgt.long_ids is not None
+    x = torch.randn(300, d, generator=g).to(dtype)
+    w = torch.rand(4000, generator=g) + 0.5
+    xr = x.float()
+    tol = FP32 if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2 * (1500 ** 0.5))
+    for reduce, weight in (('sum', None), ('mean', None), ('add', w), ('mean', w)):
+        out = ab().segment_reduce(x.to(dev()), inc, None if weight is None else weight.to(dev()), reduce)
+        ref = O.aggregate_sum_mean(xr, src, tgt, weight, reduce)
+        assert out.dtype == dtype and out.shape == ref.shape
+        if dtype == torch.float32:
+            torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=2e-4)
+        else:
+            # output is the bf16 rounding of an fp32 accumulation of exactly-represented inputs
+            torch.testing.assert_close(out.float().cpu(), ref, rtol=1e-2, atol=1e-2)
+    assert tol
+
+
+def test_segment_reduce_fp32_short_segments_match_sequential_sum_exactly():
+    """No atomics, CSR order = COO order: fp32 sums over short segments equal the sequential CPU scatter_add_."""
+    src, tgt, g = _graph(500, 400, 3000, 5)
+    torch.set_num_threads(1)
+    inc = ab().Incidence.from_coo(src.to(dev()), tgt.to(dev()))
+    x = torch.randn(500, 64, generator=g)
+    out = ab().segment_reduce(x.to(dev()), inc, None, 'sum').cpu()
+    ref = torch.zeros(400, 64).index_add_(0, tgt, x[src])
+    assert torch.equal(out, ref)
+
+
+def test_segment_reduce_edge_cases():
+    d = dev()
+    # empty graph
+    e = torch.zeros(0, dtype=torch.long, device=d)
+    inc = ab().Incidence.from_coo(e, e)
+    out = ab().segment_reduce(torch.zeros(0, 16, device=d), inc, None, 'sum')
+    assert out.shape == (0, 16)
+    # all segments singletons (self-loop hyperedges: half of real cora's segments)
+    idx = torch.arange(50, device=d)
+    inc = ab().Incidence.from_coo(idx, idx.flip(0))
+    x = torch.randn(50, 24, device=d)
+    torch.testing.assert_close(ab().segment_reduce(x, inc, None, 'mean'), x.flip(0))
+    # explicit sizes: trailing empty targets kept when n_tgt is given
+    inc = ab().Incidence.from_coo(idx, idx // 2, n_src=50, n_tgt=40)
+    out = ab().segment_reduce(x, inc, None, 'sum')
+    assert out.shape == (40, 24) and bool((out[25:] == 0).all())
+    torch.testing.assert_close(out[:25], x[0::2] + x[1::2])
+    # int64 all-ones `norm` (preprocessing.py:454) through the layer: no weight multiply needed
+    # bad inputs fail loudly
+    with pytest.raises(RuntimeError):
+        ab().segment_reduce(x.cpu(), inc, None, 'sum')
+    with pytest.raises(ValueError):
+        ab().segment_reduce(x, inc, None, 'max')
+    with pytest.raises(TypeError):
+        ab().segment_reduce(x.double(), inc, None, 'sum')
+    with pytest.raises(RuntimeError):
+        ab().Incidence.from_coo(idx.cpu(), idx.cpu())
+
+
+def test_segment_reduce_backward_vs_oracle():
+    src, tgt, g = _graph(200, 70, 2500, 9, long_seg=1200, empty=(3,))
+    inc = ab().Incidence.from_coo(src.to(dev()), tgt.to(dev()))
+    for reduce in ('sum', 'mean'):
+        x = torch.randn(200, 48, generator=g)
+        w = torch.rand(2500, generator=g) + 0.5
+        go = torch.randn(70, 48, generator=g)
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        (O.aggregate_sum_mean(xr, src, tgt, wr, reduce) * go).sum().backward()
+        xg, wg = x.to(dev()).requires_grad_(True), w.to(dev()).requires_grad_(True)
+        (ab().segment_reduce(xg, inc, wg, reduce) * go.to(dev())).sum().backward()
+        torch.testing.assert_close(xg.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(wg.grad.cpu(), wr.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('H,C', [(1, 16), (4, 32), (8, 16), (2, 12), (4, 3), (1, 5), (8, 64), (3, 100)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_pma_aggregate_vs_oracle(H, C, dtype):
+    src, tgt, g = _graph(250, 80, 3500, H * 100 + C, long_seg=1300, empty=(0, 5))
+    inc = ab().Incidence.from_coo(src.to(dev()), tgt.to(dev()))
+    v = torch.randn(250, H * C, generator=g).to(dtype)
+    score = torch.randn(250, H, generator=g) * 3.0
+    seed = torch.randn(1, H, C, generator=g)
+    vr, sr, seedr = v.float().clone().requires_grad_(True), score.clone().requires_grad_(True), seed.clone().requires_grad_(True)
+    ref, alpha_ref = O.aggregate_pma(vr.view(-1, H, C), sr, seedr, src, tgt)
+    ref = ref.reshape(-1, H * C)
+    vg, sg, seedg = v.to(dev()).requires_grad_(True), score.to(dev()).requires_grad_(True), seed.to(dev()).requires_grad_(True)
+    out, alpha = ab().pma_aggregate(vg, sg, seedg, inc, H, 0.2, return_alpha=True)
+    assert out.dtype == dtype and out.shape == ref.shape
+    tol = FP32 if dtype == torch.float32 else BF16
+    torch.testing.assert_close(out.float().cpu(), ref.detach(), **tol)
+    torch.testing.assert_close(alpha.cpu(), alpha_ref.detach(), **FP32)
+    # empty segments give the seed (zero row + att_r, layers.py:153)
+    torch.testing.assert_close(out[5].float().cpu(), seed.reshape(-1).to(dtype).float(), **tol)
+    go = torch.randn(ref.shape, generator=g)
+    (ref * go).sum().backward()
+    (out.float() * go.to(dev())).sum().backward()
+    gtol = dict(rtol=1e-3, atol=1e-4) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(vg.grad.float().cpu(), vr.grad, **gtol)
+    torch.testing.assert_close(sg.grad.cpu(), sr.grad, **gtol)
+    torch.testing.assert_close(seedg.grad.cpu(), seedr.grad, **(dict(rtol=1e-3, atol=1e-3) if dtype == torch.float32 else dict(rtol=5e-2, atol=5e-1)))
+
+
+def test_pma_extreme_scores_are_stable():
+    """Max-subtraction: scores of +-1e4 must not overflow (PyG softmax subtracts the segment max)."""
+    src, tgt, g = _graph(60, 10, 400, 77)
+    inc = ab().Incidence.from_coo(src.to(dev()), tgt.to(dev()))
+    v = torch.randn(60, 32, generator=g)
+    score = torch.randn(60, 4, generator=g) * 1e4
+    seed = torch.zeros(1, 4, 8)
+    ref, _ = O.aggregate_pma(v.view(-1, 4, 8), score, seed, src, tgt)
+    out, _ = ab().pma_aggregate(v.to(dev()), score.to(dev()), seed.to(dev()), inc, 4)
+    assert bool(torch.isfinite(out).all())
+    torch.testing.assert_close(out.cpu(), ref.reshape(-1, 32), **FP32)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs 3 and 4 shapes)
+# ------------------------------------------------------------------------------------------------------------
+def _full_size_checks(n, m, mean_size, d, heads):
+    from allset_b200 import synthetic
+    ei = synthetic.poisson_hypergraph(n, m, mean_size, seed=1234, device=dev())
+    assert bool((ei[0, 1:] >= ei[0, :-1]).all()) and int(ei[1].min()) >= n      # reference layout
+    he = ei[1] - n
+    v2e = ab().Incidence.from_coo(ei[0], he, n_src=n, n_tgt=m)
+    e2v = v2e.reversed()
+    nnz = ei.shape[1]
+    x = synthetic.features(n, d, torch.bfloat16, device=dev())
+    # CSR invariants: sorted targets, stable order, permutation
+    t = v2e.by_tgt
+    assert int(t.rowptr[0]) == 0 and int(t.rowptr[-1]) == nnz
+    assert bool((t.rowptr[1:] >= t.rowptr[:-1]).all())
+    assert torch.equal(he[t.perm64], torch.repeat_interleave(torch.arange(m, device=dev()), (t.rowptr[1:] - t.rowptr[:-1]).long()))
+    assert torch.equal(t.col.long(), ei[0][t.perm64])
+    # checksum of checksums: sum_t out[t] == sum_v deg(v) x[v]  (fp32 storage of the same values)
+    xf = x.float()
+    xe = ab().segment_reduce(xf, v2e, None, 'sum')
+    deg_v = torch.bincount(ei[0], minlength=n).double()
+    want = (deg_v[:, None] * xf.double()).sum(0)
+    torch.testing.assert_close(xe.double().sum(0), want, rtol=1e-6, atol=1e-2)
+    # bf16 storage == rounding of the fp32 result (inputs identical, fp32 accumulate in the same order)
+    xe_b = ab().segment_reduce(x, v2e, None, 'sum')
+    assert torch.equal(xe_b, xe.to(torch.bfloat16))
+    # mean of constant rows is the constant; E->V covers every vertex that has an incidence
+    ones = torch.ones(m, d, device=dev(), dtype=torch.bfloat16) * 3
+    xv = ab().segment_reduce(ones, e2v, None, 'mean')
+    has = deg_v > 0
+    assert bool((xv[has] == 3).all()) and bool((xv[~has] == 0).all())
+    # linearity in fp32: R(a x + y) = a R(x) + R(y)
+    y = torch.randn(n, d, device=dev())
+    lhs = ab().segment_reduce(2.0 * xf + y, v2e, None, 'sum')
+    rhs = 2.0 * xe + ab().segment_reduce(y, v2e, None, 'sum')
+    torch.testing.assert_close(lhs, rhs, rtol=1e-4, atol=1e-3)
+    del y, lhs, rhs, xf
+    # PMA: convex combination => constant value rows come back unchanged (+ seed); alpha sums to 1 per segment
+    score = torch.randn(n, heads, device=dev())
+    seed = torch.randn(1, heads, d // heads, device=dev())
+    const = torch.full((n, d), 0.5, device=dev(), dtype=torch.bfloat16)
+    out, alpha = ab().pma_aggregate(const, score, seed, v2e, heads, return_alpha=True)
+    torch.testing.assert_close(out.float(), (0.5 + seed.reshape(1, -1)).to(torch.bfloat16).float().expand(m, d), rtol=1e-2, atol=1e-2)
+    seg_sum = torch.zeros(m, heads, device=dev()).index_add_(0, he, alpha)
+    torch.testing.assert_close(seg_sum, torch.ones_like(seg_sum), rtol=1e-4, atol=1e-4)
+    # spot parity against the oracle on the first 2000 hyperedges
+    sel = he < 2000
+    sub_src, sub_tgt = ei[0][sel].cpu(), he[sel].cpu()
+    ref = O.aggregate_sum_mean(x.float().cpu(), sub_src, sub_tgt, None, 'sum')
+    torch.testing.assert_close(xe[:ref.shape[0]].cpu(), ref, **FP32)
+    vv = x
+    ref_p, _ = O.aggregate_pma(vv.float().cpu().view(n, heads, -1), score.cpu(), seed.cpu(), sub_src, sub_tgt)
+    out_p, _ = ab().pma_aggregate(vv, score, seed, v2e, heads)
+    torch.testing.assert_close(out_p[:ref_p.shape[0]].float().cpu(), ref_p.reshape(ref_p.shape[0], -1), **BF16)
+
+
+def test_full_size_config3_properties():
+    _full_size_checks(1_000_000, 200_000, 20, 128, 8)
+
+
+def test_full_size_config4_properties():
+    _full_size_checks(10_000_000, 2_000_000, 30, 128, 8)
+
+
+def test_powerlaw_long_segments_config5_shape():
+    """configs[4] distribution at reduced N (max-deg 4096 hyperedge forced): long-segment path vs oracle."""
+    from allset_b200 import synthetic
+    n, m, d = 200_000, 30_000, 256
+    ei = synthetic.powerlaw_hypergraph(n, m, 2, 4096, 2.0, seed=1234, device=dev())
+    he = ei[1] - n
+    assert int(torch.bincount(he).max()) == 4096
+    v2e = ab().Incidence.from_coo(ei[0], he, n_src=n, n_tgt=m)
+    assert v2e.by_tgt.long_ids is not None
+    x = synthetic.features(n, d, torch.bfloat16, device=dev())
+    out = ab().segment_reduce(x, v2e, None, 'sum')
+    ref = O.aggregate_sum_mean(x.float().cpu(), ei[0].cpu(), he.cpu(), None, 'sum')
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=1e-2, atol=1e-2)
+    outm = ab().segment_reduce(x.float(), v2e, None, 'mean')
+    refm = O.aggregate_sum_mean(x.float().cpu(), ei[0].cpu(), he.cpu(), None, 'mean')
+    torch.testing.assert_close(outm.cpu(), refm, **FP32)

@@ -1,0 +1,149 @@
+"""CPU-side checks (no GPU, no compute calls): the C-ABI library loads and exports every symbol the header
+declares, the modules mirror the reference's constructor / state_dict surface, and the product path fails loudly
+instead of falling back to any CPU implementation."""
+import ctypes
+import os
+import re
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+import allset_oracle as O
+from conftest import ROOT, load_golden
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, 'include', 'allset_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(allset_[a-z0-9_]+)\s*\(', text)))
+
+
+@pytest.fixture(scope='module')
+def built_lib():
+    from allset_b200 import build
+    return build.build()
+
+
+def test_header_declares_the_documented_entry_points():
+    names = _header_functions()
+    for must in ('allset_version', 'allset_last_error', 'allset_csr_from_coo', 'allset_segreduce_fwd',
+                 'allset_segreduce_bwd_w', 'allset_pma_fwd', 'allset_pma_bwd', 'allset_pma_alpha'):
+        assert must in names
+
+
+def test_library_exports_every_header_symbol(built_lib):
+    h = ctypes.CDLL(built_lib)
+    for name in _header_functions():
+        assert hasattr(h, name), 'liballset_b200.so does not export %s' % name
+    h.allset_version.restype = ctypes.c_int
+    m = re.search(r'#define ALLSET_ABI_VERSION (\d+)', open(os.path.join(ROOT, 'include', 'allset_b200.h')).read())
+    assert h.allset_version() == int(m.group(1))
+
+
+def test_ctypes_signatures_cover_the_header(built_lib):
+    from allset_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _header_functions()
+    assert _lib.lib().allset_version() == _lib.ABI_VERSION
+
+
+def test_library_is_sm100a_only(built_lib):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.isfile(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    out = subprocess.run([cuobjdump, '--list-elf', built_lib], capture_output=True, text=True).stdout
+    archs = set(re.findall(r'sm_(\d+a?)', out))
+    assert archs == {'100a'}, archs
+
+
+@pytest.mark.parametrize('name', ['cora_alldeepsets.pt', 'citeseer_allsettransformer.pt'])
+def test_state_dict_keys_match_reference(name):
+    import allset_b200
+    rec = load_golden(name)
+    model = allset_b200.SetGNN(SimpleNamespace(**rec['args']))
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(rec['state_dict'].keys())
+    for k, v in rec['state_dict'].items():
+        assert sd[k].shape == v.shape and sd[k].dtype == v.dtype, k
+    model.load_state_dict(rec['state_dict'], strict=True)
+
+
+def test_state_dict_keys_match_reference_variants():
+    import allset_b200
+    for rec in load_golden('setgnn_variants.pt'):
+        args = SimpleNamespace(**rec['args'])
+        model = allset_b200.SetGNN(args, rec['norm']) if args.LearnMask else allset_b200.SetGNN(args)
+        assert list(model.state_dict().keys()) == list(rec['state_dict'].keys()), rec['name']
+        model.load_state_dict(rec['state_dict'], strict=True)
+        model.reset_parameters()
+        n_ref = sum(v.numel() for k, v in rec['state_dict'].items() if 'running_' not in k and 'num_batches' not in k)
+        assert sum(p.numel() for p in model.parameters()) == n_ref
+
+
+def test_reset_parameters_distributions():
+    """glorot on lin_K / lin_V weights, xavier_uniform on the seed (reference layers.py:96-104)."""
+    import math
+    import allset_b200
+    torch.manual_seed(0)
+    p = allset_b200.PMA(64, 128, 128, 2, heads=4)
+    bound = math.sqrt(6.0 / (64 + 128))
+    assert float(p.lin_K.weight.abs().max()) <= bound and float(p.lin_K.weight.abs().max()) > 0.9 * bound
+    assert p.att_r.shape == (1, 4, 32)
+    fan_in, fan_out = 4 * 32, 1 * 32           # torch's fan computation for a [1, H, C] tensor
+    b2 = math.sqrt(6.0 / (fan_in + fan_out))
+    assert float(p.att_r.abs().max()) <= b2
+    assert p.rFF.lins[0].in_features == 128 and isinstance(p.rFF.normalizations[0], torch.nn.Identity)
+
+
+def test_no_cpu_fallback():
+    import allset_b200
+    rec = load_golden('setgnn_variants.pt')[0]
+    model = allset_b200.SetGNN(SimpleNamespace(**rec['args'])).eval()
+    data = SimpleNamespace(x=rec['x'], edge_index=rec['edge_index'].clone(), norm=rec['norm'])
+    with pytest.raises(RuntimeError, match='CUDA'):
+        model(data)
+    with pytest.raises(RuntimeError, match='CUDA|CPU'):
+        allset_b200.Incidence.from_coo(rec['edge_index'][0], rec['edge_index'][1])
+    conv = allset_b200.HalfNLHconv(14, 16, 16, 2, 0.0, 'ln', True, heads=1, attention=False)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        conv(rec['x'], rec['edge_index'], rec['norm'], 'add')
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'allset_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'allset_oracle' not in text and 'ref_harness' not in text, f
+                assert not re.search(r'^\s*(from|import)\s+oracle', text, flags=re.M), f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from allset_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/liballset_b200.so')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        _lib.lib()
+
+
+def test_synthetic_generators_follow_reference_layout():
+    from allset_b200 import synthetic
+    ei = synthetic.poisson_hypergraph(5000, 1000, 20, seed=1)
+    assert ei.dtype == torch.int64 and ei.shape[0] == 2
+    assert bool((ei[0, 1:] >= ei[0, :-1]).all())                       # ExtractV2E: sorted by node
+    assert int(ei[1].min()) == 5000 and int(ei[1].max()) == 5999       # hyperedge ids start at N
+    sizes = torch.bincount(ei[1] - 5000)
+    assert int(sizes.min()) >= 1 and abs(float(sizes.float().mean()) - 20) < 0.5
+    ei2 = synthetic.poisson_hypergraph(5000, 1000, 20, seed=1)
+    assert torch.equal(ei, ei2)
+    pl = synthetic.powerlaw_hypergraph(20000, 3000, 2, 4096, 2.0, seed=1)
+    s = torch.bincount(pl[1] - 20000)
+    assert int(s.max()) == 4096 and int(s.min()) >= 2
+    assert synthetic.algorithmic_bytes(4_000_000, 200_000, 128, 2) == 4_000_000 * 260 + 200_001 * 4 + 200_000 * 256
+    # the oracle accepts the layout as is
+    x = torch.randn(5000, 4)
+    out = O.aggregate_sum_mean(x, ei[0], ei[1] - 5000, None, 'sum')
+    assert out.shape == (1000, 4)
