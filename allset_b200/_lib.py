@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liballset_b200.so')
+LIB_PATH = os.environ.get('ALLSET_B200_LIB') or os.path.join(_HERE, 'liballset_b200.so')   # override: kernel tuning builds
 ABI_VERSION = 1
 
 F32, BF16 = 0, 1

@@ -51,8 +51,21 @@ int check_launch(const char* what) {
   return ALLSET_OK;
 }
 
-constexpr int kThreads = 256;   // 8 warps per CTA
-constexpr int kUnroll = 8;      // independent row loads in flight per lane
+#ifndef ALLSET_THREADS
+#define ALLSET_THREADS 256
+#endif
+#ifndef ALLSET_UNROLL_SUM
+#define ALLSET_UNROLL_SUM 6
+#endif
+#ifndef ALLSET_UNROLL_PMA
+#define ALLSET_UNROLL_PMA 4
+#endif
+constexpr int kThreads = ALLSET_THREADS;        // 8 warps per CTA
+// Independent row loads in flight per lane.  Measured on B200 (10M/2M/deg-30 graph, d=128 bf16): the sum kernel
+// peaks at 6 (U=4: 3.49 ms, U=6: 2.52 ms, U=8: 2.85 ms for V->E) -- more loads per lane cost registers and hence
+// resident warps; the PMA kernels carry more state per lane and peak at 4.
+constexpr int kUnrollSum = ALLSET_UNROLL_SUM;
+constexpr int kUnrollPma = ALLSET_UNROLL_PMA;
 
 // ---------------------------------------------------------------------------------------------
 // chunk access: VECTOR = one 16-byte chunk per lane; otherwise one element per lane
@@ -81,6 +94,10 @@ struct Chunk<float, true> {
   __device__ static __forceinline__ void store(float* p, const float (&f)[N]) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
   }
+  __device__ static __forceinline__ void add(const Raw& r, float (&acc)[N]) {
+    acc[0] = __fadd_rn(acc[0], __uint_as_float(r.x)); acc[1] = __fadd_rn(acc[1], __uint_as_float(r.y));
+    acc[2] = __fadd_rn(acc[2], __uint_as_float(r.z)); acc[3] = __fadd_rn(acc[3], __uint_as_float(r.w));
+  }
 };
 
 template <>
@@ -106,6 +123,16 @@ struct Chunk<__nv_bfloat16, true> {
     o.z = *reinterpret_cast<unsigned*>(&c); o.w = *reinterpret_cast<unsigned*>(&e);
     *reinterpret_cast<uint4*>(p) = o;
   }
+  // acc += bf16 halves, one FHADD.BF16 each (sm_100 mixed-precision add: bf16 -> fp32 is exact, the add rounds
+  // to nearest in fp32), so a 16-byte chunk costs 8 instructions with no unpack.
+  __device__ static __forceinline__ void add(const Raw& r, float (&acc)[N]) {
+    add2(r.x, acc[0], acc[1]); add2(r.y, acc[2], acc[3]); add2(r.z, acc[4], acc[5]); add2(r.w, acc[6], acc[7]);
+  }
+  __device__ static __forceinline__ void add2(unsigned w, float& a0, float& a1) {
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
+        "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}"
+        : "+f"(a0), "+f"(a1) : "r"(w));
+  }
 };
 
 template <>
@@ -116,6 +143,7 @@ struct Chunk<float, false> {
   __device__ static __forceinline__ Raw load(const float* p) { return __ldg(p); }
   __device__ static __forceinline__ void unpack(const Raw& r, float (&f)[N]) { f[0] = r; }
   __device__ static __forceinline__ void store(float* p, const float (&f)[N]) { *p = f[0]; }
+  __device__ static __forceinline__ void add(const Raw& r, float (&acc)[N]) { acc[0] = __fadd_rn(acc[0], r); }
 };
 
 template <>
@@ -131,6 +159,9 @@ struct Chunk<__nv_bfloat16, false> {
   }
   __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&f)[N]) {
     *p = __float2bfloat16_rn(f[0]);
+  }
+  __device__ static __forceinline__ void add(const Raw& r, float (&acc)[N]) {
+    acc[0] = __fadd_rn(acc[0], __uint_as_float(static_cast<unsigned>(r) << 16));
   }
 };
 
@@ -180,7 +211,7 @@ __device__ __forceinline__ void accumulate_rows(const T* __restrict__ x, const i
                                                 float (&acc)[Chunk<T, VECTOR>::N]) {
   using CH = Chunk<T, VECTOR>;
   constexpr int N = CH::N;
-  constexpr int U = G < kUnroll ? G : kUnroll;
+  constexpr int U = G < kUnrollSum ? G : kUnrollSum;
   for (int base = first; base < end; base += stride) {
     const int n = min(G, end - base);
     int myidx = 0;
@@ -205,12 +236,14 @@ __device__ __forceinline__ void accumulate_rows(const T* __restrict__ x, const i
       }
 #pragma unroll
       for (int k = 0; k < U; ++k) {
-        float f[N];
-        CH::unpack(raw[k], f);
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
+        if (WEIGHTED) {
+          float f[N];
+          CH::unpack(raw[k], f);
           // mul then add, each rounded: the reference materialises norm*x_j before the scatter
-          acc[i] = WEIGHTED ? __fadd_rn(acc[i], __fmul_rn(wk[k], f[i])) : __fadd_rn(acc[i], f[i]);
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc[i] = __fadd_rn(acc[i], __fmul_rn(wk[k], f[i]));
+        } else {
+          CH::add(raw[k], acc);
         }
       }
     }
@@ -320,7 +353,7 @@ __device__ __forceinline__ void pma_accumulate(const T* __restrict__ v, const fl
                                                float (&acc)[Chunk<T, VECTOR>::N]) {
   using CH = Chunk<T, VECTOR>;
   constexpr int N = CH::N;
-  constexpr int U = G < kUnroll ? G : kUnroll;
+  constexpr int U = G < kUnrollPma ? G : kUnrollPma;
   for (int base = first; base < end; base += stride) {
     const int n = min(G, end - base);
     int myidx = 0;
@@ -533,7 +566,7 @@ __device__ __forceinline__ void pma_bwd_accumulate(const T* __restrict__ go, con
                                                    float& sD, float (&gv)[Chunk<T, VECTOR>::N]) {
   using CH = Chunk<T, VECTOR>;
   constexpr int N = CH::N;
-  constexpr int U = G < kUnroll ? G : kUnroll;
+  constexpr int U = G < kUnrollPma ? G : kUnrollPma;
   for (int base = first; base < end; base += stride) {
     const int n = min(G, end - base);
     int myidx = 0;
