@@ -29,6 +29,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "allset_b200.h"
@@ -317,6 +318,266 @@ segreduce_cta_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
     }
     if (active) CH::store(out + (size_t)seg * (size_t)d + feat, acc);
   }
+}
+
+// a / c for a small positive integer count c, rc = __frcp_rn(c): one Newton correction of a * rc gives the
+// correctly rounded quotient (Markstein) without the slow-path call of the generic fp32 division.
+__device__ __forceinline__ float div_count(float a, float c, float rc) {
+  const float q = a * rc;
+  const float r = fmaf(-q, c, a);
+  const float res = fmaf(r, rc, q);
+  return fabsf(q) == INFINITY ? q : res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// STREAM kernels: rows staged through shared memory by the TMA (cp.async.bulk), one row per copy
+// ---------------------------------------------------------------------------------------------
+// Each warp owns a contiguous block of target segments, i.e. ONE contiguous range [kb, ke) of the CSR, and runs its
+// own producer/consumer ring in shared memory:
+//   produce : 32 lanes read 32 column ids with one coalesced load and each lane issues ONE bulk copy
+//             (cp.async.bulk global -> shared, `row_bytes` each) that completes on the stage's mbarrier.  Bytes in
+//             flight live in shared memory, not in registers: (stages-1) * 8 KB per warp with ~40 registers/thread.
+//   consume : after the mbarrier flips, the whole warp reads one staged row per LDS (lane = 1/32 of the row,
+//             conflict-free), adds it into fp32 accumulators (FHADD.BF16 for bf16 rows) and flushes the accumulator
+//             to `out` whenever the flat stream crosses a segment boundary.  Control flow is warp-uniform.
+// Per row this costs ~1/32 copy instruction + 1 LDS + (row_bytes/64) adds per warp instead of 16 LDG + shuffles +
+// unpack per lane group, and it removes the per-segment rowptr -> col -> row dependency chain that makes short
+// segments (E->V: ~6 incidences per vertex; real data: size-1 self-loop hyperedges) latency-bound.
+#ifndef ALLSET_STREAM_WARPS
+#define ALLSET_STREAM_WARPS 8
+#endif
+#ifndef ALLSET_STREAM_STAGE_BYTES
+#define ALLSET_STREAM_STAGE_BYTES 8192
+#endif
+#ifndef ALLSET_STREAM_SMEM
+#define ALLSET_STREAM_SMEM (192 * 1024)
+#endif
+constexpr int kStreamWarps = ALLSET_STREAM_WARPS;
+constexpr int kStreamStageBytes = ALLSET_STREAM_STAGE_BYTES;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// One lane's share of a staged row: LB bytes (LB = row_bytes / 32).  LB >= 16 is read as LB/16 16-byte chunks,
+// chunk c of lane l at byte (c*32 + l)*16, so every LDS.128 of the warp covers 512 contiguous bytes.
+template <typename T, int LB>
+struct LaneRow {
+  static constexpr int ES = sizeof(T);
+  static constexpr int NA = LB / ES;                 // fp32 accumulators per lane
+  static constexpr int CH = LB >= 16 ? LB / 16 : 1;  // 16-byte chunks per lane
+  static constexpr int CB = LB >= 16 ? 16 : LB;      // bytes per chunk
+  static constexpr int EPC = CB / ES;                // elements per chunk
+  __device__ static __forceinline__ int offset(int lane, int c) { return (c * 32 + lane) * CB; }
+  // acc += row (fp32 accumulate); `p` = shared-space byte address of the row
+  __device__ static __forceinline__ void add(uint32_t p, int lane, float (&acc)[NA]) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      uint32_t r[4] = {0u, 0u, 0u, 0u};
+      const uint32_t a = p + offset(lane, c);
+      if (CB == 16) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+      else if (CB == 8) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+      else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r[0]) : "r"(a));
+#pragma unroll
+      for (int q = 0; q < CB / 4; ++q) {
+        if (ES == 2) Chunk<__nv_bfloat16, true>::add2(r[q], acc[c * EPC + 2 * q], acc[c * EPC + 2 * q + 1]);
+        else acc[c * EPC + q] = __fadd_rn(acc[c * EPC + q], __uint_as_float(r[q]));
+      }
+    }
+  }
+  // acc += wk * row, product and sum rounded separately (the reference materialises norm * x_j first)
+  __device__ static __forceinline__ void add_weighted(uint32_t p, int lane, float wk, float (&acc)[NA]) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      uint32_t r[4] = {0u, 0u, 0u, 0u};
+      const uint32_t a = p + offset(lane, c);
+      if (CB == 16) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+      else if (CB == 8) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+      else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r[0]) : "r"(a));
+#pragma unroll
+      for (int q = 0; q < CB / 4; ++q) {
+        if (ES == 2) {
+          const float lo = __uint_as_float(r[q] << 16), hi = __uint_as_float(r[q] & 0xffff0000u);
+          acc[c * EPC + 2 * q] = __fadd_rn(acc[c * EPC + 2 * q], __fmul_rn(wk, lo));
+          acc[c * EPC + 2 * q + 1] = __fadd_rn(acc[c * EPC + 2 * q + 1], __fmul_rn(wk, hi));
+        } else {
+          acc[c * EPC + q] = __fadd_rn(acc[c * EPC + q], __fmul_rn(wk, __uint_as_float(r[q])));
+        }
+      }
+    }
+  }
+  __device__ static __forceinline__ void store(T* row, int lane, const float (&acc)[NA]) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      unsigned char* dst = reinterpret_cast<unsigned char*>(row) + offset(lane, c);
+      if (ES == 2) {
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < CB / 4; ++q) {
+          __nv_bfloat162 v = __floats2bfloat162_rn(acc[c * EPC + 2 * q], acc[c * EPC + 2 * q + 1]);
+          o[q] = *reinterpret_cast<uint32_t*>(&v);
+        }
+        if (CB == 16) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        else if (CB == 8) *reinterpret_cast<uint2*>(dst) = make_uint2(o[0], o[1]);
+        else *reinterpret_cast<uint32_t*>(dst) = o[0];
+      } else {
+        if (CB == 16) *reinterpret_cast<float4*>(dst) = make_float4(acc[c * EPC], acc[c * EPC + 1], acc[c * EPC + 2], acc[c * EPC + 3]);
+        else if (CB == 8) *reinterpret_cast<float2*>(dst) = make_float2(acc[c * EPC], acc[c * EPC + 1]);
+        else *reinterpret_cast<float*>(dst) = acc[c * EPC];
+      }
+    }
+  }
+};
+
+template <typename T, int LB, bool WEIGHTED>
+__global__ void __launch_bounds__(kStreamWarps * 32, 1)
+segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
+                        const float* __restrict__ w, const float* __restrict__ sscale, long long n_tgt, int d,
+                        int mean, int seg_per_warp, int stages, T* __restrict__ out) {
+  using LR = LaneRow<T, LB>;
+  constexpr int NA = LR::NA;
+  constexpr int ROWB = LB * 32;
+  constexpr int RPS = (kStreamStageBytes / ROWB) < 32 ? (kStreamStageBytes / ROWB) : 32;   // rows per stage
+  constexpr int CUNR = RPS < 4 ? RPS : 4;                                                  // rows per consume step
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long s_first = ((long long)blockIdx.x * kStreamWarps + warp) * seg_per_warp;
+  if (s_first >= n_tgt) return;                       // warp-uniform; nothing below synchronises across warps
+  const int nseg = (int)min((long long)seg_per_warp, n_tgt - s_first);
+  const uint32_t ring = smem_u32(smem) + (uint32_t)warp * (uint32_t)stages * (RPS * ROWB);
+  const uint32_t bars = smem_u32(smem) + (uint32_t)kStreamWarps * (uint32_t)stages * (RPS * ROWB) +
+                        (uint32_t)warp * (uint32_t)stages * 8u;
+  float* wbuf = reinterpret_cast<float*>(smem + (size_t)kStreamWarps * stages * (RPS * ROWB) +
+                                         (size_t)kStreamWarps * stages * 8) + (size_t)warp * stages * RPS;
+  if (lane < stages) mbar_init(bars + lane * 8, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+
+  const int* __restrict__ rp = rowptr + s_first;
+  const int kb = __ldg(rp), ke = __ldg(rp + nseg);
+  // window of 32 segment ends: lane j holds the end of segment wb + j; the next window is prefetched
+  int wb = 0;
+  int my_end = __ldg(rp + min(lane + 1, nseg));
+  int nxt_end = __ldg(rp + min(32 + lane + 1, nseg));
+
+  float acc[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+  T* __restrict__ ob = out + (size_t)s_first * (size_t)d;
+  int seg = 0, cur_beg = kb, cur_end = __shfl_sync(0xffffffffu, my_end, 0), pos = kb;
+
+  auto flush = [&]() {
+    if (mean) {
+      const float cnt = (float)max(cur_end - cur_beg, 1);
+      const float rc = __frcp_rn(cnt);
+#pragma unroll
+      for (int i = 0; i < NA; ++i) acc[i] = div_count(acc[i], cnt, rc);
+    }
+    LR::store(ob, lane, acc);
+    ob += d;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+    ++seg;
+    if ((seg & 31) == 0) {
+      wb += 32;
+      my_end = nxt_end;
+      nxt_end = __ldg(rp + min(wb + 32 + lane + 1, nseg));
+    }
+    cur_beg = cur_end;
+    const int e = __shfl_sync(0xffffffffu, my_end, seg & 31);
+    cur_end = seg < nseg ? e : INT32_MAX;
+  };
+
+  // ---- producer side ---------------------------------------------------------------------------------------
+  int ipos = kb;                       // next stream position to issue
+  int pf_idx = 0;                      // column id of stream position ipos + lane, loaded one step ahead
+  float pf_w = 1.f;
+  auto prefetch = [&]() {
+    pf_idx = 0;
+    pf_w = 1.f;
+    if (lane < RPS && ipos + lane < ke) {
+      pf_idx = __ldg(col + ipos + lane);
+      if (WEIGHTED) {
+        if (w != nullptr) pf_w = __ldg(w + ipos + lane);
+        if (sscale != nullptr) pf_w *= __ldg(sscale + pf_idx);
+      }
+    }
+  };
+  auto issue = [&](int st) {
+    const int n = min(RPS, ke - ipos);
+    const uint32_t bar = bars + st * 8;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)n * ROWB);
+    __syncwarp();
+    if (lane < n) {
+      bulk_g2s(ring + (uint32_t)st * (RPS * ROWB) + (uint32_t)lane * ROWB,
+               reinterpret_cast<const unsigned char*>(x) + (size_t)pf_idx * ROWB, ROWB, bar);
+      if (WEIGHTED) wbuf[st * RPS + lane] = pf_w;
+    }
+    ipos += RPS;
+    prefetch();
+  };
+  prefetch();
+  for (int st = 0; st < stages && ipos < ke; ++st) issue(st);
+
+  // ---- consumer side ---------------------------------------------------------------------------------------
+  int st = 0;
+  uint32_t phase = 0;
+  for (int cbase = kb; cbase < ke; cbase += RPS) {
+    const int n = min(RPS, ke - cbase);
+    mbar_wait(bars + st * 8, phase);
+    if (WEIGHTED) __syncwarp();
+    const uint32_t rows = ring + (uint32_t)st * (RPS * ROWB);
+    const float* wrow = wbuf + st * RPS;
+#pragma unroll 1
+    for (int r = 0; r < n; r += CUNR) {
+      if (r + CUNR <= n && cur_end - pos >= CUNR) {
+#pragma unroll
+        for (int k = 0; k < CUNR; ++k) {
+          if (WEIGHTED) LR::add_weighted(rows + (r + k) * ROWB, lane, wrow[r + k], acc);
+          else LR::add(rows + (r + k) * ROWB, lane, acc);
+        }
+        pos += CUNR;
+      } else {
+        for (int k = 0; k < CUNR && r + k < n; ++k) {
+          while (pos >= cur_end) flush();
+          if (WEIGHTED) LR::add_weighted(rows + (r + k) * ROWB, lane, wrow[r + k], acc);
+          else LR::add(rows + (r + k) * ROWB, lane, acc);
+          ++pos;
+        }
+      }
+    }
+    __syncwarp();
+    if (ipos < ke) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of this stage before the async refill
+      issue(st);
+    }
+    if (++st == stages) {
+      st = 0;
+      phase ^= 1u;
+    }
+  }
+  while (seg < nseg) flush();
 }
 
 // grad_w[k] = tgt_scale[t] * <x[col[k]], grad_out[t]>; one warp per segment (LearnMask only).
@@ -879,6 +1140,89 @@ void pma_bwd_typed(const Shape& sh, bool fused, const void* go, const void* v, c
   }
 }
 
+
+// ---- stream-kernel dispatch ----------------------------------------------------------------------------------
+int stream_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ALLSET_STREAM");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v;
+}
+
+struct StreamPlan {
+  bool ok;
+  int lane_bytes, seg_per_warp, stages, rows_per_stage;
+  unsigned blocks;
+  size_t smem;
+};
+
+// Usable when a row is 128/256/512/1024 bytes (32 lanes x 4/8/16/32 B), rows are 16-byte aligned (bulk copies) and
+// there are enough segments that every warp gets a stream of several stages.
+StreamPlan plan_stream(int d, int elem_bytes, long long n_tgt, const void* x, const void* out, bool weighted) {
+  StreamPlan p{};
+  p.ok = false;
+  if (!stream_enabled()) return p;
+  const long long row_bytes = (long long)d * elem_bytes;
+  if (row_bytes != 128 && row_bytes != 256 && row_bytes != 512 && row_bytes != 1024) return p;
+  if (((uintptr_t)x % 16) != 0 || ((uintptr_t)out % 16) != 0) return p;
+  const long long chunks = 148LL * kStreamWarps * 8;          // ~8 waves of warps, one CTA per SM
+  long long spw = (n_tgt + chunks - 1) / chunks;
+  if (spw < 16) return p;                                    // small problem: the group kernel has more parallelism
+  p.lane_bytes = (int)(row_bytes / 32);
+  p.seg_per_warp = (int)spw;
+  p.rows_per_stage = (int)(kStreamStageBytes / row_bytes < 32 ? kStreamStageBytes / row_bytes : 32);
+  const size_t stage_bytes = (size_t)p.rows_per_stage * row_bytes;
+  int stages = (int)(ALLSET_STREAM_SMEM / (kStreamWarps * stage_bytes));
+  if (stages > 8) stages = 8;
+  if (stages < 2) return p;
+  p.stages = stages;
+  p.smem = (size_t)kStreamWarps * stages * stage_bytes + (size_t)kStreamWarps * stages * 8 +
+           (weighted ? (size_t)kStreamWarps * stages * p.rows_per_stage * 4 : 0) + 16;
+  const long long warps = (n_tgt + spw - 1) / spw;
+  p.blocks = (unsigned)((warps + kStreamWarps - 1) / kStreamWarps);
+  p.ok = true;
+  return p;
+}
+
+template <typename T, int LB, bool WEIGHTED>
+int launch_stream(const StreamPlan& p, const T* x, const int* rowptr, const int* col, const float* w,
+                  const float* sscale, long long n_tgt, int d, int mean, T* out, cudaStream_t st) {
+  auto kern = segreduce_stream_kernel<T, LB, WEIGHTED>;
+  static size_t configured = 0;                                 // per instantiation
+  if (configured < p.smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return fail(ALLSET_ECUDA, "segreduce_stream: smem opt-in: %s", cudaGetErrorString(e));
+    configured = p.smem;
+  }
+  kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(x, rowptr, col, w, sscale, n_tgt, d, mean, p.seg_per_warp,
+                                                    p.stages, out);
+  return ALLSET_OK;
+}
+
+template <typename T, bool WEIGHTED>
+int stream_by_width(const StreamPlan& p, const T* x, const int* rowptr, const int* col, const float* w,
+                    const float* sscale, long long n_tgt, int d, int mean, T* out, cudaStream_t st) {
+  switch (p.lane_bytes) {
+    case 4: return launch_stream<T, 4, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, st);
+    case 8: return launch_stream<T, 8, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, st);
+    case 16: return launch_stream<T, 16, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, st);
+    default: return launch_stream<T, 32, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, st);
+  }
+}
+
+template <typename T>
+int segreduce_stream_typed(const StreamPlan& p, const void* x, const int* rowptr, const int* col, const float* w,
+                           const float* sscale, long long n_tgt, int d, int mean, void* out, cudaStream_t st) {
+  const bool weighted = (w != nullptr) || (sscale != nullptr);
+  if (weighted)
+    return stream_by_width<T, true>(p, static_cast<const T*>(x), rowptr, col, w, sscale, n_tgt, d, mean,
+                                    static_cast<T*>(out), st);
+  return stream_by_width<T, false>(p, static_cast<const T*>(x), rowptr, col, w, sscale, n_tgt, d, mean,
+                                   static_cast<T*>(out), st);
+}
+
 bool bad_dtype(int dtype) { return dtype != ALLSET_F32 && dtype != ALLSET_BF16; }
 int elem_bytes(int dtype) { return dtype == ALLSET_F32 ? 4 : 2; }
 
@@ -975,6 +1319,16 @@ int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d, con
     if (n_src != 0) return fail(ALLSET_EINVAL, "segreduce_fwd: null x/col with n_src > 0");
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // The stream kernel handles every segment length itself (a long segment is just a long piece of one warp's
+  // stream), so it is used when no segment exceeds the caller's long-segment bucket.
+  const StreamPlan sp = plan_stream(d, elem_bytes(dtype), n_tgt, x, out, w != nullptr || src_scale != nullptr);
+  if (sp.ok && n_long == 0 && x != nullptr && col != nullptr) {
+    const int rc = dtype == ALLSET_F32
+        ? segreduce_stream_typed<float>(sp, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, out, st)
+        : segreduce_stream_typed<__nv_bfloat16>(sp, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, out, st);
+    if (rc != ALLSET_OK) return rc;
+    return check_launch("segreduce_fwd(stream)");
+  }
   const Shape sh = plan(d, elem_bytes(dtype), x, out);
   if (dtype == ALLSET_F32)
     segreduce_typed<float>(sh, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, long_ids, n_long,
