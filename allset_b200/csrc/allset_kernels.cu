@@ -344,10 +344,10 @@ __device__ __forceinline__ float div_count(float a, float c, float rc) {
 // unpack per lane group, and it removes the per-segment rowptr -> col -> row dependency chain that makes short
 // segments (E->V: ~6 incidences per vertex; real data: size-1 self-loop hyperedges) latency-bound.
 #ifndef ALLSET_STREAM_WARPS
-#define ALLSET_STREAM_WARPS 8
+#define ALLSET_STREAM_WARPS 24
 #endif
 #ifndef ALLSET_STREAM_STAGE_BYTES
-#define ALLSET_STREAM_STAGE_BYTES 8192
+#define ALLSET_STREAM_STAGE_BYTES 4096
 #endif
 #ifndef ALLSET_STREAM_SMEM
 #define ALLSET_STREAM_SMEM (192 * 1024)
@@ -369,6 +369,76 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+#ifndef ALLSET_L2_HINTS
+#define ALLSET_L2_HINTS 1
+#endif
+// L2 eviction policies (PMA kernel only; measured neutral-to-negative for the plain sum kernel): gathered feature
+// rows are streamed (evict_first) so that small, heavily re-read side records
+// (the per-row attention scores: |E| * H * 4 B = 64 MB in E->V, which fits the 126 MB L2) stay resident (evict_last).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+template <bool HINT>
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint64_t policy) {
+  if (HINT && ALLSET_L2_HINTS)
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(policy) : "memory");
+  else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// arrive on `bar` once every cp.async this thread has issued so far has landed (does not add to the pending count)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Stage `n` rows of `rowb` bytes: lane r holds the source row id of row r.  ALLSET_STREAM_COPY == 0: 16-byte
+// cp.async (LDGSTS) per lane, 512 contiguous shared bytes per warp instruction -- ~3 instructions per 256-byte row;
+// == 1: one cp.async.bulk (UBLKCP) per row.  UBLKCP takes its operands from UNIFORM registers, so the compiler
+// serialises per-lane bulk copies into a 9-instruction loop per row (measured: 36 % of all instructions of the sum
+// kernel, profiles/r01_stream_bulk_*.md), which is why LDGSTS is the default.
+#ifndef ALLSET_STREAM_COPY
+#define ALLSET_STREAM_COPY 0
+#endif
+constexpr int kStreamBarCount = ALLSET_STREAM_COPY == 0 ? 32 : 1;
+template <int ROWB, bool HINT>
+__device__ __forceinline__ void stage_rows(uint32_t dst, const unsigned char* __restrict__ src, int my_row_id, int n,
+                                           uint32_t bar, int lane, uint64_t policy) {
+#if ALLSET_STREAM_COPY == 0
+  constexpr int CPR = ROWB / 16;                      // 16-byte chunks per row
+  const int total = n * CPR;
+#pragma unroll 4
+  for (int q0 = 0; q0 < total; q0 += 32) {
+    const int q = q0 + lane;
+    const int row = q / CPR, ch = q % CPR;
+    const int idx = __shfl_sync(0xffffffffu, my_row_id, row & 31);
+    if (q < total) cp_async16<HINT>(dst + (uint32_t)q * 16u, src + (size_t)idx * ROWB + (size_t)ch * 16, policy);
+  }
+#else
+  if (lane < n) bulk_g2s(dst + (uint32_t)lane * ROWB, src + (size_t)my_row_id * ROWB, ROWB, bar);
+#endif
+}
+// same for a small per-row side record of `sb` bytes (sb % 16 == 0)
+__device__ __forceinline__ void stage_side(uint32_t dst, const unsigned char* __restrict__ src, int my_row_id, int n,
+                                           uint32_t sb, uint32_t bar, int lane, uint64_t policy) {
+#if ALLSET_STREAM_COPY == 0
+  const int cpr = (int)(sb / 16u);
+  const int total = n * cpr;
+  for (int q0 = 0; q0 < total; q0 += 32) {
+    const int q = q0 + lane;
+    const int row = q / cpr, ch = q % cpr;
+    const int idx = __shfl_sync(0xffffffffu, my_row_id, row & 31);
+    if (q < total) cp_async16<true>(dst + (uint32_t)q * 16u, src + (size_t)idx * sb + (size_t)ch * 16, policy);
+  }
+#else
+  if (lane < n) bulk_g2s(dst + (uint32_t)lane * sb, src + (size_t)my_row_id * sb, sb, bar);
+#endif
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
@@ -438,13 +508,14 @@ struct LaneRow {
           __nv_bfloat162 v = __floats2bfloat162_rn(acc[c * EPC + 2 * q], acc[c * EPC + 2 * q + 1]);
           o[q] = *reinterpret_cast<uint32_t*>(&v);
         }
-        if (CB == 16) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-        else if (CB == 8) *reinterpret_cast<uint2*>(dst) = make_uint2(o[0], o[1]);
-        else *reinterpret_cast<uint32_t*>(dst) = o[0];
+        // streaming stores (st.global.cs): output rows are written once and not re-read by this kernel
+        if (CB == 16) __stcs(reinterpret_cast<uint4*>(dst), make_uint4(o[0], o[1], o[2], o[3]));
+        else if (CB == 8) __stcs(reinterpret_cast<uint2*>(dst), make_uint2(o[0], o[1]));
+        else __stcs(reinterpret_cast<unsigned int*>(dst), o[0]);
       } else {
-        if (CB == 16) *reinterpret_cast<float4*>(dst) = make_float4(acc[c * EPC], acc[c * EPC + 1], acc[c * EPC + 2], acc[c * EPC + 3]);
-        else if (CB == 8) *reinterpret_cast<float2*>(dst) = make_float2(acc[c * EPC], acc[c * EPC + 1]);
-        else *reinterpret_cast<float*>(dst) = acc[c * EPC];
+        if (CB == 16) __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[c * EPC], acc[c * EPC + 1], acc[c * EPC + 2], acc[c * EPC + 3]));
+        else if (CB == 8) __stcs(reinterpret_cast<float2*>(dst), make_float2(acc[c * EPC], acc[c * EPC + 1]));
+        else __stcs(reinterpret_cast<float*>(dst), acc[c * EPC]);
       }
     }
   }
@@ -459,7 +530,6 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
   constexpr int NA = LR::NA;
   constexpr int ROWB = LB * 32;
   constexpr int RPS = (kStreamStageBytes / ROWB) < 32 ? (kStreamStageBytes / ROWB) : 32;   // rows per stage
-  constexpr int CUNR = RPS < 4 ? RPS : 4;                                                  // rows per consume step
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long s_first = ((long long)blockIdx.x * kStreamWarps + warp) * seg_per_warp;
@@ -470,22 +540,18 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
                         (uint32_t)warp * (uint32_t)stages * 8u;
   float* wbuf = reinterpret_cast<float*>(smem + (size_t)kStreamWarps * stages * (RPS * ROWB) +
                                          (size_t)kStreamWarps * stages * 8) + (size_t)warp * stages * RPS;
-  if (lane < stages) mbar_init(bars + lane * 8, 1);
+  if (lane < stages) mbar_init(bars + lane * 8, kStreamBarCount);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
 
   const int* __restrict__ rp = rowptr + s_first;
   const int kb = __ldg(rp), ke = __ldg(rp + nseg);
-  // window of 32 segment ends: lane j holds the end of segment wb + j; the next window is prefetched
-  int wb = 0;
-  int my_end = __ldg(rp + min(lane + 1, nseg));
-  int nxt_end = __ldg(rp + min(32 + lane + 1, nseg));
-
+  // segment cursor: end of the current segment and (prefetched, warp-uniform load) of the next one
   float acc[NA];
 #pragma unroll
   for (int i = 0; i < NA; ++i) acc[i] = 0.f;
   T* __restrict__ ob = out + (size_t)s_first * (size_t)d;
-  int seg = 0, cur_beg = kb, cur_end = __shfl_sync(0xffffffffu, my_end, 0), pos = kb;
+  int seg = 0, cur_beg = kb, cur_end = __ldg(rp + 1), nxt_end = __ldg(rp + min(2, nseg)), pos = kb;
 
   auto flush = [&]() {
     if (mean) {
@@ -499,14 +565,9 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.f;
     ++seg;
-    if ((seg & 31) == 0) {
-      wb += 32;
-      my_end = nxt_end;
-      nxt_end = __ldg(rp + min(wb + 32 + lane + 1, nseg));
-    }
     cur_beg = cur_end;
-    const int e = __shfl_sync(0xffffffffu, my_end, seg & 31);
-    cur_end = seg < nseg ? e : INT32_MAX;
+    cur_end = seg < nseg ? nxt_end : INT32_MAX;
+    nxt_end = __ldg(rp + min(seg + 2, nseg));
   };
 
   // ---- producer side ---------------------------------------------------------------------------------------
@@ -527,13 +588,15 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
   auto issue = [&](int st) {
     const int n = min(RPS, ke - ipos);
     const uint32_t bar = bars + st * 8;
+#if ALLSET_STREAM_COPY == 1
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)n * ROWB);
     __syncwarp();
-    if (lane < n) {
-      bulk_g2s(ring + (uint32_t)st * (RPS * ROWB) + (uint32_t)lane * ROWB,
-               reinterpret_cast<const unsigned char*>(x) + (size_t)pf_idx * ROWB, ROWB, bar);
-      if (WEIGHTED) wbuf[st * RPS + lane] = pf_w;
-    }
+#endif
+    stage_rows<ROWB, false>(ring + (uint32_t)st * (RPS * ROWB), reinterpret_cast<const unsigned char*>(x), pf_idx, n, bar, lane, 0ull);
+    if (WEIGHTED && lane < n) wbuf[st * RPS + lane] = pf_w;
+#if ALLSET_STREAM_COPY == 0
+    cp_async_arrive(bar);
+#endif
     ipos += RPS;
     prefetch();
   };
@@ -541,6 +604,8 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
   for (int st = 0; st < stages && ipos < ke; ++st) issue(st);
 
   // ---- consumer side ---------------------------------------------------------------------------------------
+  // invariant: pos < cur_end whenever a row is consumed (empty segments are flushed as soon as they are reached)
+  while (pos >= cur_end) flush();
   int st = 0;
   uint32_t phase = 0;
   for (int cbase = kb; cbase < ke; cbase += RPS) {
@@ -549,27 +614,256 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
     if (WEIGHTED) __syncwarp();
     const uint32_t rows = ring + (uint32_t)st * (RPS * ROWB);
     const float* wrow = wbuf + st * RPS;
-#pragma unroll 1
-    for (int r = 0; r < n; r += CUNR) {
-      if (r + CUNR <= n && cur_end - pos >= CUNR) {
+    if (n == RPS) {
+      // full stage: fully unrolled, one compare per row against the (stage-relative) end of the current segment
+      int rel = cur_end - cbase;
 #pragma unroll
-        for (int k = 0; k < CUNR; ++k) {
-          if (WEIGHTED) LR::add_weighted(rows + (r + k) * ROWB, lane, wrow[r + k], acc);
-          else LR::add(rows + (r + k) * ROWB, lane, acc);
+      for (int r = 0; r < RPS; ++r) {
+        if (WEIGHTED) LR::add_weighted(rows + r * ROWB, lane, wrow[r], acc);
+        else LR::add(rows + r * ROWB, lane, acc);
+        if (rel == r + 1) {
+          do {                                   // the segment ends with this row (then skip empty segments)
+            flush();
+            rel = cur_end - cbase;
+          } while (rel == r + 1);
         }
-        pos += CUNR;
-      } else {
-        for (int k = 0; k < CUNR && r + k < n; ++k) {
-          while (pos >= cur_end) flush();
-          if (WEIGHTED) LR::add_weighted(rows + (r + k) * ROWB, lane, wrow[r + k], acc);
-          else LR::add(rows + (r + k) * ROWB, lane, acc);
-          ++pos;
-        }
+      }
+      pos += RPS;
+    } else {
+      for (int r = 0; r < n; ++r) {
+        if (WEIGHTED) LR::add_weighted(rows + r * ROWB, lane, wrow[r], acc);
+        else LR::add(rows + r * ROWB, lane, acc);
+        ++pos;
+        while (pos >= cur_end) flush();
       }
     }
     __syncwarp();
     if (ipos < ke) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of this stage before the async refill
+      issue(st);
+    }
+    if (++st == stages) {
+      st = 0;
+      phase ^= 1u;
+    }
+  }
+  while (seg < nseg) flush();
+}
+
+// d{0,1} = a * b{0,1} + d{0,1}: one FFMA2 (sm_100 packed fp32, both halves rounded like scalar FFMA)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+  asm("{\n\t.reg .b64 pa, pb, pc;\n\tmov.b64 pa, {%2, %2};\n\tmov.b64 pb, {%3, %4};\n\tmov.b64 pc, {%0, %1};\n\t"
+      "fma.rn.f32x2 pc, pa, pb, pc;\n\tmov.b64 {%0, %1}, pc;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a) {
+  asm("{\n\t.reg .b64 pa, pc;\n\tmov.b64 pa, {%2, %2};\n\tmov.b64 pc, {%0, %1};\n\t"
+      "mul.rn.f32x2 pc, pc, pa;\n\tmov.b64 {%0, %1}, pc;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// PMA over the same TMA ring: every staged item is a value row (row_bytes) plus the H fp32 scores of that source row
+// (a second bulk copy onto the same mbarrier).  The online softmax runs per lane-chunk in the log2 domain
+// (a2 = leaky_relu(score) * log2(e); p = 2^(a2 - m2)), state (m2, l, acc) is flushed at segment boundaries:
+// out = acc / (l + 1e-16) + seed  (PyG softmax then scatter-add then += att_r, reference layers.py:168-194,153).
+template <typename T, int LB>
+__global__ void __launch_bounds__(kStreamWarps * 32, 1)
+pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, const float* __restrict__ seed,
+                  const int* __restrict__ rowptr, const int* __restrict__ col, long long n_tgt, int H, int C,
+                  float slope, int seg_per_warp, int stages, T* __restrict__ out, float* __restrict__ stats) {
+  using LR = LaneRow<T, LB>;
+  constexpr int ES = LR::ES, NA = LR::NA, CH = LR::CH, CB = LR::CB, EPC = LR::EPC;
+  constexpr int ROWB = LB * 32;
+  constexpr int RPS = (kStreamStageBytes / ROWB) < 32 ? (kStreamStageBytes / ROWB) : 32;
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long s_first = ((long long)blockIdx.x * kStreamWarps + warp) * seg_per_warp;
+  if (s_first >= n_tgt) return;
+  const int nseg = (int)min((long long)seg_per_warp, n_tgt - s_first);
+  const int d = H * C;
+  const uint32_t SB = (uint32_t)H * 4u;                                       // score bytes per row
+  const uint32_t ring = smem_u32(smem) + (uint32_t)warp * (uint32_t)stages * (RPS * ROWB);
+  const uint32_t sring = smem_u32(smem) + (uint32_t)kStreamWarps * (uint32_t)stages * (RPS * ROWB) +
+                         (uint32_t)warp * (uint32_t)stages * RPS * SB;
+  const uint32_t bars = smem_u32(smem) + (uint32_t)kStreamWarps * (uint32_t)stages * RPS * (ROWB + SB) +
+                        (uint32_t)warp * (uint32_t)stages * 8u;
+  if (lane < stages) mbar_init(bars + lane * 8, kStreamBarCount);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+
+  const int* __restrict__ rp = rowptr + s_first;
+  const int kb = __ldg(rp), ke = __ldg(rp + nseg);
+
+  int hc[CH];                                   // head of each of this lane's chunks
+  float sd[NA];                                 // seed slice of this lane
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int f0 = LR::offset(lane, c) / ES;
+    hc[c] = f0 / C;
+#pragma unroll
+    for (int i = 0; i < EPC; ++i) sd[c * EPC + i] = __ldg(seed + f0 + i);
+  }
+  float m2[CH], l[CH], acc[NA];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) { m2[c] = -INFINITY; l[c] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+  T* __restrict__ ob = out + (size_t)s_first * (size_t)d;
+  float* __restrict__ sb_out = stats != nullptr ? stats + (size_t)s_first * H * 2 : nullptr;
+  int seg = 0, cur_end = __ldg(rp + 1), nxt_end = __ldg(rp + min(2, nseg)), pos = kb;
+
+  auto flush = [&]() {
+    float o[NA];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const float denom = l[c] + 1e-16f;
+      const float inv = 1.0f / denom;
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) o[c * EPC + i] = fmaf(acc[c * EPC + i], inv, sd[c * EPC + i]);
+      if (sb_out != nullptr && (LR::offset(lane, c) / ES) % C == 0) {
+        sb_out[hc[c] * 2 + 0] = m2[c] * kLn2;
+        sb_out[hc[c] * 2 + 1] = denom;
+      }
+      m2[c] = -INFINITY;
+      l[c] = 0.f;
+    }
+    LR::store(ob, lane, o);
+    ob += d;
+    if (sb_out != nullptr) sb_out += 2 * H;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+    ++seg;
+    cur_end = seg < nseg ? nxt_end : INT32_MAX;
+    nxt_end = __ldg(rp + min(seg + 2, nseg));
+  };
+
+  // acc += p * row chunk c (unpack to fp32, packed FFMA2)
+  auto fma_chunk = [&](int c, const uint32_t (&r)[4], float p) {
+#pragma unroll
+    for (int q = 0; q < CB / 4; ++q) {
+      if (ES == 2) {
+        ffma2(acc[c * EPC + 2 * q], acc[c * EPC + 2 * q + 1], p, __uint_as_float(r[q] << 16),
+              __uint_as_float(r[q] & 0xffff0000u));
+      } else {
+        acc[c * EPC + q] = fmaf(p, __uint_as_float(r[q]), acc[c * EPC + q]);
+      }
+    }
+  };
+  auto load_chunk = [&](uint32_t rowaddr, int c, uint32_t (&r)[4]) {
+    const uint32_t a = rowaddr + LR::offset(lane, c);
+    if (CB == 16) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+    else if (CB == 8) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+    else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r[0]) : "r"(a));
+  };
+  // a2 (already leaky_relu'ed and scaled by log2 e in place, see the consumer loop) of row `scoreaddr`, head of chunk c
+  auto load_a2 = [&](uint32_t scoreaddr, int c) {
+    float a2;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(scoreaddr + (uint32_t)hc[c] * 4u));
+    return a2;
+  };
+
+  const uint64_t pol_rows = l2_policy_evict_first(), pol_side = l2_policy_evict_last();
+  int ipos = kb, pf_idx = 0;
+  auto prefetch = [&]() {
+    pf_idx = 0;
+    if (lane < RPS && ipos + lane < ke) pf_idx = __ldg(col + ipos + lane);
+  };
+  auto issue = [&](int st) {
+    const int n = min(RPS, ke - ipos);
+    const uint32_t bar = bars + st * 8;
+#if ALLSET_STREAM_COPY == 1
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)n * (ROWB + SB));
+    __syncwarp();
+#endif
+    stage_rows<ROWB, true>(ring + (uint32_t)st * (RPS * ROWB), reinterpret_cast<const unsigned char*>(v), pf_idx, n, bar, lane, pol_rows);
+    stage_side(sring + (uint32_t)st * RPS * SB, reinterpret_cast<const unsigned char*>(score), pf_idx, n, SB, bar, lane, pol_side);
+#if ALLSET_STREAM_COPY == 0
+    cp_async_arrive(bar);
+#endif
+    ipos += RPS;
+    prefetch();
+  };
+  prefetch();
+  for (int st = 0; st < stages && ipos < ke; ++st) issue(st);
+
+  int st = 0;
+  uint32_t phase = 0;
+  for (int cbase = kb; cbase < ke; cbase += RPS) {
+    const int n = min(RPS, ke - cbase);
+    mbar_wait(bars + st * 8, phase);
+    const uint32_t rows = ring + (uint32_t)st * (RPS * ROWB);
+    const uint32_t scs = sring + (uint32_t)st * RPS * SB;
+    // scores of the stage -> a2 = leaky_relu(score) * log2(e), in place, each (row, head) once (not once per lane)
+    for (int i = lane; i < (n * H) / 4; i += 32) {
+      float4 sc;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w) : "r"(scs + (uint32_t)i * 16u));
+      sc.x = leaky(sc.x, slope) * kLog2e; sc.y = leaky(sc.y, slope) * kLog2e;
+      sc.z = leaky(sc.z, slope) * kLog2e; sc.w = leaky(sc.w, slope) * kLog2e;
+      asm volatile("st.shared.v4.f32 [%4], {%0,%1,%2,%3};" ::"f"(sc.x), "f"(sc.y), "f"(sc.z), "f"(sc.w), "r"(scs + (uint32_t)i * 16u) : "memory");
+    }
+    __syncwarp();
+    int r = 0;
+    while (r < n) {
+      while (pos >= cur_end) flush();
+      const int plen = min(n - r, cur_end - pos);          // rows of the current segment inside this stage
+      const uint32_t prow = rows + (uint32_t)r * ROWB, psc = scs + (uint32_t)r * SB;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        // pass 1: piece max
+        float pm = -INFINITY;
+        int k = 0;
+        for (; k + 4 <= plen; k += 4) {
+          const float a0 = load_a2(psc + (k + 0) * SB, c), a1 = load_a2(psc + (k + 1) * SB, c);
+          const float a2v = load_a2(psc + (k + 2) * SB, c), a3 = load_a2(psc + (k + 3) * SB, c);
+          pm = fmaxf(fmaxf(pm, fmaxf(a0, a1)), fmaxf(a2v, a3));
+        }
+        for (; k < plen; ++k) pm = fmaxf(pm, load_a2(psc + k * SB, c));
+        // one rescale of the carried state per piece
+        const float mn = fmaxf(m2[c], pm);
+        const float cf = ex2_approx(m2[c] - mn);            // 2^-inf = 0 for the first piece of a segment
+        m2[c] = mn;
+        float lc = l[c] * cf;
+#pragma unroll
+        for (int i = 0; i < EPC; i += 2) {
+          if (EPC >= 2) fmul2(acc[c * EPC + i], acc[c * EPC + i + 1], cf);
+          else acc[c * EPC + i] *= cf;
+        }
+        // pass 2: weights and weighted sum
+        k = 0;
+        for (; k + 2 <= plen; k += 2) {
+          uint32_t r0[4], r1[4];
+          load_chunk(prow + (k + 0) * ROWB, c, r0);
+          load_chunk(prow + (k + 1) * ROWB, c, r1);
+          const float p0 = ex2_approx(load_a2(psc + (k + 0) * SB, c) - mn);
+          const float p1 = ex2_approx(load_a2(psc + (k + 1) * SB, c) - mn);
+          lc += p0;
+          fma_chunk(c, r0, p0);
+          lc += p1;
+          fma_chunk(c, r1, p1);
+        }
+        if (k < plen) {
+          uint32_t r0[4];
+          load_chunk(prow + k * ROWB, c, r0);
+          const float p0 = ex2_approx(load_a2(psc + k * SB, c) - mn);
+          lc += p0;
+          fma_chunk(c, r0, p0);
+        }
+        l[c] = lc;
+      }
+      r += plen;
+      pos += plen;
+    }
+    __syncwarp();
+    if (ipos < ke) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       issue(st);
     }
     if (++st == stages) {
@@ -1223,6 +1517,36 @@ int segreduce_stream_typed(const StreamPlan& p, const void* x, const int* rowptr
                                    static_cast<T*>(out), st);
 }
 
+template <typename T, int LB>
+int launch_pma_stream(const StreamPlan& p, const T* v, const float* score, const float* seed, const int* rowptr,
+                      const int* col, long long n_tgt, int H, int C, float slope, T* out, float* stats,
+                      cudaStream_t st) {
+  auto kern = pma_stream_kernel<T, LB>;
+  static size_t configured = 0;
+  if (configured < p.smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return fail(ALLSET_ECUDA, "pma_stream: smem opt-in: %s", cudaGetErrorString(e));
+    configured = p.smem;
+  }
+  kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(v, score, seed, rowptr, col, n_tgt, H, C, slope, p.seg_per_warp,
+                                                    p.stages, out, stats);
+  return ALLSET_OK;
+}
+
+template <typename T>
+int pma_stream_typed(const StreamPlan& p, const void* v, const float* score, const float* seed, const int* rowptr,
+                     const int* col, long long n_tgt, int H, int C, float slope, void* out, float* stats,
+                     cudaStream_t st) {
+  const T* vi = static_cast<const T*>(v);
+  T* oi = static_cast<T*>(out);
+  switch (p.lane_bytes) {
+    case 4: return launch_pma_stream<T, 4>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, st);
+    case 8: return launch_pma_stream<T, 8>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, st);
+    case 16: return launch_pma_stream<T, 16>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, st);
+    default: return launch_pma_stream<T, 32>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, st);
+  }
+}
+
 bool bad_dtype(int dtype) { return dtype != ALLSET_F32 && dtype != ALLSET_BF16; }
 int elem_bytes(int dtype) { return dtype == ALLSET_F32 ? 4 : 2; }
 
@@ -1373,6 +1697,26 @@ int allset_pma_fwd(const void* v, const float* score, const float* seed, int dty
     return fail(ALLSET_EINVAL, "pma_fwd: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int d = H * C;
+  {
+    // stream kernel: scores travel as one H*4-byte bulk copy per row (needs H % 4 == 0 and 16-byte alignment) and a
+    // lane's chunk must not straddle two heads
+    StreamPlan sp = plan_stream(d, elem_bytes(dtype), n_tgt, v, out, false);
+    if (sp.ok) {
+      const int chunk_elems = (sp.lane_bytes >= 16 ? 16 : sp.lane_bytes) / elem_bytes(dtype);
+      const size_t stage_rows = (size_t)kStreamWarps * sp.stages * sp.rows_per_stage;
+      sp.smem += stage_rows * (size_t)H * 4;
+      if (H % 4 != 0 || C % chunk_elems != 0 || ((uintptr_t)score % 16) != 0 || sp.smem > 227 * 1024 ||
+          n_long != 0 || v == nullptr || col == nullptr || score == nullptr)
+        sp.ok = false;
+    }
+    if (sp.ok) {
+      const int rc = dtype == ALLSET_F32
+          ? pma_stream_typed<float>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, st)
+          : pma_stream_typed<__nv_bfloat16>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, st);
+      if (rc != ALLSET_OK) return rc;
+      return check_launch("pma_fwd(stream)");
+    }
+  }
   Shape sh = plan(d, elem_bytes(dtype), v, out);
   if (sh.vector && C % (16 / elem_bytes(dtype)) != 0) {   // a 16-byte chunk would straddle two heads
     sh.vector = false;

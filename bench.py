@@ -344,7 +344,7 @@ def run_b200(a):
     t_ve, t_ge, t_ev, t_gv = ph
     achieved = (b_ve + b_ev) / ((t_ve + t_ev) * 1e-3) / 1e9
     roofline = {
-        'bound': 'hbm', 'kernel': 'segreduce_group_kernel<bf16,16B chunks>' if a.dtype == 'bf16' else 'segreduce_group_kernel<f32>',
+        'bound': 'hbm', 'kernel': 'segreduce_stream_kernel<%s> (cp.async-staged segmented gather-reduce; both directions launch it)' % a.dtype,
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
         'peak_source': peak_src,
         'bytes_per_launch': (b_ve + b_ev) / 2, 'avg_launch_ms': (t_ve + t_ev) / 2,

@@ -14,7 +14,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'
   --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/ncu_launches.log 2>&1
 tail -3 $OUT/ncu_launches.log
 echo "== ncu full (segreduce)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:segreduce_group -s 2 -c 2 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'segreduce_stream|segreduce_group' -s 2 -c 2 \
   -o $OUT/prof_segreduce -f python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-pma > $OUT/ncu_full.log 2>&1
 tail -3 $OUT/ncu_full.log
 ls -la $OUT

@@ -13,6 +13,17 @@ def main():
     dt = torch.bfloat16 if os.environ.get('KB_DTYPE', 'bf16') == 'bf16' else torch.float32
     es = 2 if dt == torch.bfloat16 else 4
     dev = torch.device('cuda:0')
+    torch.zeros(1, device=dev)
+    if os.environ.get('KB_L2_FETCH'):
+        import ctypes, glob
+        cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), 'lib', 'libcudart*.so*')) + glob.glob('/usr/local/cuda/lib64/libcudart.so*')
+        rt = ctypes.CDLL(cands[0])
+        val = ctypes.c_size_t(0)
+        rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+        rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ['KB_L2_FETCH'])))
+        val2 = ctypes.c_size_t(0)
+        rt.cudaDeviceGetLimit(ctypes.byref(val2), 5)
+        print('L2 fetch granularity: was', val.value, 'set rc', rc, 'now', val2.value, 'via', cands[0], flush=True)
     ei = synthetic.poisson_hypergraph(Nv, Me, mean, seed=1234, device=dev)
     v2e = allset_b200.Incidence.from_coo(ei[0], ei[1] - Nv, n_src=Nv, n_tgt=Me)
     del ei
@@ -37,7 +48,9 @@ def main():
         ('pma_v2e', lambda: sh.v2e_pma(x_v, sv, seed, H, x_e), synthetic.algorithmic_bytes(nnz, Me, d, es, heads=H)),
         ('pma_e2v', lambda: sh.e2v_pma(x_e, se, seed, H, x_v2), synthetic.algorithmic_bytes(nnz, Nv, d, es, heads=H)),
     ):
-        ms = timeit(fn)
+        if os.environ.get('KB_ONLY') and name not in os.environ['KB_ONLY'].split(','):
+            continue
+        ms = timeit(fn, int(os.environ.get('KB_ITERS', '20')))
         res[name] = {'ms': round(ms, 4), 'gbs': round(b / ms / 1e6, 1), 'frac': round(b / ms / 1e6 / 6464.9, 4)}
     print(json.dumps(res), flush=True)
 

@@ -365,9 +365,32 @@ def _full_size_checks(n, m, mean_size, d, heads):
     ref = O.aggregate_sum_mean(x.float().cpu(), sub_src, sub_tgt, None, 'sum')
     torch.testing.assert_close(xe[:ref.shape[0]].cpu(), ref, **FP32)
     vv = x
-    ref_p, _ = O.aggregate_pma(vv.float().cpu().view(n, heads, -1), score.cpu(), seed.cpu(), sub_src, sub_tgt)
+    ref_p, ref_alpha = O.aggregate_pma(vv.float().cpu().view(n, heads, -1), score.cpu(), seed.cpu(), sub_src, sub_tgt)
     out_p, _ = ab().pma_aggregate(vv, score, seed, v2e, heads)
     torch.testing.assert_close(out_p[:ref_p.shape[0]].float().cpu(), ref_p.reshape(ref_p.shape[0], -1), **BF16)
+    # fp32 storage (the 1e-4 bar) incl. attention weights, and the weighted / mean sum kernels, same spot check
+    out_p32, alpha32 = ab().pma_aggregate(vv.float(), score, seed, v2e, heads, return_alpha=True)
+    torch.testing.assert_close(out_p32[:ref_p.shape[0]].cpu(), ref_p.reshape(ref_p.shape[0], -1), **FP32)
+    torch.testing.assert_close(alpha32[sel].cpu(), ref_alpha, **FP32)
+    del out_p32, alpha32
+    wts = torch.rand(nnz, device=dev()) + 0.5
+    for reduce in ('sum', 'mean'):
+        got = ab().segment_reduce(x.float(), v2e, wts, reduce)
+        want_w = O.aggregate_sum_mean(x.float().cpu(), sub_src, sub_tgt, wts[sel].cpu(), reduce)
+        torch.testing.assert_close(got[:want_w.shape[0]].cpu(), want_w, **FP32)
+    got = ab().segment_reduce(x, v2e, None, 'mean')
+    want_m = O.aggregate_sum_mean(x.float().cpu(), sub_src, sub_tgt, None, 'mean')
+    torch.testing.assert_close(got[:want_m.shape[0]].float().cpu(), want_m, **BF16)
+    # E->V direction (short segments, many flushes) against the oracle on the first 5000 vertices
+    xe32 = xe
+    selv = ei[0] < 5000
+    want_v = O.aggregate_sum_mean(xe32.cpu(), he[selv].cpu(), ei[0][selv].cpu(), None, 'sum')
+    got_v = ab().segment_reduce(xe32, e2v, None, 'sum')
+    torch.testing.assert_close(got_v[:want_v.shape[0]].cpu(), want_v, rtol=1e-4, atol=1e-3)
+    score_e = torch.randn(m, heads, device=dev())
+    ref_pv, _ = O.aggregate_pma(xe32.cpu().view(m, heads, -1), score_e.cpu(), seed.cpu(), he[selv].cpu(), ei[0][selv].cpu())
+    got_pv, _ = ab().pma_aggregate(xe32, score_e, seed, e2v, heads)
+    torch.testing.assert_close(got_pv[:ref_pv.shape[0]].cpu(), ref_pv.reshape(ref_pv.shape[0], -1), rtol=1e-4, atol=1e-3)
 
 
 def test_full_size_config3_properties():
