@@ -20,6 +20,7 @@ ABI_VERSION = 1
 
 F32, BF16 = 0, 1
 SUM, MEAN = 0, 1
+EUNSUPPORTED = -5
 
 _c = ctypes
 _p = _c.c_void_p
@@ -35,9 +36,13 @@ SIGNATURES = {
     'allset_long_segments': (_c.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
     'allset_segreduce_fwd': (_c.c_int, [_p, _c.c_int, _i64, _i32, _p, _p, _p, _p, _i64, _c.c_int,
                                         _p, _i32, _i32, _p, _p]),
+    'allset_segreduce_fwd_bcast': (_c.c_int, [_p, _c.c_int, _i64, _i32, _p, _p, _p, _p, _i64, _c.c_int,
+                                              _p, _c.POINTER(_c.c_void_p), _i32, _p]),
     'allset_segreduce_bwd_w': (_c.c_int, [_p, _p, _c.c_int, _i32, _p, _p, _p, _i64, _p, _p]),
     'allset_pma_fwd': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
                                   _p, _i32, _i32, _p, _p, _p]),
+    'allset_pma_fwd_bcast': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
+                                        _p, _p, _c.POINTER(_c.c_void_p), _i32, _p]),
     'allset_pma_alpha': (_c.c_int, [_p, _p, _i32, _f32, _p, _p, _i64, _p, _p]),
     'allset_rowdot_heads': (_c.c_int, [_p, _p, _p, _c.c_int, _i64, _i32, _i32, _p, _p]),
     'allset_pma_bwd': (_c.c_int, [_p, _p, _p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
@@ -172,6 +177,66 @@ def segreduce_fwd(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tg
         _check(lib().allset_segreduce_fwd(_ptr(x), _dtype_code(x), n_src, d, _ptr(rowptr), _ptr(col), _ptr(w),
                                           _ptr(src_scale), n_tgt, MEAN if mean else SUM, _ptr(long_ids), n_long,
                                           long_threshold, _ptr(out), _stream()), 'allset_segreduce_fwd')
+    return out
+
+
+class Unsupported(RuntimeError):
+    """The fused-exchange variant does not handle this shape; fall back to the plain call + an all-gather."""
+
+
+def _peer_array(peer_ptrs):
+    arr = (_c.c_void_p * max(len(peer_ptrs), 1))()
+    for i, q in enumerate(peer_ptrs):
+        arr[i] = int(q)
+    return arr
+
+
+def segreduce_fwd_bcast(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, mean: bool,
+                        out: torch.Tensor, peer_ptrs, w: Optional[torch.Tensor] = None,
+                        src_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """segreduce_fwd whose epilogue also stores every reduced row into the same row of each peer replica.
+    `out` = this rank's row range inside its own replica; `peer_ptrs` = addresses (ints, peer-mapped device pointers)
+    of that same row range in the other ranks' replicas.  Raises Unsupported for shapes the stream kernel rejects."""
+    _need(x, 'x')
+    _need(rowptr, 'rowptr', torch.int32)
+    _need(col, 'col', torch.int32)
+    _need(out, 'out', x.dtype)
+    _need(w, 'w', torch.float32, optional=True)
+    _need(src_scale, 'src_scale', torch.float32, optional=True)
+    n_src, d = x.shape
+    if tuple(out.shape) != (n_tgt, d):
+        raise ValueError('out must be [n_tgt, d]')
+    if n_tgt == 0:
+        return out
+    with torch.cuda.device(x.device):
+        code = lib().allset_segreduce_fwd_bcast(_ptr(x), _dtype_code(x), n_src, d, _ptr(rowptr), _ptr(col), _ptr(w),
+                                                _ptr(src_scale), n_tgt, MEAN if mean else SUM, _ptr(out),
+                                                _peer_array(peer_ptrs), len(peer_ptrs), _stream())
+    if code == EUNSUPPORTED:
+        raise Unsupported(lib().allset_last_error().decode())
+    _check(code, 'allset_segreduce_fwd_bcast')
+    return out
+
+
+def pma_fwd_bcast(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: int, C: int, slope: float,
+                  rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, out: torch.Tensor, peer_ptrs,
+                  stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(v, 'v')
+    _need(score, 'score', torch.float32)
+    _need(seed, 'seed', torch.float32)
+    _need(out, 'out', v.dtype)
+    _need(stats, 'stats', torch.float32, optional=True)
+    if tuple(out.shape) != (n_tgt, H * C):
+        raise ValueError('out must be [n_tgt, H*C]')
+    if n_tgt == 0:
+        return out
+    with torch.cuda.device(v.device):
+        code = lib().allset_pma_fwd_bcast(_ptr(v), _ptr(score), _ptr(seed), _dtype_code(v), H, C, float(slope),
+                                          _ptr(rowptr), _ptr(col), n_tgt, _ptr(out), _ptr(stats),
+                                          _peer_array(peer_ptrs), len(peer_ptrs), _stream())
+    if code == EUNSUPPORTED:
+        raise Unsupported(lib().allset_last_error().decode())
+    _check(code, 'allset_pma_fwd_bcast')
     return out
 
 

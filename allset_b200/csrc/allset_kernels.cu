@@ -521,11 +521,19 @@ struct LaneRow {
   }
 };
 
+// Fused exchange: besides `out`, every reduced row is also stored into the same row of up to 7 peer replicas
+// (peer-mapped device pointers: NVLink P2P stores, fire-and-forget), so the all-gather that would follow the kernel
+// rides on its epilogue.  delta[j] = byte distance from `out` row 0 to the same row in peer j's buffer.
+struct PeerOuts {
+  long long delta[7];
+  int n;
+};
+
 template <typename T, int LB, bool WEIGHTED>
 __global__ void __launch_bounds__(kStreamWarps * 32, 1)
 segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                         const float* __restrict__ w, const float* __restrict__ sscale, long long n_tgt, int d,
-                        int mean, int seg_per_warp, int stages, T* __restrict__ out) {
+                        int mean, int seg_per_warp, int stages, T* __restrict__ out, PeerOuts peers) {
   using LR = LaneRow<T, LB>;
   constexpr int NA = LR::NA;
   constexpr int ROWB = LB * 32;
@@ -561,6 +569,8 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
       for (int i = 0; i < NA; ++i) acc[i] = div_count(acc[i], cnt, rc);
     }
     LR::store(ob, lane, acc);
+    for (int j = 0; j < peers.n; ++j)
+      LR::store(reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ob) + peers.delta[j]), lane, acc);
     ob += d;
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.f;
@@ -677,7 +687,8 @@ template <typename T, int LB>
 __global__ void __launch_bounds__(kStreamWarps * 32, 1)
 pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, const float* __restrict__ seed,
                   const int* __restrict__ rowptr, const int* __restrict__ col, long long n_tgt, int H, int C,
-                  float slope, int seg_per_warp, int stages, T* __restrict__ out, float* __restrict__ stats) {
+                  float slope, int seg_per_warp, int stages, T* __restrict__ out, float* __restrict__ stats,
+                  PeerOuts peers) {
   using LR = LaneRow<T, LB>;
   constexpr int ES = LR::ES, NA = LR::NA, CH = LR::CH, CB = LR::CB, EPC = LR::EPC;
   constexpr int ROWB = LB * 32;
@@ -736,6 +747,8 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
       l[c] = 0.f;
     }
     LR::store(ob, lane, o);
+    for (int j = 0; j < peers.n; ++j)
+      LR::store(reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ob) + peers.delta[j]), lane, o);
     ob += d;
     if (sb_out != nullptr) sb_out += 2 * H;
 #pragma unroll
@@ -1482,7 +1495,8 @@ StreamPlan plan_stream(int d, int elem_bytes, long long n_tgt, const void* x, co
 
 template <typename T, int LB, bool WEIGHTED>
 int launch_stream(const StreamPlan& p, const T* x, const int* rowptr, const int* col, const float* w,
-                  const float* sscale, long long n_tgt, int d, int mean, T* out, cudaStream_t st) {
+                  const float* sscale, long long n_tgt, int d, int mean, T* out, const PeerOuts& peers,
+                  cudaStream_t st) {
   auto kern = segreduce_stream_kernel<T, LB, WEIGHTED>;
   static size_t configured = 0;                                 // per instantiation
   if (configured < p.smem) {
@@ -1491,36 +1505,52 @@ int launch_stream(const StreamPlan& p, const T* x, const int* rowptr, const int*
     configured = p.smem;
   }
   kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(x, rowptr, col, w, sscale, n_tgt, d, mean, p.seg_per_warp,
-                                                    p.stages, out);
+                                                    p.stages, out, peers);
   return ALLSET_OK;
 }
 
 template <typename T, bool WEIGHTED>
 int stream_by_width(const StreamPlan& p, const T* x, const int* rowptr, const int* col, const float* w,
-                    const float* sscale, long long n_tgt, int d, int mean, T* out, cudaStream_t st) {
+                    const float* sscale, long long n_tgt, int d, int mean, T* out, const PeerOuts& peers,
+                    cudaStream_t st) {
   switch (p.lane_bytes) {
-    case 4: return launch_stream<T, 4, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, st);
-    case 8: return launch_stream<T, 8, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, st);
-    case 16: return launch_stream<T, 16, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, st);
-    default: return launch_stream<T, 32, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, st);
+    case 4: return launch_stream<T, 4, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, st);
+    case 8: return launch_stream<T, 8, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, st);
+    case 16: return launch_stream<T, 16, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, st);
+    default: return launch_stream<T, 32, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, st);
   }
 }
 
 template <typename T>
 int segreduce_stream_typed(const StreamPlan& p, const void* x, const int* rowptr, const int* col, const float* w,
-                           const float* sscale, long long n_tgt, int d, int mean, void* out, cudaStream_t st) {
+                           const float* sscale, long long n_tgt, int d, int mean, void* out, const PeerOuts& peers,
+                           cudaStream_t st) {
   const bool weighted = (w != nullptr) || (sscale != nullptr);
   if (weighted)
     return stream_by_width<T, true>(p, static_cast<const T*>(x), rowptr, col, w, sscale, n_tgt, d, mean,
-                                    static_cast<T*>(out), st);
+                                    static_cast<T*>(out), peers, st);
   return stream_by_width<T, false>(p, static_cast<const T*>(x), rowptr, col, w, sscale, n_tgt, d, mean,
-                                   static_cast<T*>(out), st);
+                                   static_cast<T*>(out), peers, st);
+}
+
+// peer_outs[j] = address, in peer j's replica, of the row that `out` row 0 is -> byte deltas relative to `out`
+int make_peers(void* out, void* const* peer_outs, int n_peers, PeerOuts* po) {
+  po->n = 0;
+  if (n_peers < 0 || n_peers > 7) return fail(ALLSET_EINVAL, "at most 7 peer replicas (got %d)", n_peers);
+  if (n_peers > 0 && peer_outs == nullptr) return fail(ALLSET_EINVAL, "peer_outs is null");
+  for (int j = 0; j < n_peers; ++j) {
+    if (peer_outs[j] == nullptr || ((uintptr_t)peer_outs[j] % 16) != 0)
+      return fail(ALLSET_EINVAL, "peer_outs[%d] is null or not 16-byte aligned", j);
+    po->delta[j] = (long long)((intptr_t)peer_outs[j] - (intptr_t)out);
+  }
+  po->n = n_peers;
+  return ALLSET_OK;
 }
 
 template <typename T, int LB>
 int launch_pma_stream(const StreamPlan& p, const T* v, const float* score, const float* seed, const int* rowptr,
                       const int* col, long long n_tgt, int H, int C, float slope, T* out, float* stats,
-                      cudaStream_t st) {
+                      const PeerOuts& peers, cudaStream_t st) {
   auto kern = pma_stream_kernel<T, LB>;
   static size_t configured = 0;
   if (configured < p.smem) {
@@ -1529,21 +1559,21 @@ int launch_pma_stream(const StreamPlan& p, const T* v, const float* score, const
     configured = p.smem;
   }
   kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(v, score, seed, rowptr, col, n_tgt, H, C, slope, p.seg_per_warp,
-                                                    p.stages, out, stats);
+                                                    p.stages, out, stats, peers);
   return ALLSET_OK;
 }
 
 template <typename T>
 int pma_stream_typed(const StreamPlan& p, const void* v, const float* score, const float* seed, const int* rowptr,
                      const int* col, long long n_tgt, int H, int C, float slope, void* out, float* stats,
-                     cudaStream_t st) {
+                     const PeerOuts& peers, cudaStream_t st) {
   const T* vi = static_cast<const T*>(v);
   T* oi = static_cast<T*>(out);
   switch (p.lane_bytes) {
-    case 4: return launch_pma_stream<T, 4>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, st);
-    case 8: return launch_pma_stream<T, 8>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, st);
-    case 16: return launch_pma_stream<T, 16>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, st);
-    default: return launch_pma_stream<T, 32>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, st);
+    case 4: return launch_pma_stream<T, 4>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st);
+    case 8: return launch_pma_stream<T, 8>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st);
+    case 16: return launch_pma_stream<T, 16>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st);
+    default: return launch_pma_stream<T, 32>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st);
   }
 }
 
@@ -1627,10 +1657,10 @@ int allset_long_segments(const int32_t* rowptr, int64_t n_tgt, int32_t threshold
   return check_launch("long_segments");
 }
 
-int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d, const int32_t* rowptr,
-                         const int32_t* col, const float* w, const float* src_scale, int64_t n_tgt, int op,
-                         const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out,
-                         void* stream) {
+static int segreduce_fwd_impl(const void* x, int dtype, int64_t n_src, int32_t d, const int32_t* rowptr,
+                              const int32_t* col, const float* w, const float* src_scale, int64_t n_tgt, int op,
+                              const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out,
+                              void* const* peer_outs, int32_t n_peers, void* stream) {
   if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "segreduce_fwd: unknown dtype %d", dtype);
   if (op != ALLSET_SUM && op != ALLSET_MEAN) return fail(ALLSET_EINVAL, "segreduce_fwd: unknown op %d", op);
   if (d <= 0 || n_tgt < 0 || n_src < 0 || n_long < 0) return fail(ALLSET_EINVAL, "segreduce_fwd: bad size");
@@ -1646,13 +1676,19 @@ int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d, con
   // The stream kernel handles every segment length itself (a long segment is just a long piece of one warp's
   // stream), so it is used when no segment exceeds the caller's long-segment bucket.
   const StreamPlan sp = plan_stream(d, elem_bytes(dtype), n_tgt, x, out, w != nullptr || src_scale != nullptr);
+  PeerOuts peers;
+  if (int rc = make_peers(out, peer_outs, n_peers, &peers)) return rc;
   if (sp.ok && n_long == 0 && x != nullptr && col != nullptr) {
     const int rc = dtype == ALLSET_F32
-        ? segreduce_stream_typed<float>(sp, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, out, st)
-        : segreduce_stream_typed<__nv_bfloat16>(sp, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, out, st);
+        ? segreduce_stream_typed<float>(sp, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, out, peers, st)
+        : segreduce_stream_typed<__nv_bfloat16>(sp, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, out, peers, st);
     if (rc != ALLSET_OK) return rc;
     return check_launch("segreduce_fwd(stream)");
   }
+  if (n_peers > 0)
+    return fail(ALLSET_EUNSUPPORTED, "segreduce_fwd_bcast: shape not eligible for the fused-exchange stream kernel "
+                                     "(row bytes %lld, %lld segments, %d long); use segreduce_fwd + an all-gather",
+                (long long)d * elem_bytes(dtype), (long long)n_tgt, (int)n_long);
   const Shape sh = plan(d, elem_bytes(dtype), x, out);
   if (dtype == ALLSET_F32)
     segreduce_typed<float>(sh, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, long_ids, n_long,
@@ -1661,6 +1697,21 @@ int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d, con
     segreduce_typed<__nv_bfloat16>(sh, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, long_ids, n_long,
                                    long_threshold, out, st);
   return check_launch("segreduce_fwd");
+}
+
+int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d, const int32_t* rowptr,
+                         const int32_t* col, const float* w, const float* src_scale, int64_t n_tgt, int op,
+                         const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out,
+                         void* stream) {
+  return segreduce_fwd_impl(x, dtype, n_src, d, rowptr, col, w, src_scale, n_tgt, op, long_ids, n_long,
+                            long_threshold, out, nullptr, 0, stream);
+}
+
+int allset_segreduce_fwd_bcast(const void* x, int dtype, int64_t n_src, int32_t d, const int32_t* rowptr,
+                               const int32_t* col, const float* w, const float* src_scale, int64_t n_tgt, int op,
+                               void* out, void* const* peer_outs, int32_t n_peers, void* stream) {
+  return segreduce_fwd_impl(x, dtype, n_src, d, rowptr, col, w, src_scale, n_tgt, op, nullptr, 0, 0, out, peer_outs,
+                            n_peers, stream);
 }
 
 int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32_t d, const int32_t* rowptr,
@@ -1684,10 +1735,10 @@ int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32
   return check_launch("segreduce_bwd_w");
 }
 
-int allset_pma_fwd(const void* v, const float* score, const float* seed, int dtype, int32_t H, int32_t C,
-                   float slope, const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
-                   const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out, float* stats,
-                   void* stream) {
+static int pma_fwd_impl(const void* v, const float* score, const float* seed, int dtype, int32_t H, int32_t C,
+                        float slope, const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
+                        const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out, float* stats,
+                        void* const* peer_outs, int32_t n_peers, void* stream) {
   if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "pma_fwd: unknown dtype %d", dtype);
   if (H <= 0 || C <= 0 || n_tgt < 0 || n_long < 0) return fail(ALLSET_EINVAL, "pma_fwd: bad size");
   if (!(slope > 0.f)) return fail(ALLSET_EINVAL, "pma_fwd: negative_slope must be > 0");
@@ -1709,13 +1760,18 @@ int allset_pma_fwd(const void* v, const float* score, const float* seed, int dty
           n_long != 0 || v == nullptr || col == nullptr || score == nullptr)
         sp.ok = false;
     }
+    PeerOuts peers;
+    if (int rc = make_peers(out, peer_outs, n_peers, &peers)) return rc;
     if (sp.ok) {
       const int rc = dtype == ALLSET_F32
-          ? pma_stream_typed<float>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, st)
-          : pma_stream_typed<__nv_bfloat16>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, st);
+          ? pma_stream_typed<float>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, peers, st)
+          : pma_stream_typed<__nv_bfloat16>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, peers, st);
       if (rc != ALLSET_OK) return rc;
       return check_launch("pma_fwd(stream)");
     }
+    if (n_peers > 0)
+      return fail(ALLSET_EUNSUPPORTED, "pma_fwd_bcast: shape not eligible for the fused-exchange stream kernel; use "
+                                       "pma_fwd + an all-gather");
   }
   Shape sh = plan(d, elem_bytes(dtype), v, out);
   if (sh.vector && C % (16 / elem_bytes(dtype)) != 0) {   // a 16-byte chunk would straddle two heads
@@ -1736,6 +1792,21 @@ int allset_pma_fwd(const void* v, const float* score, const float* seed, int dty
     else launch_pma_fwd<__nv_bfloat16, false>(sh, vi, score, seed, rowptr, col, n_tgt, H, C, slope, long_ids, n_long, long_threshold, oi, stats, st);
   }
   return check_launch("pma_fwd");
+}
+
+int allset_pma_fwd(const void* v, const float* score, const float* seed, int dtype, int32_t H, int32_t C,
+                   float slope, const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
+                   const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out, float* stats,
+                   void* stream) {
+  return pma_fwd_impl(v, score, seed, dtype, H, C, slope, rowptr, col, n_tgt, long_ids, n_long, long_threshold, out,
+                      stats, nullptr, 0, stream);
+}
+
+int allset_pma_fwd_bcast(const void* v, const float* score, const float* seed, int dtype, int32_t H, int32_t C,
+                         float slope, const int32_t* rowptr, const int32_t* col, int64_t n_tgt, void* out,
+                         float* stats, void* const* peer_outs, int32_t n_peers, void* stream) {
+  return pma_fwd_impl(v, score, seed, dtype, H, C, slope, rowptr, col, n_tgt, nullptr, 0, 0, out, stats, peer_outs,
+                      n_peers, stream);
 }
 
 int allset_pma_alpha(const float* score, const float* stats, int32_t H, float slope, const int32_t* rowptr,

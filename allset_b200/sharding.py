@@ -96,6 +96,30 @@ def choose_ranges(rowptr: torch.Tensor, parts: int, row_weight: int = 0, toleran
     return balanced_ranges(rowptr, parts, row_weight)
 
 
+class ReplicatedRows(object):
+    """A [rows, d] feature buffer replicated on every rank of the group, allocated in SYMMETRIC memory
+    (torch.distributed._symmetric_memory) so that each rank holds peer-mapped pointers to all replicas: the fused
+    kernels store the rows they reduce straight into every replica over NVLink.  `barrier()` orders those stores
+    before the next reader (stream-ordered device-side barrier on the symmetric-memory signal pads)."""
+
+    def __init__(self, rows: int, d: int, dtype: torch.dtype, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.tensor = symm.empty((rows, d), dtype=dtype, device=device)
+        self.handle = symm.rendezvous(self.tensor, self.group)
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        self.ptrs = [int(q) for q in self.handle.buffer_ptrs]
+        self.row_bytes = d * self.tensor.element_size()
+
+    def peer_ptrs(self, first_row: int):
+        """Addresses of row `first_row` in every OTHER rank's replica."""
+        return [q + first_row * self.row_bytes for r, q in enumerate(self.ptrs) if r != self.rank]
+
+    def barrier(self):
+        self.handle.barrier(channel=0)
+
+
 class ShardedIncidence(object):
     """One rank's share of a hypergraph: the hyperedge range it reduces in V->E and the vertex range it reduces in
     E->V, as slices of the two CSRs of a full `Incidence` (every rank holds the full index; features are what is
@@ -127,51 +151,90 @@ class ShardedIncidence(object):
 
     # -- AllDeepSets ------------------------------------------------------------------------------------------
     def _reduce(self, csr, x_src, out_full, lo, hi, mean):
+        """Reduce this rank's target range into rows [lo, hi) of the replicated buffer.  `out_full` is a plain tensor
+        (exchange = a later all-gather) or a ReplicatedRows (exchange fused into the kernel's epilogue).  Returns True
+        when the exchange has already been issued by the kernel."""
         from . import _lib
+        if isinstance(out_full, ReplicatedRows) and self.world > 1 and csr.long_ids is None:
+            try:
+                _lib.segreduce_fwd_bcast(x_src, csr.rowptr, csr.col, csr.n_tgt, mean, out_full.tensor[lo:hi],
+                                         out_full.peer_ptrs(lo))
+                return True
+            except _lib.Unsupported:
+                pass
+        t = out_full.tensor if isinstance(out_full, ReplicatedRows) else out_full
         _lib.segreduce_fwd(x_src, csr.rowptr, csr.col, csr.n_tgt, mean, long_ids=csr.long_ids,
-                           long_threshold=csr.long_threshold, out=out_full[lo:hi])
+                           long_threshold=csr.long_threshold, out=t[lo:hi])
+        return False
 
     def v2e_reduce(self, x_v, x_e_full, mean: bool = False):
-        self._reduce(self.e_csr, x_v, x_e_full, self.e_lo, self.e_hi, mean)
+        return self._reduce(self.e_csr, _plain(x_v), x_e_full, self.e_lo, self.e_hi, mean)
 
     def e2v_reduce(self, x_e, x_v_full, mean: bool = False):
-        self._reduce(self.v_csr, x_e, x_v_full, self.v_lo, self.v_hi, mean)
+        return self._reduce(self.v_csr, _plain(x_e), x_v_full, self.v_lo, self.v_hi, mean)
 
     # -- AllSetTransformer ------------------------------------------------------------------------------------
     def _pma(self, csr, v, score, seed, heads, out_full, lo, hi, slope):
         from . import _lib
-        _lib.pma_fwd(v, score, seed, heads, v.shape[1] // heads, slope, csr.rowptr, csr.col, csr.n_tgt,
-                     want_stats=False, long_ids=csr.long_ids, long_threshold=csr.long_threshold, out=out_full[lo:hi])
+        C = v.shape[1] // heads
+        if isinstance(out_full, ReplicatedRows) and self.world > 1 and csr.long_ids is None:
+            try:
+                _lib.pma_fwd_bcast(v, score, seed, heads, C, slope, csr.rowptr, csr.col, csr.n_tgt,
+                                   out_full.tensor[lo:hi], out_full.peer_ptrs(lo))
+                return True
+            except _lib.Unsupported:
+                pass
+        t = out_full.tensor if isinstance(out_full, ReplicatedRows) else out_full
+        _lib.pma_fwd(v, score, seed, heads, C, slope, csr.rowptr, csr.col, csr.n_tgt, want_stats=False,
+                     long_ids=csr.long_ids, long_threshold=csr.long_threshold, out=t[lo:hi])
+        return False
 
     def v2e_pma(self, v_v, score_v, seed, heads, out_e_full, slope: float = 0.2):
-        self._pma(self.e_csr, v_v, score_v, seed, heads, out_e_full, self.e_lo, self.e_hi, slope)
+        return self._pma(self.e_csr, _plain(v_v), score_v, seed, heads, out_e_full, self.e_lo, self.e_hi, slope)
 
     def e2v_pma(self, v_e, score_e, seed, heads, out_v_full, slope: float = 0.2):
-        self._pma(self.v_csr, v_e, score_e, seed, heads, out_v_full, self.v_lo, self.v_hi, slope)
+        return self._pma(self.v_csr, _plain(v_e), score_e, seed, heads, out_v_full, self.v_lo, self.v_hi, slope)
 
     # -- exchanges --------------------------------------------------------------------------------------------
-    def gather_e(self, x_e_full):
-        if self.world > 1:
-            allgather_rows(x_e_full, self.e_ranges, self.rank, self.group)
+    def gather_e(self, x_e_full, fused: bool = False):
+        """Complete the exchange of hyperedge rows: a barrier when the kernel already stored into the peers (fused),
+        an NCCL all-gather otherwise."""
+        self._gather(x_e_full, self.e_ranges, fused)
 
-    def gather_v(self, x_v_full):
-        if self.world > 1:
-            allgather_rows(x_v_full, self.v_ranges, self.rank, self.group)
+    def gather_v(self, x_v_full, fused: bool = False):
+        self._gather(x_v_full, self.v_ranges, fused)
+
+    def _gather(self, full, ranges, fused):
+        if self.world == 1:
+            return
+        if fused and isinstance(full, ReplicatedRows):
+            full.barrier()
+        else:
+            allgather_rows(full.tensor if isinstance(full, ReplicatedRows) else full, ranges, self.rank, self.group)
 
     def launches_per_pair(self) -> int:
         """Kernels of this library launched by one V->E + E->V pair on this rank."""
         return 2 + (self.e_csr.long_ids is not None) + (self.v_csr.long_ids is not None)
 
-    def layer_pair_sum(self, x_v, x_e_full, x_v_new_full, mean: bool = False):
-        self.v2e_reduce(x_v, x_e_full, mean)
-        self.gather_e(x_e_full)
-        self.e2v_reduce(x_e_full, x_v_new_full, mean)
-        self.gather_v(x_v_new_full)
+    def layer_pair_sum(self, x_v, x_e_full, x_v_new_full, mean: bool = False, replicate_v: bool = True):
+        """V->E, exchange X_e, E->V and (replicate_v) exchange the updated X_v so that another layer can follow.
+        With replicate_v=False the result stays vertex-sharded (rows [v_lo, v_hi) valid on this rank): enough when the
+        next operator is row-parallel, e.g. SetGNN's classifier after the last layer."""
+        self.gather_e(x_e_full, self.v2e_reduce(x_v, x_e_full, mean))
+        if replicate_v:
+            self.gather_v(x_v_new_full, self.e2v_reduce(x_e_full, x_v_new_full, mean))
+        else:
+            self.e2v_reduce(x_e_full, _plain(x_v_new_full), mean)
         return x_v_new_full
 
-    def layer_pair_pma(self, v_v, score_v, score_e, seed, heads, out_e_full, out_v_full):
-        self.v2e_pma(v_v, score_v, seed, heads, out_e_full)
-        self.gather_e(out_e_full)
-        self.e2v_pma(out_e_full, score_e, seed, heads, out_v_full)
-        self.gather_v(out_v_full)
+    def layer_pair_pma(self, v_v, score_v, score_e, seed, heads, out_e_full, out_v_full, replicate_v: bool = True):
+        self.gather_e(out_e_full, self.v2e_pma(v_v, score_v, seed, heads, out_e_full))
+        if replicate_v:
+            self.gather_v(out_v_full, self.e2v_pma(out_e_full, score_e, seed, heads, out_v_full))
+        else:
+            self.e2v_pma(out_e_full, score_e, seed, heads, _plain(out_v_full))
         return out_v_full
+
+
+def _plain(t):
+    return t.tensor if isinstance(t, ReplicatedRows) else t

@@ -56,6 +56,10 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-pma', action='store_true')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'fused', 'nccl'],
+                    help='N>1: fused = P2P stores from the kernel epilogue into symmetric memory; nccl = all-gather after')
+    ap.add_argument('--replicate-xv', action='store_true',
+                    help='N>1: also replicate the updated X_v inside every step (needed only when another layer follows)')
     return ap.parse_args()
 
 
@@ -221,8 +225,25 @@ def run_b200(a):
     torch.cuda.empty_cache()
 
     x_v = synthetic.features(Nv, d, dtype, seed=a.seed, device=dev)
-    x_e = torch.empty((Me, d), dtype=dtype, device=dev)
-    x_v2 = torch.empty((Nv, d), dtype=dtype, device=dev)
+    exchange = 'none'
+    x_e = x_v2 = None
+    if world > 1 and a.exchange in ('auto', 'fused'):
+        try:
+            x_e = sharding.ReplicatedRows(Me, d, dtype, dev)
+            x_v2 = sharding.ReplicatedRows(Nv, d, dtype, dev)
+            exchange = 'fused P2P stores from the kernel epilogue into symmetric memory + device barrier'
+        except Exception as e:  # noqa
+            if a.exchange == 'fused':
+                raise
+            if rank == 0:
+                sys.stderr.write('symmetric memory unavailable (%r); falling back to NCCL all-gather\n' % (e,))
+            x_e = x_v2 = None
+    if x_e is None:
+        x_e = torch.empty((Me, d), dtype=dtype, device=dev)
+        x_v2 = torch.empty((Nv, d), dtype=dtype, device=dev)
+        if world > 1:
+            exchange = 'NCCL all-gather after the kernel'
+    plain = sharding._plain
 
     def barrier():
         if world > 1:
@@ -255,15 +276,18 @@ def run_b200(a):
         phases = [max_over_ranks(sum(m[i].elapsed_time(m[i + 1]) for m in marks) / steps) for i in range(n_phases)]
         return total_ms, phases
 
+    replicate = [a.replicate_xv]
+
     def sum_step(marks):
         if marks: marks[0].record()
-        sh.v2e_reduce(x_v, x_e)
+        fe = sh.v2e_reduce(x_v, x_e)
         if marks: marks[1].record()
-        sh.gather_e(x_e)
+        sh.gather_e(x_e, fe)
         if marks: marks[2].record()
-        sh.e2v_reduce(x_e, x_v2)
+        fv = sh.e2v_reduce(x_e, x_v2 if replicate[0] else plain(x_v2))
         if marks: marks[3].record()
-        sh.gather_v(x_v2)
+        if replicate[0]:
+            sh.gather_v(x_v2, fv)
         if marks: marks[4].record()
 
     sampler = ClockSampler(local_rank)
@@ -271,6 +295,32 @@ def run_b200(a):
     total_ms, ph = timed_steps(sum_step, 4, a.steps, a.warmup)
     ms_per_step = total_ms / a.steps
     value = Me / (ms_per_step * 1e-3)
+    verified = None
+    if world > 1:
+        # every rank holds the full graph: recompute the pair unsharded and compare bit for bit (the per-segment
+        # summation order does not depend on the partition)
+        replicate[0] = True
+        sum_step(None)
+        t, sgl = v2e.by_tgt, v2e.by_src
+        ref_e = _lib.segreduce_fwd(x_v, t.rowptr, t.col, t.n_tgt, False, long_ids=t.long_ids, long_threshold=t.long_threshold)
+        ref_v = _lib.segreduce_fwd(ref_e, sgl.rowptr, sgl.col, sgl.n_tgt, False, long_ids=sgl.long_ids, long_threshold=sgl.long_threshold)
+        ok = bool(torch.equal(plain(x_e), ref_e)) and bool(torch.equal(plain(x_v2), ref_v))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        verified = bool(flag.item())
+        del ref_e, ref_v
+        replicate[0] = a.replicate_xv
+        if not verified:
+            raise RuntimeError('sharded V->E/E->V result differs from the unsharded one')
+    other = None
+    if world > 1:                                  # the other exchange mode, reported beside the headline
+        replicate[0] = not a.replicate_xv
+        o_ms, o_ph = timed_steps(sum_step, 4, max(5, a.steps // 2), 2)
+        o_steps = max(5, a.steps // 2)
+        other = {'replicate_xv': replicate[0], 'value': Me / (o_ms / o_steps * 1e-3), 'unit': UNIT,
+                 'ms_per_step': o_ms / o_steps,
+                 'phases_ms': {'v2e': o_ph[0], 'exchange_x_e': o_ph[1], 'e2v': o_ph[2], 'exchange_x_v': o_ph[3]}}
+        replicate[0] = a.replicate_xv
 
     # ---- end to end through the public API: host-resident features in, result read back, every step -------------
     e2e = None
@@ -306,7 +356,7 @@ def run_b200(a):
                 res = allset_b200.segment_reduce(xe, inc_e2v, None, 'sum')
                 res.record_stream(s_out)
             else:
-                sh.layer_pair_sum(x_in[b], x_e, xv_out[b])
+                sh.layer_pair_sum(x_in[b], x_e, xv_out[b], replicate_v=False)
                 res = xv_out[b][sh.v_lo:sh.v_hi]                             # each rank reads back the rows it owns
             ev = torch.cuda.Event(); ev.record(cur); state['comp_done'][b] = ev
             with torch.cuda.stream(s_out):
@@ -351,13 +401,14 @@ def run_b200(a):
 
         def pma_step(marks):
             if marks: marks[0].record()
-            sh.v2e_pma(x_v, score_v, seed, H, x_e)
+            fe = sh.v2e_pma(x_v, score_v, seed, H, x_e)
             if marks: marks[1].record()
-            sh.gather_e(x_e)
+            sh.gather_e(x_e, fe)
             if marks: marks[2].record()
-            sh.e2v_pma(x_e, score_e, seed, H, x_v2)
+            fv = sh.e2v_pma(x_e, score_e, seed, H, x_v2 if replicate[0] else plain(x_v2))
             if marks: marks[3].record()
-            sh.gather_v(x_v2)
+            if replicate[0]:
+                sh.gather_v(x_v2, fv)
             if marks: marks[4].record()
 
         p_ms, pph = timed_steps(pma_step, 4, a.steps, a.warmup)
@@ -366,7 +417,7 @@ def run_b200(a):
         b_ve = synthetic.algorithmic_bytes(nnz_e, sh.e_hi - sh.e_lo, d, es, heads=H)
         b_ev = synthetic.algorithmic_bytes(nnz_v, sh.v_hi - sh.v_lo, d, es, heads=H)
         pma = {'value': Me / (p_ms / a.steps * 1e-3), 'unit': UNIT, 'heads': H, 'ms_per_step': p_ms / a.steps,
-               'v2e_ms': pph[0], 'e2v_ms': pph[2], 'gather_e_ms': pph[1], 'gather_v_ms': pph[3],
+               'v2e_ms': pph[0], 'e2v_ms': pph[2], 'exchange_x_e_ms': pph[1], 'exchange_x_v_ms': pph[3],
                'v2e_gbs': b_ve / (pph[0] * 1e-3) / 1e9, 'e2v_gbs': b_ev / (pph[2] * 1e-3) / 1e9}
         del score_v, score_e
 
@@ -413,7 +464,10 @@ def run_b200(a):
             'dtype': a.dtype, 'data': 'synthetic',
             'config': {'workload': workload_name(a), 'nodes': Nv, 'hyperedges': Me, 'nnz': nnz, 'd': d,
                        'seed': a.seed, 'parallelism': 'single GPU' if world == 1 else
-                       'hyperedge-sharded V->E / vertex-sharded E->V x%d, NCCL all-gather of X_e and X_v per step' % world,
+                       'hyperedge-sharded V->E / vertex-sharded E->V x%d; X_e exchanged between the directions every '
+                       'step; updated X_v %s' % (world, 'replicated every step (another layer can follow)' if a.replicate_xv
+                                                else 'left vertex-sharded (last layer: the next op is row-parallel); see other_mode'),
+                       'exchange': exchange,
                        'l2': 'inputs larger than L2 (X_v %.2f GB, col %.2f GB per step; no flush)'
                              % (Nv * d * es / 1e9, nnz * 4 / 1e9)},
             'clocks': clocks,
@@ -421,7 +475,9 @@ def run_b200(a):
             'gpu_launches': sh.launches_per_pair() * a.steps,
             'roofline': roofline,
             'cpu_baseline': cpu_baseline,
-            'phases_ms': {'v2e': t_ve, 'allgather_x_e': t_ge, 'e2v': t_ev, 'allgather_x_v': t_gv},
+            'phases_ms': {'v2e': t_ve, 'exchange_x_e': t_ge, 'e2v': t_ev, 'exchange_x_v': t_gv},
+            'other_mode': other, 'sharded_equals_unsharded': verified,
+            'v2e_only': {'value': Me / (t_ve * 1e-3), 'unit': UNIT, 'note': 'the collective-free V->E segmented reduce alone'},
             'incidence_visits_per_s': 2 * nnz / (ms_per_step * 1e-3),
             'pma': pma,
         }

@@ -44,7 +44,8 @@ enum {
   ALLSET_EINVAL = -1,   /* bad argument (null pointer, negative size, unknown enum) */
   ALLSET_ERANGE = -2,   /* size does not fit the int32 CSR (nnz or rows >= 2^31) */
   ALLSET_EWORKSPACE = -3, /* workspace too small */
-  ALLSET_ECUDA = -4     /* CUDA launch / runtime error (text in allset_last_error) */
+  ALLSET_ECUDA = -4,    /* CUDA launch / runtime error (text in allset_last_error) */
+  ALLSET_EUNSUPPORTED = -5 /* shape not handled by the requested (fused-exchange) variant; use the plain call */
 };
 
 /* ABI version of the loaded library (== ALLSET_ABI_VERSION it was built with). */
@@ -89,6 +90,21 @@ int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d,
                          const int32_t* long_ids, int32_t n_long, int32_t long_threshold,
                          void* out, void* stream);
 
+/* Fused compute + exchange (multi-GPU, one process per GPU; no counterpart in the single-device reference).
+ * Same reduction as allset_segreduce_fwd, but every reduced row is ALSO stored, from the kernel's epilogue, into the
+ * same row of `n_peers` (<= 7) peer replicas over NVLink (P2P stores), so the all-gather of the rank's row range that
+ * would follow the kernel costs no extra launch and overlaps the reduce.
+ *   out          this rank's rows inside its own replica (row 0 of the rank's range)
+ *   peer_outs    HOST array of n_peers peer-mapped DEVICE pointers: the address of that same row in each peer replica
+ * The caller must order a cross-rank barrier after the kernel before any rank reads the gathered rows.
+ * Returns ALLSET_EUNSUPPORTED when the shape is not eligible for the stream kernel (row bytes not in
+ * {128,256,512,1024}, too few segments): call allset_segreduce_fwd and all-gather instead. */
+int allset_segreduce_fwd_bcast(const void* x, int dtype, int64_t n_src, int32_t d,
+                               const int32_t* rowptr, const int32_t* col,
+                               const float* w, const float* src_scale,
+                               int64_t n_tgt, int op,
+                               void* out, void* const* peer_outs, int32_t n_peers, void* stream);
+
 /* Gradient w.r.t. the per-incidence weights (SetGNN.LearnMask, src/models.py:451-452):
  * grad_w[k] = tgt_scale[t] * <x[col[k], :], grad_out[t, :]>  for k in segment t (CSR order).
  * tgt_scale [n_tgt] fp32 or NULL (mean: 1/max(count,1)). */
@@ -111,6 +127,12 @@ int allset_pma_fwd(const void* v, const float* score, const float* seed, int dty
                    const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
                    const int32_t* long_ids, int32_t n_long, int32_t long_threshold,
                    void* out, float* stats, void* stream);
+
+/* allset_pma_fwd with the fused exchange of allset_segreduce_fwd_bcast (same contract for out / peer_outs). */
+int allset_pma_fwd_bcast(const void* v, const float* score, const float* seed, int dtype,
+                         int32_t H, int32_t C, float slope,
+                         const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
+                         void* out, float* stats, void* const* peer_outs, int32_t n_peers, void* stream);
 
 /* Attention weights per incidence in CSR order (PMA.forward(return_attention_weights=True),
  * src/layers.py:159-166): alpha[k, h] for k in segment t from score and stats. */
