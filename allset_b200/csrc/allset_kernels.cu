@@ -529,7 +529,15 @@ struct PeerOuts {
   int n;
 };
 
-template <typename T, int LB, bool WEIGHTED>
+// static indexing only (a dynamically indexed by-value struct would be copied to local memory)
+template <typename T, typename LR, int NA>
+__device__ __forceinline__ void store_to_peers(T* ob, const PeerOuts& peers, int lane, const float (&acc)[NA]) {
+#pragma unroll
+  for (int j = 0; j < 7; ++j)
+    if (j < peers.n) LR::store(reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ob) + peers.delta[j]), lane, acc);
+}
+
+template <typename T, int LB, bool WEIGHTED, bool BCAST>
 __global__ void __launch_bounds__(kStreamWarps * 32, 1)
 segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                         const float* __restrict__ w, const float* __restrict__ sscale, long long n_tgt, int d,
@@ -569,8 +577,7 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
       for (int i = 0; i < NA; ++i) acc[i] = div_count(acc[i], cnt, rc);
     }
     LR::store(ob, lane, acc);
-    for (int j = 0; j < peers.n; ++j)
-      LR::store(reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ob) + peers.delta[j]), lane, acc);
+    if (BCAST) store_to_peers<T, LR, NA>(ob, peers, lane, acc);
     ob += d;
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.f;
@@ -624,8 +631,9 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
     if (WEIGHTED) __syncwarp();
     const uint32_t rows = ring + (uint32_t)st * (RPS * ROWB);
     const float* wrow = wbuf + st * RPS;
-    if (n == RPS) {
+    if (!BCAST && n == RPS) {
       // full stage: fully unrolled, one compare per row against the (stage-relative) end of the current segment
+      // (the fused-exchange variant keeps a single flush site: its epilogue stores to up to 8 replicas)
       int rel = cur_end - cbase;
 #pragma unroll
       for (int r = 0; r < RPS; ++r) {
@@ -683,7 +691,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // (a second bulk copy onto the same mbarrier).  The online softmax runs per lane-chunk in the log2 domain
 // (a2 = leaky_relu(score) * log2(e); p = 2^(a2 - m2)), state (m2, l, acc) is flushed at segment boundaries:
 // out = acc / (l + 1e-16) + seed  (PyG softmax then scatter-add then += att_r, reference layers.py:168-194,153).
-template <typename T, int LB>
+template <typename T, int LB, bool BCAST>
 __global__ void __launch_bounds__(kStreamWarps * 32, 1)
 pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, const float* __restrict__ seed,
                   const int* __restrict__ rowptr, const int* __restrict__ col, long long n_tgt, int H, int C,
@@ -747,8 +755,7 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
       l[c] = 0.f;
     }
     LR::store(ob, lane, o);
-    for (int j = 0; j < peers.n; ++j)
-      LR::store(reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ob) + peers.delta[j]), lane, o);
+    if (BCAST) store_to_peers<T, LR, NA>(ob, peers, lane, o);
     ob += d;
     if (sb_out != nullptr) sb_out += 2 * H;
 #pragma unroll
@@ -1497,7 +1504,20 @@ template <typename T, int LB, bool WEIGHTED>
 int launch_stream(const StreamPlan& p, const T* x, const int* rowptr, const int* col, const float* w,
                   const float* sscale, long long n_tgt, int d, int mean, T* out, const PeerOuts& peers,
                   cudaStream_t st) {
-  auto kern = segreduce_stream_kernel<T, LB, WEIGHTED>;
+  if (peers.n > 0) {
+    if (WEIGHTED) return fail(ALLSET_EUNSUPPORTED, "segreduce_fwd_bcast: per-incidence weights are not supported");
+    auto kern = segreduce_stream_kernel<T, LB, false, true>;
+    static size_t configured = 0;                               // per instantiation
+    if (configured < p.smem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+      if (e != cudaSuccess) return fail(ALLSET_ECUDA, "segreduce_stream: smem opt-in: %s", cudaGetErrorString(e));
+      configured = p.smem;
+    }
+    kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(x, rowptr, col, w, sscale, n_tgt, d, mean, p.seg_per_warp,
+                                                      p.stages, out, peers);
+    return ALLSET_OK;
+  }
+  auto kern = segreduce_stream_kernel<T, LB, WEIGHTED, false>;
   static size_t configured = 0;                                 // per instantiation
   if (configured < p.smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
@@ -1551,12 +1571,13 @@ template <typename T, int LB>
 int launch_pma_stream(const StreamPlan& p, const T* v, const float* score, const float* seed, const int* rowptr,
                       const int* col, long long n_tgt, int H, int C, float slope, T* out, float* stats,
                       const PeerOuts& peers, cudaStream_t st) {
-  auto kern = pma_stream_kernel<T, LB>;
-  static size_t configured = 0;
-  if (configured < p.smem) {
+  static size_t configured[2] = {0, 0};
+  const int b = peers.n > 0 ? 1 : 0;
+  auto kern = b ? pma_stream_kernel<T, LB, true> : pma_stream_kernel<T, LB, false>;
+  if (configured[b] < p.smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return fail(ALLSET_ECUDA, "pma_stream: smem opt-in: %s", cudaGetErrorString(e));
-    configured = p.smem;
+    configured[b] = p.smem;
   }
   kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(v, score, seed, rowptr, col, n_tgt, H, C, slope, p.seg_per_warp,
                                                     p.stages, out, stats, peers);
