@@ -1481,9 +1481,12 @@ StreamPlan plan_stream(int d, int elem_bytes, long long n_tgt, const void* x, co
   const long long row_bytes = (long long)d * elem_bytes;
   if (row_bytes != 128 && row_bytes != 256 && row_bytes != 512 && row_bytes != 1024) return p;
   if (((uintptr_t)x % 16) != 0 || ((uintptr_t)out % 16) != 0) return p;
-  const long long chunks = 148LL * kStreamWarps * 8;          // ~8 waves of warps, one CTA per SM
+  // >= 16 segments per warp (a stream of several stages), ~8 waves of warps (one CTA per SM) when the graph is large
+  // enough, never less than one full wave -- below that the group kernel has more parallelism
+  const long long chunks = 148LL * kStreamWarps * 8;
   long long spw = (n_tgt + chunks - 1) / chunks;
-  if (spw < 16) return p;                                    // small problem: the group kernel has more parallelism
+  if (spw < 16) spw = 16;
+  if (n_tgt < 148LL * kStreamWarps * spw) return p;
   p.lane_bytes = (int)(row_bytes / 32);
   p.seg_per_warp = (int)spw;
   p.rows_per_stage = (int)(kStreamStageBytes / row_bytes < 32 ? kStreamStageBytes / row_bytes : 32);

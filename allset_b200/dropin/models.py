@@ -1,0 +1,10 @@
+"""Drop-in `models` module: `SetGNN` is the B200-native one (same ctor / forward / state_dict as reference
+src/models.py:295-484); the ten baseline models are forwarded from the reference unchanged."""
+import os as _os
+import sys as _sys
+
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))))
+from allset_b200.dropin._forward import load_reference as _load, public_names as _names  # noqa: E402
+
+globals().update(_names(_load('models')))
+from allset_b200.models import SetGNN  # noqa: E402,F401

@@ -417,3 +417,91 @@ def test_powerlaw_long_segments_config5_shape():
     outm = ab().segment_reduce(x.float(), v2e, None, 'mean')
     refm = O.aggregate_sum_mean(x.float().cpu(), ei[0].cpu(), he.cpu(), None, 'mean')
     torch.testing.assert_close(outm.cpu(), refm, **FP32)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused compute + exchange (multi-GPU kernels), exercised on ONE device: the "peer replicas" are other buffers
+# ------------------------------------------------------------------------------------------------------------
+def test_fused_exchange_stores_every_replica():
+    from allset_b200 import _lib, sharding, synthetic
+    n, m, d, heads = 400_000, 200_000, 128, 8
+    ei = synthetic.poisson_hypergraph(n, m, 8, seed=7, device=dev())
+    v2e = ab().Incidence.from_coo(ei[0], ei[1] - n, n_src=n, n_tgt=m)
+    x = synthetic.features(n, d, torch.bfloat16, seed=3, device=dev())
+    t = v2e.by_tgt
+    ref = _lib.segreduce_fwd(x, t.rowptr, t.col, m, False)
+    # this "rank" owns hyperedges [lo, hi); three replicas of the full buffer
+    lo, hi = 50_000, 200_000
+    rp, col, _ = sharding.slice_csr(t.rowptr, t.col, lo, hi)
+    mine = torch.zeros(m, d, dtype=torch.bfloat16, device=dev())
+    peers = [torch.zeros_like(mine) for _ in range(2)]
+    _lib.segreduce_fwd_bcast(x, rp, col, hi - lo, False, mine[lo:hi], [p[lo:hi].data_ptr() for p in peers])
+    for buf in [mine] + peers:
+        assert torch.equal(buf[lo:hi], ref[lo:hi]) and bool((buf[:lo] == 0).all())
+    # mean + PMA variants
+    refm = _lib.segreduce_fwd(x, t.rowptr, t.col, m, True)
+    _lib.segreduce_fwd_bcast(x, rp, col, hi - lo, True, mine[lo:hi], [peers[0][lo:hi].data_ptr()])
+    assert torch.equal(mine[lo:hi], refm[lo:hi]) and torch.equal(peers[0][lo:hi], refm[lo:hi])
+    score = torch.randn(n, heads, device=dev())
+    seed = torch.randn(d, device=dev())
+    refp, _ = _lib.pma_fwd(x, score, seed, heads, d // heads, 0.2, t.rowptr, t.col, m, want_stats=False)
+    _lib.pma_fwd_bcast(x, score, seed, heads, d // heads, 0.2, rp, col, hi - lo, mine[lo:hi],
+                       [p[lo:hi].data_ptr() for p in peers])
+    for buf in [mine] + peers:
+        assert torch.equal(buf[lo:hi], refp[lo:hi])
+    # shapes the stream kernel does not take are refused, not silently mishandled
+    with pytest.raises(_lib.Unsupported):
+        xs = torch.randn(1000, 20, device=dev())
+        rp2 = torch.arange(0, 1001, dtype=torch.int32, device=dev())
+        col2 = torch.arange(0, 1000, dtype=torch.int32, device=dev())
+        out2 = torch.empty(1000, 20, device=dev())
+        _lib.segreduce_fwd_bcast(xs, rp2, col2, 1000, False, out2, [out2.data_ptr()])
+
+
+def _mp_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    d_ = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=d_)
+    try:
+        import allset_b200
+        from allset_b200 import _lib, sharding, synthetic
+        n, m, d = 600_000, 320_000, 128
+        ei = synthetic.poisson_hypergraph(n, m, 6, seed=5, device=d_)
+        v2e = allset_b200.Incidence.from_coo(ei[0], ei[1] - n, n_src=n, n_tgt=m)
+        sh = sharding.ShardedIncidence(v2e, rank, world)
+        x = synthetic.features(n, d, torch.bfloat16, seed=2, device=d_)
+        results = {}
+        for mode in ('nccl', 'fused'):
+            if mode == 'fused':
+                x_e, x_v2 = sharding.ReplicatedRows(m, d, torch.bfloat16, d_), sharding.ReplicatedRows(n, d, torch.bfloat16, d_)
+            else:
+                x_e, x_v2 = torch.empty(m, d, dtype=torch.bfloat16, device=d_), torch.empty(n, d, dtype=torch.bfloat16, device=d_)
+            sh.layer_pair_sum(x, x_e, x_v2)
+            torch.cuda.synchronize()
+            results[mode] = (sharding._plain(x_e).clone(), sharding._plain(x_v2).clone())
+        t, s = v2e.by_tgt, v2e.by_src
+        ref_e = _lib.segreduce_fwd(x, t.rowptr, t.col, m, False)
+        ref_v = _lib.segreduce_fwd(ref_e, s.rowptr, s.col, n, False)
+        ok = all(torch.equal(results[k][0], ref_e) and torch.equal(results[k][1], ref_v) for k in results)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_sharded_layer_pair_two_gpus_nccl_and_fused():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
