@@ -211,6 +211,72 @@ def variant_cases(mods):
     return out
 
 
+def preprocessing_cases(mods):
+    """Inputs / outputs of the reference's own ExtractV2E, Add_Self_Loops, norm_contruction (preprocessing.py:394-464)."""
+    import copy
+    import io
+    import tempfile
+    import warnings
+    import zipfile
+    from types import SimpleNamespace
+    cases = []
+
+    def run(name, raw_ei, n_x, n_he):
+        d = SimpleNamespace(edge_index=raw_ei.clone(), n_x=torch.tensor([n_x]), num_hyperedges=torch.tensor([n_he]))
+        d = mods.preprocessing.ExtractV2E(d)
+        v2e = d.edge_index.clone()
+        d = mods.preprocessing.Add_Self_Loops(d)
+        with_loops = d.edge_index.clone()
+        tot = int(d.totedges)
+        ones = mods.preprocessing.norm_contruction(copy.copy(d), option='all_one').norm.clone()
+        sym = mods.preprocessing.norm_contruction(copy.copy(d), option='deg_half_sym').norm.clone()
+        sym_noloop = mods.preprocessing.norm_contruction(SimpleNamespace(edge_index=v2e.clone()), option='deg_half_sym').norm.clone()
+        cases.append({'name': name, 'raw': raw_ei.clone(), 'n_x': n_x, 'num_hyperedges': n_he, 'v2e': v2e,
+                      'with_loops': with_loops, 'totedges': tot, 'norm_all_one': ones, 'norm_deg_half_sym': sym,
+                      'norm_deg_half_sym_noloop': sym_noloop})
+
+    # real datasets: the raw star expansion exactly as load_citation_dataset builds it
+    for name in ('cora', 'citeseer'):
+        with tempfile.TemporaryDirectory() as tmp, zipfile.ZipFile(ref_harness._RAW_ZIP) as z:
+            base = 'AllSet_all_raw_data/cocitation/%s/' % name
+            os.makedirs(os.path.join(tmp, name))
+            for f in ('features.pickle', 'labels.pickle', 'hypergraph.pickle'):
+                with open(os.path.join(tmp, name, f), 'wb') as out:
+                    out.write(z.read(base + f))
+            with warnings.catch_warnings(), ref_harness._quiet():
+                warnings.simplefilter('ignore')
+                data = mods.loaders.load_citation_dataset(path=tmp, dataset=name)
+        run(name, data.edge_index, int(data.n_x), int(data.num_hyperedges))
+    # random star expansions with singleton hyperedges, repeated members and nodes of degree 1
+    gen = torch.Generator().manual_seed(99)
+    for i, (n, m, nnz) in enumerate([(30, 12, 70), (200, 90, 500), (500, 400, 900)]):
+        node = torch.randint(0, n, (nnz,), generator=gen)
+        he = torch.randint(0, m, (nnz,), generator=gen)
+        he[:m] = torch.arange(m)                       # every hyperedge id present (ids must be contiguous)
+        node[:n] = torch.arange(n) if nnz >= n else node[:n]
+        k = min(m, 8)
+        # make the last k hyperedges singletons
+        single = he >= m - k
+        keep = ~single
+        keep[torch.arange(nnz)[single][:0]] = True
+        first = {}
+        for j in range(nnz):
+            if single[j]:
+                e = int(he[j])
+                if e not in first:
+                    first[e] = j
+                    keep[j] = True
+        node, he = node[keep], he[keep]
+        vv = torch.cat([node, he + n]); ee = torch.cat([he + n, node])
+        raw = torch.stack([vv, ee])
+        # coalesce like torch_sparse.coalesce (sorted by (row, col), duplicates removed)
+        key = raw[0] * (n + m) + raw[1]
+        key = torch.unique(key)
+        raw = torch.stack([key // (n + m), key % (n + m)])
+        run('random%d' % i, raw, n, m)
+    return cases
+
+
 def main():
     if not ref_harness.available():
         raise SystemExit('reference tree not found: golden vectors can only be generated in the dev container')
@@ -235,6 +301,9 @@ def main():
     cases = variant_cases(mods)
     torch.save(cases, os.path.join(OUT, 'setgnn_variants.pt'))
     print('setgnn_variants', len(cases))
+    cases = preprocessing_cases(mods)
+    torch.save(cases, os.path.join(OUT, 'preprocessing.pt'))
+    print('preprocessing', len(cases), [(c['name'], tuple(c['with_loops'].shape), c['totedges']) for c in cases])
     for f in sorted(os.listdir(OUT)):
         print('%-36s %8.2f MB' % (f, os.path.getsize(os.path.join(OUT, f)) / 1e6))
 
