@@ -206,7 +206,18 @@ def run_b200(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on STDOUT at communicator creation; the contract is ONE JSON line there
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     if world != a.gpus and rank == 0:
         sys.stderr.write('warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE\n' % (a.gpus, world))
     _lib.lib()                                            # fail loudly here if the CUDA library is missing
@@ -346,7 +357,12 @@ def run_b200(a):
                     s_in.wait_event(state['comp_done'][b])                   # x_in[b] no longer being read
                 else:
                     s_in.wait_stream(cur)
-                x_in[b].copy_(x_host, non_blocking=True)                     # H2D of this step's input
+                if world == 1:
+                    x_in[b].copy_(x_host, non_blocking=True)                 # H2D of this step's input
+                else:
+                    # every rank pulls 1/N of the input over ITS PCIe link, NVLink replicates it (V->E needs all rows)
+                    x_in[b][sh.v_lo:sh.v_hi].copy_(x_host[sh.v_lo:sh.v_hi], non_blocking=True)
+                    sharding.allgather_rows(x_in[b], sh.v_ranges, rank)
                 ev = torch.cuda.Event(); ev.record(s_in); state['in_done'][b] = ev
             cur.wait_event(state['in_done'][b])
             if state['out_done'][b] is not None:
@@ -382,9 +398,10 @@ def run_b200(a):
         e2e_steps = max(4, min(a.steps, 20))
         e2e_ms = e2e_run(e2e_steps, 3)
         e2e = {'value': Me / (e2e_ms / e2e_steps * 1e-3), 'unit': UNIT,
-               'h2d_bytes_per_step': int(Nv * d * es) * world, 'd2h_bytes_per_step': int(Nv * d * es),
+               'h2d_bytes_per_step': int(Nv * d * es), 'd2h_bytes_per_step': int(Nv * d * es),
                'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
-               'pipeline': 'H2D(k+1) || compute(k) || D2H(k-1), double-buffered, 3 streams',
+               'pipeline': 'H2D(k+1) || compute(k) || D2H(k-1), double-buffered, 3 streams' + ('' if world == 1 else
+                            '; each rank copies 1/N of X_v from the host and NCCL all-gathers it over NVLink'),
                'api': 'allset_b200.segment_reduce(x, Incidence, None, "sum") x2' if world == 1
                       else 'allset_b200.sharding.ShardedIncidence.layer_pair_sum'}
         del x_host, out_host, x_in, xv_out
