@@ -30,6 +30,7 @@ _i32, _i64, _f32, _sz = _c.c_int32, _c.c_int64, _c.c_float, _c.c_size_t
 SIGNATURES = {
     'allset_version': (_c.c_int, []),
     'allset_last_error': (_c.c_char_p, []),
+    'allset_stream_eligible': (_c.c_int, [_c.c_int, _i32, _i64]),
     'allset_csr_workspace_bytes': (_sz, [_i64, _i64]),
     'allset_csr_from_coo': (_c.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     'allset_long_segments_workspace_bytes': (_sz, [_i64]),
@@ -146,10 +147,23 @@ def long_segments(rowptr: torch.Tensor, n_tgt: int, threshold: int) -> Optional[
 # ----------------------------------------------------------------------------------------------------------
 # AllDeepSets
 # ----------------------------------------------------------------------------------------------------------
+# Longest segment a single warp's stream is allowed to own.  Measured on a power-law graph (sizes ~ s^-2 up to 4096,
+# d=256): reducing 4096-row segments inside one warp's stream is 18-36 % slower than bucketing them for the CTA
+# kernels (5.0-5.8 ms vs 4.3 ms), so only segments up to ~1.5 average warp chunks stay inline.
+STREAM_MAX_SEGMENT = 2048
+
+
+def stream_takes_long_segments(t: torch.Tensor, n_tgt: int, max_len: int) -> bool:
+    """True when the stream kernels handle this shape and the longest segment is short enough to stay inline."""
+    if max_len > STREAM_MAX_SEGMENT or t.dim() != 2:
+        return False
+    return bool(lib().allset_stream_eligible(_dtype_code(t), t.shape[1], n_tgt))
+
+
 def segreduce_fwd(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, mean: bool,
                   w: Optional[torch.Tensor] = None, src_scale: Optional[torch.Tensor] = None,
                   long_ids: Optional[torch.Tensor] = None, long_threshold: int = 0,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, max_segment_len: int = 0) -> torch.Tensor:
     _need(x, 'x')
     _need(rowptr, 'rowptr', torch.int32)
     _need(col, 'col', torch.int32)
@@ -172,6 +186,8 @@ def segreduce_fwd(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tg
             raise ValueError('out must be [n_tgt, d]')
     if d == 0 or n_tgt == 0:
         return out
+    if long_ids is not None and max_segment_len and stream_takes_long_segments(x, n_tgt, max_segment_len):
+        long_ids = None
     n_long = 0 if long_ids is None else long_ids.numel()
     with torch.cuda.device(x.device):
         _check(lib().allset_segreduce_fwd(_ptr(x), _dtype_code(x), n_src, d, _ptr(rowptr), _ptr(col), _ptr(w),
@@ -259,7 +275,8 @@ def segreduce_bwd_w(x: torch.Tensor, grad_out: torch.Tensor, rowptr: torch.Tenso
 # ----------------------------------------------------------------------------------------------------------
 def pma_fwd(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: int, C: int, slope: float,
             rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, want_stats: bool = True,
-            long_ids: Optional[torch.Tensor] = None, long_threshold: int = 0, out: Optional[torch.Tensor] = None):
+            long_ids: Optional[torch.Tensor] = None, long_threshold: int = 0, out: Optional[torch.Tensor] = None,
+            max_segment_len: int = 0):
     """v [n_src, H*C], score [n_src, H] f32, seed [H*C] f32 -> (out [n_tgt, H*C], stats [n_tgt, H, 2] | None)."""
     _need(v, 'v')
     _need(score, 'score', torch.float32)
@@ -278,6 +295,8 @@ def pma_fwd(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: int, C:
     stats = torch.empty((n_tgt, H, 2), dtype=torch.float32, device=v.device) if want_stats else None
     if n_tgt == 0:
         return out, stats
+    if long_ids is not None and max_segment_len and H % 4 == 0 and stream_takes_long_segments(v, n_tgt, max_segment_len):
+        long_ids = None
     n_long = 0 if long_ids is None else long_ids.numel()
     with torch.cuda.device(v.device):
         _check(lib().allset_pma_fwd(_ptr(v), _ptr(score), _ptr(seed), _dtype_code(v), H, C, float(slope), _ptr(rowptr),

@@ -450,6 +450,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 
+// Work split of the stream kernels: warp `chunk` of `n_chunks` owns the target segments [first, first + nseg) such that
+// every chunk carries (nearly) the same COST = incidences gathered + segments flushed, cost(s) = rowptr[s] + s.  The
+// boundary is found on the fly by a warp-cooperative 32-ary search over rowptr (~5 dependent loads), so skewed
+// (power-law) segment sizes do not unbalance the warps and no partition array has to be built or passed.
+__device__ __forceinline__ long long chunk_boundary(const int* __restrict__ rowptr, long long n_tgt, long long total,
+                                                    long long chunk, long long n_chunks, int lane) {
+  if (chunk <= 0) return 0;
+  if (chunk >= n_chunks) return n_tgt;
+  const long long target = total * chunk / n_chunks;      // total <= 2^33, chunk < 2^20: no overflow
+  if (target <= 0) return 0;
+  // cost is strictly increasing; invariant cost(lo) < target <= cost(hi); the answer is the smallest s with
+  // cost(s) >= target, i.e. hi once hi - lo == 1
+  long long lo = 0, hi = n_tgt;
+  while (hi - lo > 1) {
+    const long long stride = (hi - lo + 31) / 32;
+    long long sj = lo + (long long)(lane + 1) * stride;   // lane 31 (and possibly more) probes hi itself
+    if (sj > hi) sj = hi;
+    const bool ge = (long long)__ldg(rowptr + sj) + sj >= target;
+    const int first = __ffs(__ballot_sync(0xffffffffu, ge)) - 1;
+    long long nhi = lo + (long long)(first + 1) * stride;
+    if (nhi > hi) nhi = hi;
+    if (first > 0) lo = lo + (long long)first * stride;
+    hi = nhi;
+  }
+  return hi;
+}
+
 // One lane's share of a staged row: LB bytes (LB = row_bytes / 32).  LB >= 16 is read as LB/16 16-byte chunks,
 // chunk c of lane l at byte (c*32 + l)*16, so every LDS.128 of the warp covers 512 contiguous bytes.
 template <typename T, int LB>
@@ -548,9 +575,14 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
   constexpr int RPS = (kStreamStageBytes / ROWB) < 32 ? (kStreamStageBytes / ROWB) : 32;   // rows per stage
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long s_first = ((long long)blockIdx.x * kStreamWarps + warp) * seg_per_warp;
-  if (s_first >= n_tgt) return;                       // warp-uniform; nothing below synchronises across warps
-  const int nseg = (int)min((long long)seg_per_warp, n_tgt - s_first);
+  // seg_per_warp only sizes the grid (host); the actual block of segments is cost-balanced
+  const long long n_chunks = (n_tgt + seg_per_warp - 1) / seg_per_warp;
+  const long long chunk = (long long)blockIdx.x * kStreamWarps + warp;
+  if (chunk >= n_chunks) return;                      // warp-uniform; nothing below synchronises across warps
+  const long long total_cost = (long long)__ldg(rowptr + n_tgt) + n_tgt;
+  const long long s_first = chunk_boundary(rowptr, n_tgt, total_cost, chunk, n_chunks, lane);
+  const int nseg = (int)(chunk_boundary(rowptr, n_tgt, total_cost, chunk + 1, n_chunks, lane) - s_first);
+  if (nseg <= 0) return;
   const uint32_t ring = smem_u32(smem) + (uint32_t)warp * (uint32_t)stages * (RPS * ROWB);
   const uint32_t bars = smem_u32(smem) + (uint32_t)kStreamWarps * (uint32_t)stages * (RPS * ROWB) +
                         (uint32_t)warp * (uint32_t)stages * 8u;
@@ -704,9 +736,13 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
   constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long s_first = ((long long)blockIdx.x * kStreamWarps + warp) * seg_per_warp;
-  if (s_first >= n_tgt) return;
-  const int nseg = (int)min((long long)seg_per_warp, n_tgt - s_first);
+  const long long n_chunks = (n_tgt + seg_per_warp - 1) / seg_per_warp;
+  const long long chunk = (long long)blockIdx.x * kStreamWarps + warp;
+  if (chunk >= n_chunks) return;
+  const long long total_cost = (long long)__ldg(rowptr + n_tgt) + n_tgt;
+  const long long s_first = chunk_boundary(rowptr, n_tgt, total_cost, chunk, n_chunks, lane);
+  const int nseg = (int)(chunk_boundary(rowptr, n_tgt, total_cost, chunk + 1, n_chunks, lane) - s_first);
+  if (nseg <= 0) return;
   const int d = H * C;
   const uint32_t SB = (uint32_t)H * 4u;                                       // score bytes per row
   const uint32_t ring = smem_u32(smem) + (uint32_t)warp * (uint32_t)stages * (RPS * ROWB);
@@ -1612,6 +1648,13 @@ int elem_bytes(int dtype) { return dtype == ALLSET_F32 ? 4 : 2; }
 extern "C" {
 
 int allset_version(void) { return ALLSET_ABI_VERSION; }
+
+int allset_stream_eligible(int dtype, int32_t d, int64_t n_tgt) {
+  if (bad_dtype(dtype) || d <= 0 || n_tgt <= 0) return 0;
+  // alignment is checked again at launch; a 256-byte aligned dummy stands in for the row pointers here
+  return plan_stream(d, elem_bytes(dtype), n_tgt, reinterpret_cast<const void*>(256), reinterpret_cast<const void*>(256),
+                     false).ok ? 1 : 0;
+}
 
 const char* allset_last_error(void) { return g_err; }
 

@@ -30,6 +30,8 @@ class Csr(object):
         self.n_tgt, self.n_src, self.nnz = int(n_tgt), int(n_src), int(col.numel())
         self.long_threshold = int(threshold)
         self.long_ids = _lib.long_segments(rowptr, self.n_tgt, self.long_threshold) if self.nnz > threshold else None
+        # longest segment (one sync at graph build): moderate lengths stay inside the stream kernels
+        self.max_len = int((rowptr[1:self.n_tgt + 1] - rowptr[:self.n_tgt]).max()) if (self.long_ids is not None and self.n_tgt > 0) else 0
         self._perm64 = None
         self._inv_count = None
 

@@ -32,7 +32,7 @@ class _SegReduce(torch.autograd.Function):
         if weight is not None:
             w_csr = weight.detach().float().index_select(0, t.perm64)
         out = _lib.segreduce_fwd(x, t.rowptr, t.col, t.n_tgt, mean, w=w_csr, long_ids=t.long_ids,
-                                 long_threshold=t.long_threshold)
+                                 long_threshold=t.long_threshold, max_segment_len=t.max_len)
         ctx.inc, ctx.mean = inc, mean
         ctx.has_weight = weight is not None
         ctx.weight_dtype = None if weight is None else weight.dtype
@@ -52,7 +52,7 @@ class _SegReduce(torch.autograd.Function):
             w_T = None if weight is None else weight.float().index_select(0, s.perm64)
             grad_x = _lib.segreduce_fwd(grad_out, s.rowptr, s.col, s.n_tgt, False, w=w_T,
                                         src_scale=t.inv_count if mean else None,
-                                        long_ids=s.long_ids, long_threshold=s.long_threshold)
+                                        long_ids=s.long_ids, long_threshold=s.long_threshold, max_segment_len=s.max_len)
         if ctx.has_weight and ctx.needs_input_grad[1]:
             gw_csr = _lib.segreduce_bwd_w(x, grad_out, t.rowptr, t.col, t.n_tgt,
                                           tgt_scale=t.inv_count if mean else None)
@@ -87,7 +87,7 @@ class _PMA(torch.autograd.Function):
         score = score.float().contiguous()
         seed_f = seed.detach().float().reshape(-1).contiguous()
         out, stats = _lib.pma_fwd(v, score, seed_f, H, C, slope, t.rowptr, t.col, t.n_tgt, want_stats=True,
-                                  long_ids=t.long_ids, long_threshold=t.long_threshold)
+                                  long_ids=t.long_ids, long_threshold=t.long_threshold, max_segment_len=t.max_len)
         ctx.inc, ctx.H, ctx.C, ctx.slope = inc, H, C, slope
         ctx.seed_shape, ctx.seed_dtype, ctx.score_dtype = seed.shape, seed.dtype, score.dtype
         ctx.save_for_backward(v, score, seed_f, out, stats)

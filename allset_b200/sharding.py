@@ -155,7 +155,8 @@ class ShardedIncidence(object):
         (exchange = a later all-gather) or a ReplicatedRows (exchange fused into the kernel's epilogue).  Returns True
         when the exchange has already been issued by the kernel."""
         from . import _lib
-        if isinstance(out_full, ReplicatedRows) and self.world > 1 and csr.long_ids is None:
+        if isinstance(out_full, ReplicatedRows) and self.world > 1 and \
+                (csr.long_ids is None or _lib.stream_takes_long_segments(x_src, csr.n_tgt, csr.max_len)):
             try:
                 _lib.segreduce_fwd_bcast(x_src, csr.rowptr, csr.col, csr.n_tgt, mean, out_full.tensor[lo:hi],
                                          out_full.peer_ptrs(lo))
@@ -164,7 +165,7 @@ class ShardedIncidence(object):
                 pass
         t = out_full.tensor if isinstance(out_full, ReplicatedRows) else out_full
         _lib.segreduce_fwd(x_src, csr.rowptr, csr.col, csr.n_tgt, mean, long_ids=csr.long_ids,
-                           long_threshold=csr.long_threshold, out=t[lo:hi])
+                           long_threshold=csr.long_threshold, out=t[lo:hi], max_segment_len=csr.max_len)
         return False
 
     def v2e_reduce(self, x_v, x_e_full, mean: bool = False):
@@ -177,7 +178,8 @@ class ShardedIncidence(object):
     def _pma(self, csr, v, score, seed, heads, out_full, lo, hi, slope):
         from . import _lib
         C = v.shape[1] // heads
-        if isinstance(out_full, ReplicatedRows) and self.world > 1 and csr.long_ids is None:
+        if isinstance(out_full, ReplicatedRows) and self.world > 1 and \
+                (csr.long_ids is None or _lib.stream_takes_long_segments(v, csr.n_tgt, csr.max_len)):
             try:
                 _lib.pma_fwd_bcast(v, score, seed, heads, C, slope, csr.rowptr, csr.col, csr.n_tgt,
                                    out_full.tensor[lo:hi], out_full.peer_ptrs(lo))
@@ -186,7 +188,8 @@ class ShardedIncidence(object):
                 pass
         t = out_full.tensor if isinstance(out_full, ReplicatedRows) else out_full
         _lib.pma_fwd(v, score, seed, heads, C, slope, csr.rowptr, csr.col, csr.n_tgt, want_stats=False,
-                     long_ids=csr.long_ids, long_threshold=csr.long_threshold, out=t[lo:hi])
+                     long_ids=csr.long_ids, long_threshold=csr.long_threshold, out=t[lo:hi],
+                     max_segment_len=csr.max_len)
         return False
 
     def v2e_pma(self, v_v, score_v, seed, heads, out_e_full, slope: float = 0.2):

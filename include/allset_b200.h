@@ -54,6 +54,11 @@ int allset_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* allset_last_error(void);
 
+/* 1 when (dtype, d, n_tgt) takes the STREAM kernels (rows of 128/256/512/1024 bytes, enough target segments).  Those
+ * kernels reduce a segment of any length inside one warp's stream, so a caller whose longest segment is moderate
+ * (<= ~2K incidences) should then pass n_long = 0 instead of bucketing long segments for the CTA kernels. */
+int allset_stream_eligible(int dtype, int32_t d, int64_t n_tgt);
+
 /* --- incidence container ------------------------------------------------------------------
  * Replaces the implicit work torch_scatter does on every call (unsorted COO index + a
  * D2H `index.max()` to size the output, src/layers.py:656): the COO list is sorted ONCE per

@@ -24,12 +24,15 @@ def main():
         val2 = ctypes.c_size_t(0)
         rt.cudaDeviceGetLimit(ctypes.byref(val2), 5)
         print('L2 fetch granularity: was', val.value, 'set rc', rc, 'now', val2.value, 'via', cands[0], flush=True)
-    ei = synthetic.poisson_hypergraph(Nv, Me, mean, seed=1234, device=dev)
+    if os.environ.get('KB_GRAPH') == 'powerlaw':
+        ei = synthetic.powerlaw_hypergraph(Nv, Me, 2, 4096, 2.0, seed=1234, device=dev)
+    else:
+        ei = synthetic.poisson_hypergraph(Nv, Me, mean, seed=1234, device=dev)
     v2e = allset_b200.Incidence.from_coo(ei[0], ei[1] - Nv, n_src=Nv, n_tgt=Me)
     del ei
     sh = sharding.ShardedIncidence(v2e, 0, 1)
     x_v = synthetic.features(Nv, d, dt, device=dev); x_e = torch.empty(Me, d, dtype=dt, device=dev); x_v2 = torch.empty_like(x_v)
-    H = 8
+    H = int(os.environ.get('KB_HEADS', '8'))
     sv = torch.randn(Nv, H, device=dev); se = torch.randn(Me, H, device=dev); seed = torch.randn(d, device=dev)
     def timeit(fn, n=20):
         for _ in range(3): fn()
@@ -40,7 +43,8 @@ def main():
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
     nnz = v2e.nnz
-    res = {'lib': os.path.basename(_lib.LIB_PATH), 'nnz': nnz}
+    res = {'lib': os.path.basename(_lib.LIB_PATH), 'graph': os.environ.get('KB_GRAPH', 'poisson'), 'N': Nv, 'M': Me, 'd': d, 'dtype': str(dt), 'nnz': nnz,
+           'long_segments_v2e': 0 if v2e.by_tgt.long_ids is None else int(v2e.by_tgt.long_ids.numel())}
     for name, fn, b in (
         ('sum_v2e', lambda: sh.v2e_reduce(x_v, x_e), synthetic.algorithmic_bytes(nnz, Me, d, es)),
         ('sum_e2v', lambda: sh.e2v_reduce(x_e, x_v2), synthetic.algorithmic_bytes(nnz, Nv, d, es)),
