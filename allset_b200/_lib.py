@@ -39,6 +39,7 @@ SIGNATURES = {
                                         _p, _i32, _i32, _p, _p]),
     'allset_segreduce_fwd_bcast': (_c.c_int, [_p, _c.c_int, _i64, _i32, _p, _p, _p, _p, _i64, _c.c_int,
                                               _p, _c.POINTER(_c.c_void_p), _i32, _p]),
+    'allset_bias_act_norm': (_c.c_int, [_p, _p, _c.c_int, _p, _p, _p, _f32, _i64, _i32, _p, _p]),
     'allset_segreduce_bwd_w': (_c.c_int, [_p, _p, _c.c_int, _i32, _p, _p, _p, _i64, _p, _p]),
     'allset_pma_fwd': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
                                   _p, _i32, _i32, _p, _p, _p]),
@@ -193,6 +194,30 @@ def segreduce_fwd(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tg
         _check(lib().allset_segreduce_fwd(_ptr(x), _dtype_code(x), n_src, d, _ptr(rowptr), _ptr(col), _ptr(w),
                                           _ptr(src_scale), n_tgt, MEAN if mean else SUM, _ptr(long_ids), n_long,
                                           long_threshold, _ptr(out), _stream()), 'allset_segreduce_fwd')
+    return out
+
+
+def bias_act_norm(x: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+                  residual: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
+                  beta: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm(residual + relu(x + bias)), every stage optional, one pass over [rows, d] fp32 rows."""
+    _need(x, 'x', torch.float32)
+    _need(bias, 'bias', torch.float32, optional=True)
+    _need(residual, 'residual', torch.float32, optional=True)
+    _need(gamma, 'gamma', torch.float32, optional=True)
+    _need(beta, 'beta', torch.float32, optional=True)
+    if x.dim() != 2:
+        raise ValueError('x must be [rows, d]')
+    rows, d = x.shape
+    if (bias is not None and bias.numel() != d) or (gamma is not None and gamma.numel() != d) or \
+            (beta is not None and beta.numel() != d) or (residual is not None and residual.shape != x.shape):
+        raise ValueError('bias_act_norm: shape mismatch')
+    out = torch.empty_like(x)
+    if rows == 0:
+        return out
+    with torch.cuda.device(x.device):
+        _check(lib().allset_bias_act_norm(_ptr(x), _ptr(bias), 1 if relu else 0, _ptr(residual), _ptr(gamma), _ptr(beta),
+                                          float(eps), rows, d, _ptr(out), _stream()), 'allset_bias_act_norm')
     return out
 
 

@@ -1327,6 +1327,117 @@ pma_score_finish_kernel(const T* __restrict__ gv, const T* __restrict__ v, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dense glue of MLP / PMA (reference layers.py:571-579, 153-157): out = LayerNorm(residual + relu(x + bias)), every
+// stage optional.  One warp per row, the row lives in registers (d = 128 * NV: NV float4 per lane), two-pass mean /
+// variance with warp shuffles -> one HBM read and one write of the row, where ATen spends a bias kernel, a ReLU
+// kernel and a LayerNorm kernel (measured 1.67 ms per [1M,128] LayerNorm alone vs 0.16 ms at HBM speed).
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+bias_act_norm_kernel(const float* __restrict__ x, const float* __restrict__ bias, int relu,
+                     const float* __restrict__ residual, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, long long rows, float* __restrict__ out) {
+  constexpr int D = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = __ldcs(xr + i * 32 + lane);
+  if (bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + i * 32 + lane);
+      v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+    }
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f);
+    }
+  }
+  if (residual != nullptr) {
+    const float4* rr = reinterpret_cast<const float4*>(residual + row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 r = __ldcs(rr + i * 32 + lane);
+      v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+    }
+  }
+  if (gamma != nullptr) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + e * e);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (beta != nullptr) b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+      v[i].x = (v[i].x - mean) * rstd * g.x + b.x; v[i].y = (v[i].y - mean) * rstd * g.y + b.y;
+      v[i].z = (v[i].z - mean) * rstd * g.z + b.z; v[i].w = (v[i].w - mean) * rstd * g.w + b.w;
+    }
+  }
+  float4* orow = reinterpret_cast<float4*>(out + row * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) orow[i * 32 + lane] = v[i];
+}
+
+// any width: one warp per row, three passes over the (L1/L2-resident) row
+__global__ void __launch_bounds__(256)
+bias_act_norm_generic_kernel(const float* __restrict__ x, const float* __restrict__ bias, int relu,
+                             const float* __restrict__ residual, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float eps, long long rows, int d,
+                             float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const float* xr = x + row * d;
+  const float* rr = residual != nullptr ? residual + row * d : nullptr;
+  auto value = [&](int j) {
+    float t = xr[j];
+    if (bias != nullptr) t += __ldg(bias + j);
+    if (relu) t = fmaxf(t, 0.f);
+    if (rr != nullptr) t += rr[j];
+    return t;
+  };
+  float mean = 0.f, rstd = 1.f;
+  if (gamma != nullptr) {
+    float sum = 0.f;
+    for (int j = lane; j < d; j += 32) sum += value(j);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean = sum / (float)d;
+    float sq = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      const float t = value(j) - mean;
+      sq += t * t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    rstd = rsqrtf(sq / (float)d + eps);
+  }
+  for (int j = lane; j < d; j += 32) {
+    float t = value(j);
+    if (gamma != nullptr) t = (t - mean) * rstd * __ldg(gamma + j) + (beta != nullptr ? __ldg(beta + j) : 0.f);
+    out[row * d + j] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // CSR construction
 // ---------------------------------------------------------------------------------------------
 __global__ void csr_keys_kernel(const long long* __restrict__ tgt, long long nnz, int* __restrict__ keys,
@@ -1779,6 +1890,31 @@ int allset_segreduce_fwd_bcast(const void* x, int dtype, int64_t n_src, int32_t 
                                void* out, void* const* peer_outs, int32_t n_peers, void* stream) {
   return segreduce_fwd_impl(x, dtype, n_src, d, rowptr, col, w, src_scale, n_tgt, op, nullptr, 0, 0, out, peer_outs,
                             n_peers, stream);
+}
+
+
+int allset_bias_act_norm(const float* x, const float* bias, int relu, const float* residual, const float* gamma,
+                         const float* beta, float eps, int64_t rows, int32_t d, float* out, void* stream) {
+  if (rows < 0 || d <= 0) return fail(ALLSET_EINVAL, "bias_act_norm: bad size");
+  if (rows == 0) return ALLSET_OK;
+  if (x == nullptr || out == nullptr) return fail(ALLSET_EINVAL, "bias_act_norm: null pointer");
+  if (beta != nullptr && gamma == nullptr) return fail(ALLSET_EINVAL, "bias_act_norm: beta without gamma");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)((rows + 7) / 8);          // 8 warps = 8 rows per CTA
+  const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)gamma |
+                         (uintptr_t)beta;
+  const bool vec = (d % 128 == 0) && (bits % 16 == 0);
+  if (vec && d == 128)
+    bias_act_norm_kernel<1><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out);
+  else if (vec && d == 256)
+    bias_act_norm_kernel<2><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out);
+  else if (vec && d == 512)
+    bias_act_norm_kernel<4><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out);
+  else if (vec && d == 1024)
+    bias_act_norm_kernel<8><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out);
+  else
+    bias_act_norm_generic_kernel<<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, d, out);
+  return check_launch("bias_act_norm");
 }
 
 int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32_t d, const int32_t* rowptr,

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 from torch import Tensor
 from torch.nn import Linear, Parameter
 
-from . import ops
+from . import _lib, ops
 from .graph import Incidence, incidence_of
 
 __all__ = ['MLP', 'PMA', 'HalfNLHconv', 'glorot', 'zeros']
@@ -63,13 +63,43 @@ class MLP(nn.Module):
             if not isinstance(norm, nn.Identity):
                 norm.reset_parameters()
 
-    def forward(self, x):
+    def forward(self, x, final_relu: bool = False):
+        """`final_relu` (extension, default off = reference behaviour) applies the ReLU that every caller on the path
+        wraps around the MLP (`F.relu(self.f_enc(x))`, reference src/layers.py:631,634) inside the last fused pass."""
+        if self._fused_ok(x):
+            y, bias = self.forward_fused_open(x)
+            return _lib.bias_act_norm(y, bias, relu=final_relu)
         x = self.normalizations[0](x)
         for i, lin in enumerate(self.lins[:-1]):
             x = F.relu(lin(x), inplace=True)
             x = self.normalizations[i + 1](x)
             x = F.dropout(x, p=self.dropout, training=self.training)
-        return self.lins[-1](x)
+        x = self.lins[-1](x)
+        return F.relu(x) if final_relu else x
+
+    # -- inference fast path: cuBLAS GEMMs without bias + ONE fused pass (bias, ReLU, LayerNorm) between them --------
+    def _fused_ok(self, x) -> bool:
+        if torch.is_grad_enabled() or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+            return False
+        if self.training and self.dropout > 0:
+            return False
+        return all(isinstance(n, (nn.LayerNorm, nn.Identity)) for n in self.normalizations)
+
+    @staticmethod
+    def _ln(norm):
+        if isinstance(norm, nn.LayerNorm):
+            return dict(gamma=norm.weight, beta=norm.bias, eps=norm.eps)
+        return {}
+
+    def forward_fused_open(self, x):
+        """Everything up to the last Linear's GEMM: returns (y = h @ W_last^T WITHOUT bias, bias_last) so that the
+        caller can fold the bias, an activation, a residual and a LayerNorm into one pass (allset_bias_act_norm)."""
+        x = x.contiguous()
+        if isinstance(self.normalizations[0], nn.LayerNorm):
+            x = _lib.bias_act_norm(x, **self._ln(self.normalizations[0]))
+        for i, lin in enumerate(self.lins[:-1]):
+            x = _lib.bias_act_norm(F.linear(x, lin.weight), lin.bias, relu=True, **self._ln(self.normalizations[i + 1]))
+        return F.linear(x, self.lins[-1].weight), self.lins[-1].bias
 
 
 def _resolve(edge_index, n_src: int) -> Incidence:
@@ -124,15 +154,30 @@ class PMA(nn.Module):
         assert x.dim() == 2, 'Static graphs not supported in `GATConv`.'
         H, C = self.heads, self.hidden
         inc = _resolve(edge_index, x.size(0))
-        x_K = self.lin_K(x).view(-1, H, C)
-        x_V = self.lin_V(x)
-        score = (x_K * self.att_r).sum(dim=-1)                          # [n_src, H], no 1/sqrt(C)
+        # score = (lin_K(x).view(-1,H,C) * att_r).sum(-1)  (reference :128,:130), folded: there is one seed per head,
+        # so the score is linear in x with W_eff[h,:] = sum_c att_r[h,c] W_K[hC+c,:] -- an [n_src,in]x[in,H] GEMV instead
+        # of the [n_src,in]x[in,H*C] GEMM + multiply + reduce.  Same algebra, differentiable, no 1/sqrt(C).
+        seed = self.att_r.view(H, C)
+        w_eff = (self.lin_K.weight.view(H, C, -1) * seed.unsqueeze(-1)).sum(dim=1)         # [H, in]
+        b_eff = (self.lin_K.bias.view(H, C) * seed).sum(dim=1)                             # [H]
+        score = F.linear(x, w_eff, b_eff)                                                  # [n_src, H]
+        fused = self.rFF._fused_ok(x)
+        if fused:
+            x_V = _lib.bias_act_norm(F.linear(x.contiguous(), self.lin_V.weight), self.lin_V.bias)
+        else:
+            x_V = self.lin_V(x)
         v = x_V if self.agg_dtype is None else x_V.to(self.agg_dtype)
         want_alpha = isinstance(return_attention_weights, bool)
         out, alpha = ops.pma_aggregate(v, score, self.att_r, inc, H, self.negative_slope, return_alpha=want_alpha)
         out = out.to(x_V.dtype)                                          # [n_tgt, H*C], seed already added
-        out = self.ln0(out)
-        out = self.ln1(out + F.relu(self.rFF(out)))
+        if fused:
+            out = _lib.bias_act_norm(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps)
+            y, bias = self.rFF.forward_fused_open(out)
+            out = _lib.bias_act_norm(y, bias, relu=True, residual=out, gamma=self.ln1.weight, beta=self.ln1.bias,
+                                     eps=self.ln1.eps)                   # ln1(out + relu(rFF(out))), one pass
+        else:
+            out = self.ln0(out)
+            out = self.ln1(out + F.relu(self.rFF(out)))
         if want_alpha:
             return out, (edge_index, alpha)
         return out
@@ -180,7 +225,7 @@ class HalfNLHconv(nn.Module):
             return self.prop(x, edge_index)              # norm and aggr are ignored, as in the reference
         if aggr is None:
             raise ValueError('aggr was not passed!')
-        x = F.relu(self.f_enc(x))
+        x = self.f_enc(x, final_relu=True) if isinstance(self.f_enc, MLP) else F.relu(self.f_enc(x))
         x = F.dropout(x, p=self.dropout, training=self.training)
         inc = _resolve(edge_index, x.size(0))
         weight = None
@@ -188,5 +233,5 @@ class HalfNLHconv(nn.Module):
             weight = norm
         xs = x if self.agg_dtype is None else x.to(self.agg_dtype)
         x = ops.segment_reduce(xs, inc, weight, aggr).to(x.dtype)
-        x = F.relu(self.f_dec(x))
+        x = self.f_dec(x, final_relu=True) if isinstance(self.f_dec, MLP) else F.relu(self.f_dec(x))
         return x

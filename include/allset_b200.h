@@ -110,6 +110,16 @@ int allset_segreduce_fwd_bcast(const void* x, int dtype, int64_t n_src, int32_t 
                                int64_t n_tgt, int op,
                                void* out, void* const* peer_outs, int32_t n_peers, void* stream);
 
+/* --- dense glue of MLP / PMA ----------------------------------------------------------------
+ * out[r, :] = LayerNorm_{gamma,beta,eps}( residual[r, :] + relu( x[r, :] + bias ) ), each stage optional
+ * (bias / residual / gamma may be NULL, relu 0|1; beta requires gamma).  fp32, row-major [rows, d].
+ * Replaces, in ONE pass over the rows, the bias add of nn.Linear, F.relu and nn.LayerNorm that surround every Linear
+ * in MLP.forward (src/layers.py:571-579: Linear -> ReLU -> norm) and PMA's `ln1(out + relu(rFF(out)))`
+ * (src/layers.py:155-157).  The GEMMs themselves stay on cuBLAS (the reference hands them to a library too). */
+int allset_bias_act_norm(const float* x, const float* bias, int relu, const float* residual,
+                         const float* gamma, const float* beta, float eps,
+                         int64_t rows, int32_t d, float* out, void* stream);
+
 /* Gradient w.r.t. the per-incidence weights (SetGNN.LearnMask, src/models.py:451-452):
  * grad_w[k] = tgt_scale[t] * <x[col[k], :], grad_out[t, :]>  for k in segment t (CSR order).
  * tgt_scale [n_tgt] fp32 or NULL (mean: 1/max(count,1)). */

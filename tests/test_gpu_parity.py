@@ -552,3 +552,63 @@ def test_stream_kernels_own_moderately_long_segments():
     out_stream = _lib.segreduce_fwd(x, t.rowptr, t.col, m, False, long_ids=t.long_ids, long_threshold=t.long_threshold,
                                     max_segment_len=t.max_len)
     torch.testing.assert_close(out_stream, out_group, rtol=1e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused dense glue (inference path of MLP / PMA)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('d', [128, 256, 512, 1024, 64, 20, 1433, 3])
+def test_bias_act_norm_vs_torch(d):
+    from allset_b200 import _lib
+    g = torch.Generator().manual_seed(d)
+    rows = 1000
+    x = torch.randn(rows, d, generator=g).to(dev()) * 3
+    b = torch.randn(d, generator=g).to(dev())
+    r = torch.randn(rows, d, generator=g).to(dev())
+    gam = (torch.rand(d, generator=g) + 0.5).to(dev())
+    bet = torch.randn(d, generator=g).to(dev())
+    tol = dict(rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(_lib.bias_act_norm(x, b), x + b, **tol)
+    torch.testing.assert_close(_lib.bias_act_norm(x, b, relu=True), F.relu(x + b), **tol)
+    torch.testing.assert_close(_lib.bias_act_norm(x, gamma=gam, beta=bet), F.layer_norm(x, (d,), gam, bet, 1e-5), **tol)
+    torch.testing.assert_close(_lib.bias_act_norm(x, b, relu=True, gamma=gam, beta=bet),
+                               F.layer_norm(F.relu(x + b), (d,), gam, bet, 1e-5), **tol)
+    torch.testing.assert_close(_lib.bias_act_norm(x, b, relu=True, residual=r, gamma=gam, beta=bet),
+                               F.layer_norm(r + F.relu(x + b), (d,), gam, bet, 1e-5), **tol)
+    assert _lib.bias_act_norm(x[:0], b).shape == (0, d)
+
+
+@pytest.mark.parametrize('name,idx', [('cora_alldeepsets.pt', None), ('citeseer_allsettransformer.pt', None)] +
+                         [('setgnn_variants.pt', i) for i in range(12)])
+def test_setgnn_inference_fast_path_matches_reference(name, idx):
+    """torch.no_grad() + eval(): MLP / PMA take the fused bias+ReLU+LayerNorm kernels and the folded score GEMV."""
+    rec = load_golden(name) if idx is None else load_golden(name)[idx]
+    model, data = _build(rec)
+    taps, hooks = _taps(model)
+    with torch.no_grad():
+        out = model(data)
+    for h in hooks:
+        h.remove()
+    torch.testing.assert_close(out.cpu(), rec['logits'], **FP32)
+    s = rec['tap_stride']
+    for mine, ref in zip(taps, rec['taps']):
+        torch.testing.assert_close(mine[::s], ref, **FP32)
+
+
+def test_layers_inference_fast_path():
+    for rec in load_golden('layers_small.pt'):
+        e = rec['extra']
+        if rec['kind'] == 'pma':
+            m = ab().PMA(e['in_channels'], e['hid_dim'], e['out_channels'], e['num_layers'], heads=e['heads'])
+        else:
+            m = ab().HalfNLHconv(e['in_dim'], e['hid_dim'], e['out_dim'], e['num_layers'], 0.3, e['Normalization'],
+                                 e['InputNorm'], heads=1, attention=False)
+        m.load_state_dict(rec['state_dict'], strict=True)
+        m.to(dev()).eval()
+        with torch.no_grad():
+            if rec['kind'] == 'pma':
+                out, (_, alpha) = m(rec['x'].to(dev()), rec['edge_index'].to(dev()), return_attention_weights=True)
+                torch.testing.assert_close(alpha.cpu(), rec['alpha'], **FP32)
+            else:
+                out = m(rec['x'].to(dev()), rec['edge_index'].to(dev()), rec['norm'].to(dev()), rec['aggr'])
+        torch.testing.assert_close(out.cpu(), rec['out'], **FP32)
