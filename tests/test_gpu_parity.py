@@ -612,3 +612,30 @@ def test_layers_inference_fast_path():
             else:
                 out = m(rec['x'].to(dev()), rec['edge_index'].to(dev()), rec['norm'].to(dev()), rec['aggr'])
         torch.testing.assert_close(out.cpu(), rec['out'], **FP32)
+
+
+def test_c_abi_error_codes():
+    """Sizes beyond the int32 CSR, unknown enums and null pointers are refused with a code + message, never a crash."""
+    from allset_b200 import _lib
+    h = _lib.lib()
+    x = torch.zeros(4, 8, device=dev())
+    rp = torch.zeros(5, dtype=torch.int32, device=dev())
+    col = torch.zeros(1, dtype=torch.int32, device=dev())
+    out = torch.zeros(4, 8, device=dev())
+    assert h.allset_csr_workspace_bytes(2 ** 31, 10) == 0
+    assert h.allset_csr_from_coo(None, None, 2 ** 31, 10, rp.data_ptr(), None, None, None, 0, None) == -2       # ERANGE
+    assert b'int32' in h.allset_last_error()
+    assert h.allset_segreduce_fwd(x.data_ptr(), 7, 4, 8, rp.data_ptr(), col.data_ptr(), None, None, 4, 0, None, 0, 0,
+                                  out.data_ptr(), None) == -1                                                    # dtype
+    assert h.allset_segreduce_fwd(x.data_ptr(), 0, 4, 8, rp.data_ptr(), col.data_ptr(), None, None, 4, 9, None, 0, 0,
+                                  out.data_ptr(), None) == -1                                                    # op
+    assert h.allset_segreduce_fwd(x.data_ptr(), 0, 4, 8, None, col.data_ptr(), None, None, 4, 0, None, 0, 0,
+                                  out.data_ptr(), None) == -1                                                    # null rowptr
+    assert h.allset_pma_fwd(x.data_ptr(), x.data_ptr(), x.data_ptr(), 0, 2, 4, -0.5, rp.data_ptr(), col.data_ptr(), 4,
+                            None, 0, 0, out.data_ptr(), None, None) == -1                                        # slope
+    ws = torch.zeros(16, dtype=torch.uint8, device=dev())
+    t = torch.zeros(3, dtype=torch.int64, device=dev())
+    assert h.allset_csr_from_coo(t.data_ptr(), t.data_ptr(), 3, 4, rp.data_ptr(), col.data_ptr(), col.data_ptr(),
+                                 ws.data_ptr(), 16, None) == -3                                                  # workspace
+    assert h.allset_stream_eligible(1, 128, 10_000_000) == 1 and h.allset_stream_eligible(1, 20, 10_000_000) == 0
+    assert h.allset_stream_eligible(1, 128, 1000) == 0
