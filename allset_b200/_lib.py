@@ -39,7 +39,9 @@ SIGNATURES = {
                                         _p, _i32, _i32, _p, _p]),
     'allset_segreduce_fwd_bcast': (_c.c_int, [_p, _c.c_int, _i64, _i32, _p, _p, _p, _p, _i64, _c.c_int,
                                               _p, _c.POINTER(_c.c_void_p), _i32, _p]),
-    'allset_bias_act_norm': (_c.c_int, [_p, _p, _c.c_int, _p, _p, _p, _f32, _i64, _i32, _p, _p]),
+    'allset_bias_act_norm': (_c.c_int, [_p, _p, _c.c_int, _p, _p, _p, _f32, _i64, _i32, _p, _p, _p]),
+    'allset_bias_act_norm_bwd_blocks': (_i32, [_i64]),
+    'allset_bias_act_norm_bwd': (_c.c_int, [_p, _p, _p, _c.c_int, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
     'allset_segreduce_bwd_w': (_c.c_int, [_p, _p, _c.c_int, _i32, _p, _p, _p, _i64, _p, _p]),
     'allset_pma_fwd': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
                                   _p, _i32, _i32, _p, _p, _p]),
@@ -199,8 +201,9 @@ def segreduce_fwd(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tg
 
 def bias_act_norm(x: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
                   residual: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
-                  beta: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
-    """LayerNorm(residual + relu(x + bias)), every stage optional, one pass over [rows, d] fp32 rows."""
+                  beta: Optional[torch.Tensor] = None, eps: float = 1e-5, want_stats: bool = False):
+    """LayerNorm(residual + relu(x + bias)), every stage optional, one pass over [rows, d] fp32 rows.
+    want_stats: also return the per-row (mean, rstd) [rows, 2] the backward pass needs."""
     _need(x, 'x', torch.float32)
     _need(bias, 'bias', torch.float32, optional=True)
     _need(residual, 'residual', torch.float32, optional=True)
@@ -213,12 +216,38 @@ def bias_act_norm(x: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bo
             (beta is not None and beta.numel() != d) or (residual is not None and residual.shape != x.shape):
         raise ValueError('bias_act_norm: shape mismatch')
     out = torch.empty_like(x)
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if (want_stats and gamma is not None) else None
+    if rows > 0:
+        with torch.cuda.device(x.device):
+            _check(lib().allset_bias_act_norm(_ptr(x), _ptr(bias), 1 if relu else 0, _ptr(residual), _ptr(gamma),
+                                              _ptr(beta), float(eps), rows, d, _ptr(out), _ptr(stats), _stream()),
+                   'allset_bias_act_norm')
+    return (out, stats) if want_stats else out
+
+
+BIAS_ACT_NORM_BWD_WIDTHS = (128, 256, 512, 1024)
+
+
+def bias_act_norm_bwd(dy: torch.Tensor, x: torch.Tensor, bias: Optional[torch.Tensor], relu: bool,
+                      residual: Optional[torch.Tensor], gamma: Optional[torch.Tensor], stats: Optional[torch.Tensor],
+                      want_dres: bool):
+    """-> (dx, dres | None, dgamma, dbeta, dbias) ; the three column sums come from per-CTA partials summed here."""
+    _need(dy, 'dy', torch.float32)
+    _need(x, 'x', torch.float32)
+    rows, d = x.shape
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    blocks = lib().allset_bias_act_norm_bwd_blocks(rows)
+    partial = torch.empty((blocks, 3, d), dtype=torch.float32, device=x.device)
     if rows == 0:
-        return out
+        z = torch.zeros(d, device=x.device)
+        return dx, dres, z, z.clone(), z.clone()
     with torch.cuda.device(x.device):
-        _check(lib().allset_bias_act_norm(_ptr(x), _ptr(bias), 1 if relu else 0, _ptr(residual), _ptr(gamma), _ptr(beta),
-                                          float(eps), rows, d, _ptr(out), _stream()), 'allset_bias_act_norm')
-    return out
+        _check(lib().allset_bias_act_norm_bwd(_ptr(dy), _ptr(x), _ptr(bias), 1 if relu else 0, _ptr(residual), _ptr(gamma),
+                                              _ptr(stats), rows, d, _ptr(dx), _ptr(dres), _ptr(partial), _stream()),
+               'allset_bias_act_norm_bwd')
+    sums = partial.sum(dim=0)
+    return dx, dres, sums[0], sums[1], sums[2]
 
 
 class Unsupported(RuntimeError):

@@ -1336,7 +1336,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 bias_act_norm_kernel(const float* __restrict__ x, const float* __restrict__ bias, int relu,
                      const float* __restrict__ residual, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float eps, long long rows, float* __restrict__ out) {
+                     const float* __restrict__ beta, float eps, long long rows, float* __restrict__ out,
+                     float* __restrict__ stats) {
   constexpr int D = 128 * NV;
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1382,6 +1383,7 @@ bias_act_norm_kernel(const float* __restrict__ x, const float* __restrict__ bias
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq * (1.f / D) + eps);
+    if (stats != nullptr && lane == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
@@ -1396,12 +1398,115 @@ bias_act_norm_kernel(const float* __restrict__ x, const float* __restrict__ bias
   for (int i = 0; i < NV; ++i) orow[i * 32 + lane] = v[i];
 }
 
+// Backward of bias_act_norm for d = 128 * NV.  A warp walks rows with a grid stride, so every lane owns fixed columns:
+// d(gamma), d(beta), d(bias) accumulate in registers over all rows of the warp, are combined per CTA in shared memory
+// and written as ONE partial row per CTA (`partial[cta][3][D]`, summed by the host: deterministic, no atomics).
+//   z = residual + act(x + bias),  zh = (z - mean) * rstd,  y = zh * gamma + beta
+//   g = dy * gamma;  dz = rstd * (g - mean_d(g) - zh * mean_d(g * zh))   (dz = dy without LayerNorm)
+//   d(residual) = dz;  d(x) = dz * [x + bias > 0]  (relu)  else dz
+template <int NV>
+__global__ void __launch_bounds__(256)
+bias_act_norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ bias,
+                         int relu, const float* __restrict__ residual, const float* __restrict__ gamma,
+                         const float* __restrict__ stats, long long rows, float* __restrict__ dx,
+                         float* __restrict__ dres, float* __restrict__ partial) {
+  constexpr int D = 128 * NV;
+  __shared__ float red[8][3][32 * 4];                 // per warp, per quantity, one float4 slot per lane (re-used per i)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nwarps = (long long)gridDim.x * 8;
+  float4 bsv[NV], gmv[NV];
+  float4 dgam[NV], dbet[NV], dbia[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    bsv[i] = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias) + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gmv[i] = gamma != nullptr ? __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane) : make_float4(1.f, 1.f, 1.f, 1.f);
+    dgam[i] = dbet[i] = dbia[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += nwarps) {
+    float4 pre[NV], g[NV], zh[NV];
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const float4* dyr = reinterpret_cast<const float4*>(dy + row * D);
+    float mean = 0.f, rstd = 1.f;
+    if (gamma != nullptr) {
+      const float2 st = __ldg(reinterpret_cast<const float2*>(stats + row * 2));
+      mean = st.x; rstd = st.y;
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 p = __ldcs(xr + i * 32 + lane);
+      p.x += bsv[i].x; p.y += bsv[i].y; p.z += bsv[i].z; p.w += bsv[i].w;
+      pre[i] = p;
+      float4 z = p;
+      if (relu) { z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f); z.z = fmaxf(z.z, 0.f); z.w = fmaxf(z.w, 0.f); }
+      if (residual != nullptr) {
+        const float4 r = __ldcs(reinterpret_cast<const float4*>(residual + row * D) + i * 32 + lane);
+        z.x += r.x; z.y += r.y; z.z += r.z; z.w += r.w;
+      }
+      const float4 d_ = __ldcs(dyr + i * 32 + lane);
+      float4 h = make_float4((z.x - mean) * rstd, (z.y - mean) * rstd, (z.z - mean) * rstd, (z.w - mean) * rstd);
+      zh[i] = h;
+      float4 gg = make_float4(d_.x * gmv[i].x, d_.y * gmv[i].y, d_.z * gmv[i].z, d_.w * gmv[i].w);
+      g[i] = gg;
+      if (gamma != nullptr) {
+        dgam[i].x += d_.x * h.x; dgam[i].y += d_.y * h.y; dgam[i].z += d_.z * h.z; dgam[i].w += d_.w * h.w;
+        dbet[i].x += d_.x; dbet[i].y += d_.y; dbet[i].z += d_.z; dbet[i].w += d_.w;
+        s1 += (gg.x + gg.y) + (gg.z + gg.w);
+        s2 += (gg.x * h.x + gg.y * h.y) + (gg.z * h.z + gg.w * h.w);
+      }
+    }
+    if (gamma != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      s1 *= (1.f / D);
+      s2 *= (1.f / D);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 dz = g[i];
+      if (gamma != nullptr) {
+        dz.x = rstd * (g[i].x - s1 - zh[i].x * s2); dz.y = rstd * (g[i].y - s1 - zh[i].y * s2);
+        dz.z = rstd * (g[i].z - s1 - zh[i].z * s2); dz.w = rstd * (g[i].w - s1 - zh[i].w * s2);
+      }
+      if (dres != nullptr) reinterpret_cast<float4*>(dres + row * D)[i * 32 + lane] = dz;
+      float4 dp = dz;
+      if (relu) {
+        dp.x = pre[i].x > 0.f ? dz.x : 0.f; dp.y = pre[i].y > 0.f ? dz.y : 0.f;
+        dp.z = pre[i].z > 0.f ? dz.z : 0.f; dp.w = pre[i].w > 0.f ? dz.w : 0.f;
+      }
+      dbia[i].x += dp.x; dbia[i].y += dp.y; dbia[i].z += dp.z; dbia[i].w += dp.w;
+      reinterpret_cast<float4*>(dx + row * D)[i * 32 + lane] = dp;
+    }
+  }
+  // CTA-level combine of the column sums, one NV slice at a time through shared memory
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    reinterpret_cast<float4*>(red[warp][0])[lane] = dgam[i];
+    reinterpret_cast<float4*>(red[warp][1])[lane] = dbet[i];
+    reinterpret_cast<float4*>(red[warp][2])[lane] = dbia[i];
+    __syncthreads();
+    if (warp < 3) {                                 // warp q sums quantity q over the 8 warps
+      float4 a = reinterpret_cast<float4*>(red[0][warp])[lane];
+#pragma unroll
+      for (int w2 = 1; w2 < 8; ++w2) {
+        const float4 b = reinterpret_cast<float4*>(red[w2][warp])[lane];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      reinterpret_cast<float4*>(partial + ((size_t)blockIdx.x * 3 + warp) * D)[i * 32 + lane] = a;
+    }
+    __syncthreads();
+  }
+}
+
 // any width: one warp per row, three passes over the (L1/L2-resident) row
 __global__ void __launch_bounds__(256)
 bias_act_norm_generic_kernel(const float* __restrict__ x, const float* __restrict__ bias, int relu,
                              const float* __restrict__ residual, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float eps, long long rows, int d,
-                             float* __restrict__ out) {
+                             float* __restrict__ out, float* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -1429,6 +1534,7 @@ bias_act_norm_generic_kernel(const float* __restrict__ x, const float* __restric
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     rstd = rsqrtf(sq / (float)d + eps);
+    if (stats != nullptr && lane == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
   }
   for (int j = lane; j < d; j += 32) {
     float t = value(j);
@@ -1894,7 +2000,8 @@ int allset_segreduce_fwd_bcast(const void* x, int dtype, int64_t n_src, int32_t 
 
 
 int allset_bias_act_norm(const float* x, const float* bias, int relu, const float* residual, const float* gamma,
-                         const float* beta, float eps, int64_t rows, int32_t d, float* out, void* stream) {
+                         const float* beta, float eps, int64_t rows, int32_t d, float* out, float* stats,
+                         void* stream) {
   if (rows < 0 || d <= 0) return fail(ALLSET_EINVAL, "bias_act_norm: bad size");
   if (rows == 0) return ALLSET_OK;
   if (x == nullptr || out == nullptr) return fail(ALLSET_EINVAL, "bias_act_norm: null pointer");
@@ -1903,18 +2010,52 @@ int allset_bias_act_norm(const float* x, const float* bias, int relu, const floa
   const unsigned blocks = (unsigned)((rows + 7) / 8);          // 8 warps = 8 rows per CTA
   const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)gamma |
                          (uintptr_t)beta;
-  const bool vec = (d % 128 == 0) && (bits % 16 == 0);
+  const bool vec = (d % 128 == 0) && (bits % 16 == 0) && ((uintptr_t)stats % 8 == 0);
   if (vec && d == 128)
-    bias_act_norm_kernel<1><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out);
+    bias_act_norm_kernel<1><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out, stats);
   else if (vec && d == 256)
-    bias_act_norm_kernel<2><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out);
+    bias_act_norm_kernel<2><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out, stats);
   else if (vec && d == 512)
-    bias_act_norm_kernel<4><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out);
+    bias_act_norm_kernel<4><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out, stats);
   else if (vec && d == 1024)
-    bias_act_norm_kernel<8><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out);
+    bias_act_norm_kernel<8><<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, out, stats);
   else
-    bias_act_norm_generic_kernel<<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, d, out);
+    bias_act_norm_generic_kernel<<<blocks, 256, 0, st>>>(x, bias, relu, residual, gamma, beta, eps, rows, d, out, stats);
   return check_launch("bias_act_norm");
+}
+
+int32_t allset_bias_act_norm_bwd_blocks(int64_t rows) {
+  // persistent-style grid: each warp walks rows with a grid stride so the column sums amortise
+  long long b = (rows + 7) / 8;
+  const long long cap = 148LL * 4;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int32_t)b;
+}
+
+int allset_bias_act_norm_bwd(const float* dy, const float* x, const float* bias, int relu, const float* residual,
+                             const float* gamma, const float* stats, int64_t rows, int32_t d, float* dx,
+                             float* dres, float* partial, void* stream) {
+  if (rows < 0 || d <= 0) return fail(ALLSET_EINVAL, "bias_act_norm_bwd: bad size");
+  if (rows == 0) return ALLSET_OK;
+  if (dy == nullptr || x == nullptr || dx == nullptr || partial == nullptr)
+    return fail(ALLSET_EINVAL, "bias_act_norm_bwd: null pointer");
+  if (gamma != nullptr && stats == nullptr) return fail(ALLSET_EINVAL, "bias_act_norm_bwd: stats required with gamma");
+  const uintptr_t bits = (uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)bias | (uintptr_t)residual |
+                         (uintptr_t)gamma | (uintptr_t)dres | (uintptr_t)partial;
+  if (!(d == 128 || d == 256 || d == 512 || d == 1024) || bits % 16 != 0 || (uintptr_t)stats % 8 != 0)
+    return fail(ALLSET_EUNSUPPORTED, "bias_act_norm_bwd: needs d in {128,256,512,1024} and 16-byte aligned rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)allset_bias_act_norm_bwd_blocks(rows);
+  if (d == 128)
+    bias_act_norm_bwd_kernel<1><<<blocks, 256, 0, st>>>(dy, x, bias, relu, residual, gamma, stats, rows, dx, dres, partial);
+  else if (d == 256)
+    bias_act_norm_bwd_kernel<2><<<blocks, 256, 0, st>>>(dy, x, bias, relu, residual, gamma, stats, rows, dx, dres, partial);
+  else if (d == 512)
+    bias_act_norm_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, x, bias, relu, residual, gamma, stats, rows, dx, dres, partial);
+  else
+    bias_act_norm_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, x, bias, relu, residual, gamma, stats, rows, dx, dres, partial);
+  return check_launch("bias_act_norm_bwd");
 }
 
 int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32_t d, const int32_t* rowptr,

@@ -68,7 +68,7 @@ class MLP(nn.Module):
         wraps around the MLP (`F.relu(self.f_enc(x))`, reference src/layers.py:631,634) inside the last fused pass."""
         if self._fused_ok(x):
             y, bias = self.forward_fused_open(x)
-            return _lib.bias_act_norm(y, bias, relu=final_relu)
+            return ops.bias_act_norm(y, bias, relu=final_relu)
         x = self.normalizations[0](x)
         for i, lin in enumerate(self.lins[:-1]):
             x = F.relu(lin(x), inplace=True)
@@ -77,13 +77,15 @@ class MLP(nn.Module):
         x = self.lins[-1](x)
         return F.relu(x) if final_relu else x
 
-    # -- inference fast path: cuBLAS GEMMs without bias + ONE fused pass (bias, ReLU, LayerNorm) between them --------
+    # -- fast path: cuBLAS GEMMs WITHOUT bias + ONE fused pass (bias, ReLU, LayerNorm) between them, forward and
+    #    backward (allset_bias_act_norm[_bwd]); dropout stays a separate ATen op ---------------------------------------
     def _fused_ok(self, x) -> bool:
-        if torch.is_grad_enabled() or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+        if not all(isinstance(n, (nn.LayerNorm, nn.Identity)) for n in self.normalizations):
             return False
-        if self.training and self.dropout > 0:
-            return False
-        return all(isinstance(n, (nn.LayerNorm, nn.Identity)) for n in self.normalizations)
+        widths = [lin.out_features for lin in self.lins]
+        if isinstance(self.normalizations[0], nn.LayerNorm):
+            widths.append(self.lins[0].in_features)
+        return all(ops.fused_dense_ok(x, w) for w in widths)
 
     @staticmethod
     def _ln(norm):
@@ -93,12 +95,12 @@ class MLP(nn.Module):
 
     def forward_fused_open(self, x):
         """Everything up to the last Linear's GEMM: returns (y = h @ W_last^T WITHOUT bias, bias_last) so that the
-        caller can fold the bias, an activation, a residual and a LayerNorm into one pass (allset_bias_act_norm)."""
-        x = x.contiguous()
+        caller can fold the bias, an activation, a residual and a LayerNorm into one pass (ops.bias_act_norm)."""
         if isinstance(self.normalizations[0], nn.LayerNorm):
-            x = _lib.bias_act_norm(x, **self._ln(self.normalizations[0]))
+            x = ops.bias_act_norm(x, **self._ln(self.normalizations[0]))
         for i, lin in enumerate(self.lins[:-1]):
-            x = _lib.bias_act_norm(F.linear(x, lin.weight), lin.bias, relu=True, **self._ln(self.normalizations[i + 1]))
+            x = ops.bias_act_norm(F.linear(x, lin.weight), lin.bias, relu=True, **self._ln(self.normalizations[i + 1]))
+            x = F.dropout(x, p=self.dropout, training=self.training)
         return F.linear(x, self.lins[-1].weight), self.lins[-1].bias
 
 
@@ -161,9 +163,9 @@ class PMA(nn.Module):
         w_eff = (self.lin_K.weight.view(H, C, -1) * seed.unsqueeze(-1)).sum(dim=1)         # [H, in]
         b_eff = (self.lin_K.bias.view(H, C) * seed).sum(dim=1)                             # [H]
         score = F.linear(x, w_eff, b_eff)                                                  # [n_src, H]
-        fused = self.rFF._fused_ok(x)
+        fused = self.rFF._fused_ok(x) and ops.fused_dense_ok(x, self.heads * self.hidden)
         if fused:
-            x_V = _lib.bias_act_norm(F.linear(x.contiguous(), self.lin_V.weight), self.lin_V.bias)
+            x_V = ops.bias_act_norm(F.linear(x, self.lin_V.weight), self.lin_V.bias)
         else:
             x_V = self.lin_V(x)
         v = x_V if self.agg_dtype is None else x_V.to(self.agg_dtype)
@@ -171,10 +173,10 @@ class PMA(nn.Module):
         out, alpha = ops.pma_aggregate(v, score, self.att_r, inc, H, self.negative_slope, return_alpha=want_alpha)
         out = out.to(x_V.dtype)                                          # [n_tgt, H*C], seed already added
         if fused:
-            out = _lib.bias_act_norm(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps)
+            out = ops.bias_act_norm(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps)
             y, bias = self.rFF.forward_fused_open(out)
-            out = _lib.bias_act_norm(y, bias, relu=True, residual=out, gamma=self.ln1.weight, beta=self.ln1.bias,
-                                     eps=self.ln1.eps)                   # ln1(out + relu(rFF(out))), one pass
+            out = ops.bias_act_norm(y, bias, relu=True, residual=out, gamma=self.ln1.weight, beta=self.ln1.bias,
+                                    eps=self.ln1.eps)                    # ln1(out + relu(rFF(out))), one pass
         else:
             out = self.ln0(out)
             out = self.ln1(out + F.relu(self.rFF(out)))

@@ -136,3 +136,51 @@ def pma_aggregate(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, inc:
         alpha = torch.empty_like(a_csr)
         alpha.index_copy_(0, t.perm64, a_csr)
     return out, alpha
+
+
+class _BiasActNorm(torch.autograd.Function):
+    """out = LayerNorm(residual + relu(x + bias)) with a fused forward AND backward (allset_bias_act_norm[_bwd])."""
+
+    @staticmethod
+    def forward(ctx, x, bias, residual, gamma, beta, relu: bool, eps: float):
+        x = x.contiguous()
+        res = None if residual is None else residual.contiguous()
+        out, stats = _lib.bias_act_norm(x, bias, relu, res, gamma, beta, eps, want_stats=True)
+        ctx.relu = relu
+        ctx.has = (bias is not None, residual is not None, gamma is not None, beta is not None)
+        ctx.save_for_backward(x, bias, res, gamma, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, bias, res, gamma, stats = ctx.saved_tensors
+        has_bias, has_res, has_gamma, has_beta = ctx.has
+        dx, dres, dgamma, dbeta, dbias = _lib.bias_act_norm_bwd(dy.contiguous(), x, bias, ctx.relu, res, gamma, stats,
+                                                                want_dres=has_res and ctx.needs_input_grad[2])
+        return (dx if ctx.needs_input_grad[0] else None,
+                dbias if has_bias and ctx.needs_input_grad[1] else None,
+                dres if has_res and ctx.needs_input_grad[2] else None,
+                dgamma if has_gamma and ctx.needs_input_grad[3] else None,
+                dbeta if has_beta and ctx.needs_input_grad[4] else None,
+                None, None)
+
+
+def bias_act_norm(x: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+                  residual: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
+                  beta: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
+    """Differentiable LayerNorm(residual + relu(x + bias)), every stage optional; x [rows, d] fp32 CUDA.
+    The fused backward needs d in {128, 256, 512, 1024}; callers check `fused_dense_ok` first."""
+    if not torch.is_grad_enabled():
+        return _lib.bias_act_norm(x.contiguous(), bias, relu, None if residual is None else residual.contiguous(),
+                                  gamma, beta, eps)
+    return _BiasActNorm.apply(x, bias, residual, gamma, beta, relu, eps)
+
+
+FUSED_DENSE_MIN_ROWS = 8192      # below this a forward is launch-bound and the ATen chain has less host overhead
+
+
+def fused_dense_ok(x: torch.Tensor, width: int) -> bool:
+    """Whether [rows, width] fp32 rows should take the fused dense glue under the current autograd mode."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.shape[0] < FUSED_DENSE_MIN_ROWS:
+        return False
+    return (not torch.is_grad_enabled()) or width in _lib.BIAS_ACT_NORM_BWD_WIDTHS

@@ -115,10 +115,20 @@ int allset_segreduce_fwd_bcast(const void* x, int dtype, int64_t n_src, int32_t 
  * (bias / residual / gamma may be NULL, relu 0|1; beta requires gamma).  fp32, row-major [rows, d].
  * Replaces, in ONE pass over the rows, the bias add of nn.Linear, F.relu and nn.LayerNorm that surround every Linear
  * in MLP.forward (src/layers.py:571-579: Linear -> ReLU -> norm) and PMA's `ln1(out + relu(rFF(out)))`
- * (src/layers.py:155-157).  The GEMMs themselves stay on cuBLAS (the reference hands them to a library too). */
+ * (src/layers.py:155-157).  The GEMMs themselves stay on cuBLAS (the reference hands them to a library too).
+ * stats [rows, 2] = (mean, rstd) of the LayerNorm, or NULL (needed only for the backward pass). */
 int allset_bias_act_norm(const float* x, const float* bias, int relu, const float* residual,
                          const float* gamma, const float* beta, float eps,
-                         int64_t rows, int32_t d, float* out, void* stream);
+                         int64_t rows, int32_t d, float* out, float* stats, void* stream);
+
+/* Backward of allset_bias_act_norm (d in {128,256,512,1024}; ALLSET_EUNSUPPORTED otherwise):
+ *   dx [rows, d] = gradient w.r.t. x;  dres [rows, d] or NULL = gradient w.r.t. residual;
+ *   partial [blocks, 3, d] = per-CTA column sums of (d gamma, d beta, d bias), blocks =
+ *   allset_bias_act_norm_bwd_blocks(rows); the caller sums over dim 0 (deterministic, no atomics). */
+int32_t allset_bias_act_norm_bwd_blocks(int64_t rows);
+int allset_bias_act_norm_bwd(const float* dy, const float* x, const float* bias, int relu,
+                             const float* residual, const float* gamma, const float* stats,
+                             int64_t rows, int32_t d, float* dx, float* dres, float* partial, void* stream);
 
 /* Gradient w.r.t. the per-incidence weights (SetGNN.LearnMask, src/models.py:451-452):
  * grad_w[k] = tgt_scale[t] * <x[col[k], :], grad_out[t, :]>  for k in segment t (CSR order).

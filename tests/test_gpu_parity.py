@@ -580,8 +580,10 @@ def test_bias_act_norm_vs_torch(d):
 
 @pytest.mark.parametrize('name,idx', [('cora_alldeepsets.pt', None), ('citeseer_allsettransformer.pt', None)] +
                          [('setgnn_variants.pt', i) for i in range(12)])
-def test_setgnn_inference_fast_path_matches_reference(name, idx):
+def test_setgnn_inference_fast_path_matches_reference(name, idx, monkeypatch):
     """torch.no_grad() + eval(): MLP / PMA take the fused bias+ReLU+LayerNorm kernels and the folded score GEMV."""
+    from allset_b200 import ops
+    monkeypatch.setattr(ops, 'FUSED_DENSE_MIN_ROWS', 0)          # the golden graphs are small: force the fused path
     rec = load_golden(name) if idx is None else load_golden(name)[idx]
     model, data = _build(rec)
     taps, hooks = _taps(model)
@@ -595,7 +597,9 @@ def test_setgnn_inference_fast_path_matches_reference(name, idx):
         torch.testing.assert_close(mine[::s], ref, **FP32)
 
 
-def test_layers_inference_fast_path():
+def test_layers_inference_fast_path(monkeypatch):
+    from allset_b200 import ops
+    monkeypatch.setattr(ops, 'FUSED_DENSE_MIN_ROWS', 0)
     for rec in load_golden('layers_small.pt'):
         e = rec['extra']
         if rec['kind'] == 'pma':
@@ -639,3 +643,59 @@ def test_c_abi_error_codes():
                                  ws.data_ptr(), 16, None) == -3                                                  # workspace
     assert h.allset_stream_eligible(1, 128, 10_000_000) == 1 and h.allset_stream_eligible(1, 20, 10_000_000) == 0
     assert h.allset_stream_eligible(1, 128, 1000) == 0
+
+
+@pytest.mark.parametrize('d', [128, 256, 512, 1024])
+@pytest.mark.parametrize('variant', ['bias_relu_ln', 'ln_only', 'bias_only', 'residual_ln', 'bias_relu'])
+def test_bias_act_norm_backward_vs_torch(d, variant):
+    from allset_b200 import ops
+    g = torch.Generator().manual_seed(d + len(variant))
+    rows = 3001                                      # not a multiple of the CTA row count: grid-stride tail
+    x = (torch.randn(rows, d, generator=g) * 2).to(dev())
+    b = torch.randn(d, generator=g).to(dev())
+    r = torch.randn(rows, d, generator=g).to(dev())
+    gam = (torch.rand(d, generator=g) + 0.5).to(dev())
+    bet = torch.randn(d, generator=g).to(dev())
+    dy = torch.randn(rows, d, generator=g).to(dev())
+    use = {'bias_relu_ln': dict(bias=b, relu=True, gamma=gam, beta=bet), 'ln_only': dict(gamma=gam, beta=bet),
+           'bias_only': dict(bias=b), 'residual_ln': dict(bias=b, relu=True, residual=r, gamma=gam, beta=bet),
+           'bias_relu': dict(bias=b, relu=True)}[variant]
+
+    def ref_fn(x_, kw):
+        t = x_ + kw['bias'] if 'bias' in kw else x_
+        if kw.get('relu'):
+            t = F.relu(t)
+        if 'residual' in kw:
+            t = t + kw['residual']
+        if 'gamma' in kw:
+            t = F.layer_norm(t, (d,), kw['gamma'], kw['beta'], 1e-5)
+        return t
+
+    leaves_a = {k: (v.clone().requires_grad_(True) if torch.is_tensor(v) else v) for k, v in use.items()}
+    leaves_b = {k: (v.clone().requires_grad_(True) if torch.is_tensor(v) else v) for k, v in use.items()}
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    out = ops.bias_act_norm(xa, **leaves_a)
+    ref = ref_fn(xb, leaves_b)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    (out * dy).sum().backward()
+    (ref * dy).sum().backward()
+    torch.testing.assert_close(xa.grad, xb.grad, rtol=1e-4, atol=1e-5)
+    for k in use:
+        if torch.is_tensor(use[k]):
+            assert_grad_close(leaves_a[k].grad, leaves_b[k].grad, k, rel=1e-4)
+
+
+def test_fused_dense_training_path_matches_reference_gradients(monkeypatch):
+    """Autograd through the fused dense glue (forward AND backward kernels) on the real citeseer model (d=128)."""
+    from allset_b200 import ops
+    monkeypatch.setattr(ops, 'FUSED_DENSE_MIN_ROWS', 0)
+    rec = load_golden('citeseer_allsettransformer.pt')
+    model, data = _build(rec)
+    data.x.requires_grad_(True)
+    out = model(data)
+    torch.testing.assert_close(out.detach().cpu(), rec['logits'], **FP32)
+    (out * rec['grad_logits'].to(dev())).sum().backward()
+    torch.testing.assert_close(data.x.grad.sum(dim=1).cpu(), rec['grad_x_rowsum'], rtol=1e-3, atol=1e-4)
+    grads = dict((k, p.grad) for k, p in model.named_parameters() if p.grad is not None)
+    for k, g in rec['grads'].items():
+        assert_grad_close(grads[k].cpu(), g, k)
