@@ -102,7 +102,8 @@ class ReplicatedRows(object):
     kernels store the rows they reduce straight into every replica over NVLink.  `barrier()` orders those stores
     before the next reader (stream-ordered device-side barrier on the symmetric-memory signal pads)."""
 
-    def __init__(self, rows: int, d: int, dtype: torch.dtype, device, group=None):
+    def __init__(self, rows: int, d: int, dtype: torch.dtype, device, group=None, multicast=None):
+        import os
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
@@ -111,9 +112,22 @@ class ReplicatedRows(object):
         self.rank, self.world = self.handle.rank, self.handle.world_size
         self.ptrs = [int(q) for q in self.handle.buffer_ptrs]
         self.row_bytes = d * self.tensor.element_size()
+        # NVLS: one store to the multicast address is replicated by the NVSwitch into every rank's buffer, so a rank
+        # sends each row ONCE instead of world-1 times (a multimem.st is an ordinary st.global on that address).
+        self.multicast_ptr = 0
+        if multicast is None:
+            multicast = os.environ.get('ALLSET_MULTICAST', '1') != '0'
+        if multicast:
+            try:
+                self.multicast_ptr = int(getattr(self.handle, 'multicast_ptr', 0) or 0)
+            except Exception:  # noqa
+                self.multicast_ptr = 0
 
     def peer_ptrs(self, first_row: int):
-        """Addresses of row `first_row` in every OTHER rank's replica."""
+        """Where the kernel must ALSO store row `first_row`...: the multicast address when the switch can replicate,
+        else that row in every other rank's replica."""
+        if self.multicast_ptr:
+            return [self.multicast_ptr + first_row * self.row_bytes]
         return [q + first_row * self.row_bytes for r, q in enumerate(self.ptrs) if r != self.rank]
 
     def barrier(self):

@@ -242,7 +242,8 @@ def run_b200(a):
         try:
             x_e = sharding.ReplicatedRows(Me, d, dtype, dev)
             x_v2 = sharding.ReplicatedRows(Nv, d, dtype, dev)
-            exchange = 'fused P2P stores from the kernel epilogue into symmetric memory + device barrier'
+            exchange = ('fused %s stores from the kernel epilogue into symmetric memory + device barrier'
+                        % ('NVLS multicast' if x_e.multicast_ptr else 'P2P'))
         except Exception as e:  # noqa
             if a.exchange == 'fused':
                 raise
