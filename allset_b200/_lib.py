@@ -42,6 +42,8 @@ SIGNATURES = {
     'allset_bias_act_norm': (_c.c_int, [_p, _p, _c.c_int, _p, _p, _p, _f32, _i64, _i32, _p, _p, _p]),
     'allset_bias_act_norm_bwd_blocks': (_i32, [_i64]),
     'allset_bias_act_norm_bwd': (_c.c_int, [_p, _p, _p, _c.c_int, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
+    'allset_mlp2_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _c.c_int, _i64, _i32,
+                                   _p, _c.c_int, _p, _p]),
     'allset_segreduce_bwd_w': (_c.c_int, [_p, _p, _c.c_int, _i32, _p, _p, _p, _i64, _p, _p]),
     'allset_pma_fwd': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
                                   _p, _i32, _i32, _p, _p, _p]),
@@ -248,6 +250,50 @@ def bias_act_norm_bwd(dy: torch.Tensor, x: torch.Tensor, bias: Optional[torch.Te
                'allset_bias_act_norm_bwd')
     sums = partial.sum(dim=0)
     return dx, dres, sums[0], sums[1], sums[2]
+
+
+MLP2_WIDTHS = (64, 128)
+
+
+def mlp2_fwd(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor,
+             b2: Optional[torch.Tensor], ln0=None, ln1=None, relu_out: bool = False,
+             out_dtype: Optional[torch.dtype] = None, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = [relu]( LN1?( relu( LN0?(x) W1^T + b1 ) ) W2^T + b2 ) in one tcgen05 kernel (bf16 operands, fp32
+    accumulate).  x [rows, d] f32|bf16, d in MLP2_WIDTHS; w1, w2 [d, d] f32 ([out, in]); ln0 / ln1 = None or
+    (gamma, beta | None, eps); out_dtype f32 (default) | bf16.  `status`: optional int32[1] diagnostic word."""
+    _need(x, 'x')
+    xd = _dtype_code(x)
+    if x.dim() != 2:
+        raise ValueError('x must be [rows, d]')
+    rows, d = x.shape
+    for name, t, shape in (('w1', w1, (d, d)), ('w2', w2, (d, d))):
+        _need(t, name, torch.float32)
+        if tuple(t.shape) != shape:
+            raise ValueError('mlp2_fwd: %s must be %s, got %s' % (name, shape, tuple(t.shape)))
+    for name, t in (('b1', b1), ('b2', b2)):
+        _need(t, name, torch.float32, optional=True)
+        if t is not None and t.numel() != d:
+            raise ValueError('mlp2_fwd: %s must have %d entries' % (name, d))
+    g = [None, None]
+    b = [None, None]
+    eps = [1e-5, 1e-5]
+    for i, ln in enumerate((ln0, ln1)):
+        if ln is None:
+            continue
+        g[i], b[i], eps[i] = ln
+        _need(g[i], 'ln%d gamma' % i, torch.float32)
+        _need(b[i], 'ln%d beta' % i, torch.float32, optional=True)
+        if g[i].numel() != d or (b[i] is not None and b[i].numel() != d):
+            raise ValueError('mlp2_fwd: LayerNorm %d parameters must have %d entries' % (i, d))
+    out_dtype = torch.float32 if out_dtype is None else out_dtype
+    out = torch.empty((rows, d), dtype=out_dtype, device=x.device)
+    od = _dtype_code(out)
+    _need(status, 'status', torch.int32, optional=True)
+    with torch.cuda.device(x.device):
+        _check(lib().allset_mlp2_fwd(_ptr(x), xd, _ptr(g[0]), _ptr(b[0]), float(eps[0]), _ptr(w1), _ptr(b1),
+                                     _ptr(g[1]), _ptr(b[1]), float(eps[1]), _ptr(w2), _ptr(b2), 1 if relu_out else 0,
+                                     rows, d, _ptr(out), od, _ptr(status), _stream()), 'allset_mlp2_fwd')
+    return out
 
 
 class Unsupported(RuntimeError):

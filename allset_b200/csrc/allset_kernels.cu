@@ -1862,6 +1862,10 @@ int elem_bytes(int dtype) { return dtype == ALLSET_F32 ? 4 : 2; }
 // =============================================================================================
 // C ABI
 // =============================================================================================
+namespace {
+#include "mlp_tcgen05.cuh"
+}  // namespace
+
 extern "C" {
 
 int allset_version(void) { return ALLSET_ABI_VERSION; }
@@ -2056,6 +2060,36 @@ int allset_bias_act_norm_bwd(const float* dy, const float* x, const float* bias,
   else
     bias_act_norm_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, x, bias, relu, residual, gamma, stats, rows, dx, dres, partial);
   return check_launch("bias_act_norm_bwd");
+}
+
+int allset_mlp2_fwd(const void* x, int x_dtype, const float* ln0_gamma, const float* ln0_beta, float ln0_eps,
+                    const float* w1, const float* b1, const float* ln1_gamma, const float* ln1_beta, float ln1_eps,
+                    const float* w2, const float* b2, int relu_out, int64_t rows, int32_t d, void* out, int out_dtype,
+                    int32_t* status, void* stream) {
+  if (rows < 0 || d <= 0) return fail(ALLSET_EINVAL, "mlp2_fwd: bad size");
+  if (bad_dtype(x_dtype) || bad_dtype(out_dtype)) return fail(ALLSET_EINVAL, "mlp2_fwd: dtype must be 0 (f32) or 1 (bf16)");
+  if (d != 64 && d != 128) return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: width %d not supported (64 or 128)", (int)d);
+  if (rows == 0) return ALLSET_OK;
+  if (x == nullptr || out == nullptr || w1 == nullptr || w2 == nullptr) return fail(ALLSET_EINVAL, "mlp2_fwd: null pointer");
+  if ((ln0_beta != nullptr && ln0_gamma == nullptr) || (ln1_beta != nullptr && ln1_gamma == nullptr))
+    return fail(ALLSET_EINVAL, "mlp2_fwd: LayerNorm beta without gamma");
+  const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w1 | (uintptr_t)w2;
+  if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: x, out, w1, w2 must be 16-byte aligned");
+  mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, ln1_gamma, ln1_beta, w2, b2, ln0_eps, ln1_eps, relu_out,
+                 (long long)rows, status};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  using bf16 = __nv_bfloat16;
+#define ALLSET_MLP2_CASE(D_)                                                                  \
+  if (d == D_) {                                                                              \
+    if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_F32) return mlp5::launch<float, float, D_>(p, st);   \
+    if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_BF16) return mlp5::launch<float, bf16, D_>(p, st);   \
+    if (x_dtype == ALLSET_BF16 && out_dtype == ALLSET_F32) return mlp5::launch<bf16, float, D_>(p, st);   \
+    return mlp5::launch<bf16, bf16, D_>(p, st);                                               \
+  }
+  ALLSET_MLP2_CASE(64)
+  ALLSET_MLP2_CASE(128)
+#undef ALLSET_MLP2_CASE
+  return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: unreachable");
 }
 
 int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32_t d, const int32_t* rowptr,

@@ -1,0 +1,462 @@
+// mlp_tcgen05.cuh -- fused two-layer MLP on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// Included by allset_kernels.cu inside its anonymous namespace (uses smem_u32 / mbar_init / ld_nc_16 from there).
+//
+// The dense glue around the aggregation is, per half layer, the reference's
+//     MLP.forward  (src/layers.py:571-579):  norm0 -> Linear -> ReLU -> norm -> dropout -> Linear
+// wrapped in F.relu by HalfNLHconv.forward (src/layers.py:631,634).  In eval mode with equal widths
+// (in = hid = out = D, the shape of 3 of the 4 MLPs of every AllDeepSets layer) this kernel does the whole
+// chain in ONE pass over the rows:
+//
+//     out[r,:] = [relu]( LN1?( relu( LN0?(x[r,:]) W1^T + b1 ) ) W2^T + b2 )
+//
+// HBM traffic = read x once + write out once (the separate LayerNorm / bias / ReLU passes and the hidden
+// activation never touch HBM), so the kernel is HBM-bound: 768 B per row at D=128 fp32-in / bf16-out against
+// 2 x 65.5 kFLOP per row -- 170 flop/B, below the bf16 ridge (~250 flop/B), which is why bf16 operands on
+// tcgen05 are the right tool: fp32 SIMT FMA (75 TFLOP/s) would be 3x over the HBM time.
+//
+// Structure (persistent, 2 CTAs of 256 threads per SM, 128-row tiles):
+//   setup   : W1, W2 (fp32 [D, D], nn.Linear layout = K-major "B" operand) -> bf16 in shared memory in the
+//             canonical K-major SWIZZLE_128B UMMA layout (8-row x 128-byte atoms, 16-byte chunk index XOR row&7);
+//             tcgen05.alloc of 2*D TMEM columns (two fp32 accumulators of 128 lanes x D columns).
+//   phase A : all 8 warps load 128 rows (coalesced 16-byte loads, a warp covers whole rows), LayerNorm with
+//             warp shuffles, write the bf16 A tile in the same swizzled layout; fence.proxy.async.
+//   MMA 1   : ONE thread issues D/16 tcgen05.mma (M=128, N=D, K=16, kind::f16, bf16 x bf16 -> fp32 in TMEM)
+//             and tcgen05.commit -> mbarrier.
+//   epi 1   : warps 0-3, thread = row = TMEM lane: tcgen05.ld 32 columns at a time, + b1, ReLU, LayerNorm
+//             (three passes over TMEM: the row lives in TMEM, not in registers), bf16 -> A tile again.
+//   MMA 2   : as MMA 1 into the second accumulator.
+//   epi 2   : + b2, ReLU, convert, stage the tile in shared memory (XOR-swizzled, conflict-free), then all
+//             8 warps write it out with coalesced 16-byte stores.
+// The second resident CTA of the SM overlaps its loads with this CTA's MMA / epilogue phases.
+
+namespace mlp5 {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 256;
+
+struct Params {
+  const void* x;
+  void* out;
+  const float* ln0_g;
+  const float* ln0_b;
+  const float* w1;
+  const float* b1;
+  const float* ln1_g;
+  const float* ln1_b;
+  const float* w2;
+  const float* b2;
+  float eps0, eps1;
+  int relu_out;
+  long long rows;
+  int* status;      // device word, set to 1 if an mbarrier wait timed out (debug aid; never in a correct run)
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate; issued by ONE thread for the whole CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 TMEM lanes (one per thread of the warp) x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in
+// bits [0,14), leading byte offset (unused for swizzled K-major, canonical value 1) in [16,30), stride byte
+// offset = 1024 B between 8-row atoms in [32,46), version 1 (sm_100) in [46,48), layout type 2 = SWIZZLE_128B
+// in [61,64).  Advancing by UMMA_K = 16 bf16 inside the 128-byte swizzle row = +32 B on the start address.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D fp32, A/B bf16, both K-major
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// bounded wait: a wrong descriptor must not hang the box -- after ~2 s flag the status word and carry on
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity, int* status) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) {
+      if (status != nullptr) atomicExch(status, 1);
+      return;
+    }
+  }
+}
+
+// byte offset of the 16-byte chunk holding columns [8*j, 8*j+8) of row r in a [rows x K] bf16 operand tile
+// stored as K/64 blocks of [rows x 64] in the K-major SWIZZLE_128B layout
+template <int ROWS>
+__device__ __forceinline__ uint32_t sw128_chunk(int r, int j) {
+  return (uint32_t)((j >> 3) * (ROWS * 128) + (r >> 3) * 1024 + (r & 7) * 128 + (((j & 7) ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_shared16(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared8(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared16(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+template <typename T>
+struct RowChunk;   // one 16-byte chunk of a feature row as floats
+template <>
+struct RowChunk<float> {
+  static constexpr int N = 4;
+  __device__ static void unpack(const uint4& q, float (&v)[4]) {
+    v[0] = __uint_as_float(q.x); v[1] = __uint_as_float(q.y); v[2] = __uint_as_float(q.z); v[3] = __uint_as_float(q.w);
+  }
+};
+template <>
+struct RowChunk<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void unpack(const uint4& q, float (&v)[8]) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+};
+
+template <int D>
+struct Layout {
+  static constexpr int KB = D / 64;                 // 128-byte swizzle blocks along K
+  static constexpr int A_BYTES = kTileM * D * 2;    // bf16 activation tile
+  static constexpr int W_BYTES = D * D * 2;         // one bf16 weight matrix
+  static constexpr int TMEM_COLS = (2 * D <= 32) ? 32 : (2 * D <= 64) ? 64 : (2 * D <= 128) ? 128 : (2 * D <= 256) ? 256 : 512;
+  template <typename TOut>
+  __host__ __device__ static constexpr int pass_bytes() { return (D * (int)sizeof(TOut) < 256) ? D * (int)sizeof(TOut) : 256; }
+  template <typename TOut>
+  __host__ __device__ static constexpr int buf_bytes() {
+    return (A_BYTES > kTileM * pass_bytes<TOut>()) ? A_BYTES : kTileM * pass_bytes<TOut>();
+  }
+  template <typename TOut>
+  __host__ __device__ static constexpr int smem_bytes() {   // + 1024 slack to align the base, + parameters, barriers, TMEM pointer
+    return 1024 + 2 * W_BYTES + buf_bytes<TOut>() + 4 * D * 4 + 64;
+  }
+};
+
+// one GEMM of the tile: acc[128 x D] = A[128 x D] * W[D x D]^T
+template <int D>
+__device__ __forceinline__ void issue_gemm(uint32_t a_base, uint32_t w_base, uint32_t tmem_acc, uint32_t bar) {
+  constexpr uint32_t idesc = instr_desc_bf16(kTileM, D);
+#pragma unroll
+  for (int k = 0; k < D / 16; ++k) {
+    const uint32_t koff = (uint32_t)((k >> 2) * (kTileM * 128) + (k & 3) * 32);
+    const uint32_t woff = (uint32_t)((k >> 2) * (D * 128) + (k & 3) * 32);
+    umma_bf16(tmem_acc, smem_desc_sw128(a_base + koff), smem_desc_sw128(w_base + woff), idesc, k > 0 ? 1u : 0u);
+  }
+  umma_commit(bar);
+}
+
+template <typename TIn, typename TOut, int D>
+__global__ void __launch_bounds__(kThreads, 2) mlp2_tcgen05_kernel(const Params p) {
+  using L = Layout<D>;
+  static_assert(D == 64 || D == 128, "mlp2_tcgen05: widths 64 and 128");
+  constexpr int PASS_BYTES = L::template pass_bytes<TOut>();
+  constexpr int OUT_ROW_BYTES = D * (int)sizeof(TOut);
+  constexpr int NPASS = OUT_ROW_BYTES / PASS_BYTES;
+  constexpr int CPP = PASS_BYTES / (int)sizeof(TOut);       // output columns per pass (multiple of 32)
+  constexpr int CHUNKS_PER_ROW = PASS_BYTES / 16;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t sW1 = raw_addr + pad;
+  const uint32_t sW2 = sW1 + L::W_BYTES;
+  const uint32_t sA = sW2 + L::W_BYTES;
+  float* sPar = reinterpret_cast<float*>(smem + 2 * L::W_BYTES + L::template buf_bytes<TOut>());   // b1, g1, be1, b2
+  const uint32_t sBar = sA + L::template buf_bytes<TOut>() + 4 * D * 4;                           // 2 mbarriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * L::W_BYTES + L::template buf_bytes<TOut>() + 4 * D * 4 + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_ln0 = p.ln0_g != nullptr, has_ln1 = p.ln1_g != nullptr;
+
+  // ---- setup ------------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    mbar_init(sBar, 1);
+    mbar_init(sBar + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), L::TMEM_COLS);
+  // weights: fp32 [D(out) x D(in)] row-major -> bf16, K-major SWIZZLE_128B
+  for (int idx = tid; idx < 2 * D * (D / 8); idx += kThreads) {
+    const int which = idx / (D * (D / 8));
+    const int rem = idx - which * (D * (D / 8));
+    const int n = rem / (D / 8), j = rem % (D / 8);
+    const float* w = (which ? p.w2 : p.w1) + (size_t)n * D + j * 8;
+    const float4 lo = *reinterpret_cast<const float4*>(w);
+    const float4 hi = *reinterpret_cast<const float4*>(w + 4);
+    st_shared16((which ? sW2 : sW1) + sw128_chunk<D>(n, j), pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w),
+                pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+  }
+  for (int i = tid; i < D; i += kThreads) {
+    sPar[i] = p.b1 ? p.b1[i] : 0.f;
+    sPar[D + i] = has_ln1 ? p.ln1_g[i] : 1.f;
+    sPar[2 * D + i] = (has_ln1 && p.ln1_b) ? p.ln1_b[i] : 0.f;
+    sPar[3 * D + i] = p.b2 ? p.b2[i] : 0.f;
+  }
+  proxy_fence_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc1 = tmem_base, tmem_acc2 = tmem_base + D;
+
+  // ---- phase A geometry: a 16-byte chunk per lane, LPR lanes per row ----------------------------------------
+  constexpr int EPC = RowChunk<TIn>::N;
+  constexpr int LPR = D / EPC;              // 32 / 16 / 8 lanes per row
+  constexpr int RPI = 32 / LPR;             // rows per warp instruction
+  constexpr int ROWS_PER_WARP = kTileM / (kThreads / 32);
+  constexpr int ITERS = ROWS_PER_WARP / RPI;
+  constexpr int UB = ITERS < 8 ? ITERS : 8;
+  const int sub = lane / LPR, cl = lane % LPR;
+  float g0[EPC], be0[EPC];
+#pragma unroll
+  for (int i = 0; i < EPC; ++i) {
+    g0[i] = has_ln0 ? p.ln0_g[cl * EPC + i] : 1.f;
+    be0[i] = (has_ln0 && p.ln0_b) ? p.ln0_b[cl * EPC + i] : 0.f;
+  }
+  const unsigned char* xb = static_cast<const unsigned char*>(p.x);
+  unsigned char* ob = static_cast<unsigned char*>(p.out);
+  const long long n_tiles = (p.rows + kTileM - 1) / kTileM;
+  uint32_t parity = 0;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
+    const long long row0 = tile * kTileM;
+
+    // ---- phase A: load rows, LayerNorm 0, bf16 A tile ---------------------------------------------------------
+#pragma unroll
+    for (int it0 = 0; it0 < ITERS; it0 += UB) {
+      uint4 raw[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int r = warp * ROWS_PER_WARP + (it0 + u) * RPI + sub;
+        const long long gr = row0 + r;
+        raw[u] = (gr < p.rows) ? ld_nc_16(xb + (size_t)gr * (D * sizeof(TIn)) + cl * 16) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int r = warp * ROWS_PER_WARP + (it0 + u) * RPI + sub;
+        float v[EPC];
+        RowChunk<TIn>::unpack(raw[u], v);
+        if (has_ln0) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < EPC; ++i) s += v[i];
+#pragma unroll
+          for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          const float mean = s * (1.f / D);
+          float q = 0.f;
+#pragma unroll
+          for (int i = 0; i < EPC; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+#pragma unroll
+          for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+          const float rstd = rsqrtf(q * (1.f / D) + p.eps0);
+#pragma unroll
+          for (int i = 0; i < EPC; ++i) v[i] = v[i] * rstd * g0[i] + be0[i];
+        }
+        // columns [cl*EPC, cl*EPC+EPC): chunk j = cl*EPC/8, byte (cl*EPC % 8) * 2 inside it
+        const uint32_t dst = sA + sw128_chunk<kTileM>(r, (cl * EPC) >> 3) + (uint32_t)(((cl * EPC) & 7) * 2);
+        if constexpr (EPC == 4) {
+          st_shared8(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+        } else {
+          st_shared16(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+      }
+    }
+    proxy_fence_async();
+    tc_fence_before();
+    __syncthreads();                                                        // S1: A tile complete
+
+    // ---- GEMM 1 -------------------------------------------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm<D>(sA, sW1, tmem_acc1, sBar);
+    }
+    __syncwarp();
+    if (warp < 4) {
+      // ---- epilogue 1: thread = row = TMEM lane -------------------------------------------------------------
+      mbar_wait_bounded(sBar, parity, p.status);
+      tc_fence_after();
+      const int r = tid;
+      const uint32_t t1 = tmem_acc1 + ((uint32_t)(warp * 32) << 16);
+      float mean = 0.f, rstd = 1.f;
+      if (has_ln1) {
+        float s = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+          float v[32];
+          tmem_ld32(t1 + c, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s += fmaxf(v[i] + sPar[c + i], 0.f);
+        }
+        mean = s * (1.f / D);
+        float q = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+          float v[32];
+          tmem_ld32(t1 + c, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float h = fmaxf(v[i] + sPar[c + i], 0.f) - mean;
+            q += h * h;
+          }
+        }
+        rstd = rsqrtf(q * (1.f / D) + p.eps1);
+      }
+#pragma unroll 1
+      for (int c = 0; c < D; c += 32) {
+        float v[32];
+        tmem_ld32(t1 + c, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float h = fmaxf(v[i] + sPar[c + i], 0.f);
+          v[i] = has_ln1 ? (h - mean) * rstd * sPar[D + c + i] + sPar[2 * D + c + i] : h;
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          st_shared16(sA + sw128_chunk<kTileM>(r, (c >> 3) + q4), pack_bf16(v[8 * q4], v[8 * q4 + 1]),
+                      pack_bf16(v[8 * q4 + 2], v[8 * q4 + 3]), pack_bf16(v[8 * q4 + 4], v[8 * q4 + 5]),
+                      pack_bf16(v[8 * q4 + 6], v[8 * q4 + 7]));
+      }
+      proxy_fence_async();
+      tc_fence_before();
+    }
+    __syncthreads();                                                        // S2: hidden tile complete
+
+    // ---- GEMM 2 -------------------------------------------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm<D>(sA, sW2, tmem_acc2, sBar + 8);
+    }
+    __syncwarp();
+    if (warp < 4) {
+      mbar_wait_bounded(sBar + 8, parity, p.status);
+      tc_fence_after();
+    }
+    // ---- epilogue 2: + b2, ReLU, convert, stage, coalesced write-out -------------------------------------------
+#pragma unroll 1
+    for (int pass = 0; pass < NPASS; ++pass) {
+      if (warp < 4) {
+        const int r = tid;
+        const uint32_t t2 = tmem_acc2 + ((uint32_t)(warp * 32) << 16) + pass * CPP;
+#pragma unroll 1
+        for (int c = 0; c < CPP; c += 32) {
+          float v[32];
+          tmem_ld32(t2 + c, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] += sPar[3 * D + pass * CPP + c + i];
+            if (p.relu_out) v[i] = fmaxf(v[i], 0.f);
+          }
+          const uint32_t rowb = sA + (uint32_t)r * PASS_BYTES;
+          if constexpr (sizeof(TOut) == 2) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int c16 = (c >> 3) + q4;
+              st_shared16(rowb + (uint32_t)((c16 ^ (r & 7)) << 4), pack_bf16(v[8 * q4], v[8 * q4 + 1]),
+                          pack_bf16(v[8 * q4 + 2], v[8 * q4 + 3]), pack_bf16(v[8 * q4 + 4], v[8 * q4 + 5]),
+                          pack_bf16(v[8 * q4 + 6], v[8 * q4 + 7]));
+            }
+          } else {
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8) {
+              const int c16 = (c >> 2) + q8;
+              st_shared16(rowb + (uint32_t)((c16 ^ (r & 7)) << 4), __float_as_uint(v[4 * q8]),
+                          __float_as_uint(v[4 * q8 + 1]), __float_as_uint(v[4 * q8 + 2]), __float_as_uint(v[4 * q8 + 3]));
+            }
+          }
+        }
+        tc_fence_before();
+      }
+      __syncthreads();                                                      // S3: staged
+#pragma unroll
+      for (int idx = tid; idx < kTileM * CHUNKS_PER_ROW; idx += kThreads) {
+        const int r = idx / CHUNKS_PER_ROW, c16 = idx % CHUNKS_PER_ROW;
+        const uint4 q = ld_shared16(sA + (uint32_t)r * PASS_BYTES + (uint32_t)((c16 ^ (r & 7)) << 4));
+        const long long gr = row0 + r;
+        if (gr < p.rows)
+          *reinterpret_cast<uint4*>(ob + (size_t)gr * OUT_ROW_BYTES + pass * PASS_BYTES + c16 * 16) = q;
+      }
+      __syncthreads();                                                      // S4: staging buffer free again
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
+}
+
+template <typename TIn, typename TOut, int D>
+int launch(const Params& p, cudaStream_t st) {
+  constexpr int smem = Layout<D>::template smem_bytes<TOut>();
+  cudaError_t e = cudaFuncSetAttribute(mlp2_tcgen05_kernel<TIn, TOut, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return fail(ALLSET_ECUDA, "mlp2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const long long n_tiles = (p.rows + kTileM - 1) / kTileM;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = 2LL * sms;
+  if (grid > n_tiles) grid = n_tiles;
+  mlp2_tcgen05_kernel<TIn, TOut, D><<<(unsigned)grid, kThreads, smem, st>>>(p);
+  return check_launch("mlp2_fwd");
+}
+
+}  // namespace mlp5

@@ -55,6 +55,9 @@ class MLP(nn.Module):
         norms = [make(in_channels) if (InputNorm and Normalization != 'None') else nn.Identity()]
         norms += [make(hidden_channels) for _ in range(depth - 1)]
         self.normalizations = nn.ModuleList(norms)
+        # extension: torch.bfloat16 lets eval-mode forwards of square two-layer MLPs run as ONE tcgen05 kernel with
+        # bf16 operands (allset_mlp2_fwd); None (default) keeps fp32 numerics (cuBLAS SGEMM + fused glue)
+        self.tc_dtype: Optional[torch.dtype] = None
 
     def reset_parameters(self):
         for lin in self.lins:
@@ -63,9 +66,17 @@ class MLP(nn.Module):
             if not isinstance(norm, nn.Identity):
                 norm.reset_parameters()
 
-    def forward(self, x, final_relu: bool = False):
+    def forward(self, x, final_relu: bool = False, out_dtype: Optional[torch.dtype] = None):
         """`final_relu` (extension, default off = reference behaviour) applies the ReLU that every caller on the path
-        wraps around the MLP (`F.relu(self.f_enc(x))`, reference src/layers.py:631,634) inside the last fused pass."""
+        wraps around the MLP (`F.relu(self.f_enc(x))`, reference src/layers.py:631,634) inside the last fused pass.
+        `out_dtype` (extension) is honoured by the tcgen05 path only; other paths return x.dtype."""
+        if self._tc_ok(x):
+            l0, l1 = self.normalizations
+            return _lib.mlp2_fwd(x.contiguous(), self.lins[0].weight, self.lins[0].bias, self.lins[1].weight,
+                                 self.lins[1].bias, self._ln_tuple(l0), self._ln_tuple(l1), final_relu,
+                                 out_dtype or torch.float32)
+        if x.dtype != self.lins[0].weight.dtype:
+            x = x.to(self.lins[0].weight.dtype)
         if self._fused_ok(x):
             y, bias = self.forward_fused_open(x)
             return ops.bias_act_norm(y, bias, relu=final_relu)
@@ -86,6 +97,23 @@ class MLP(nn.Module):
         if isinstance(self.normalizations[0], nn.LayerNorm):
             widths.append(self.lins[0].in_features)
         return all(ops.fused_dense_ok(x, w) for w in widths)
+
+    # -- tensor-core path: the whole two-layer MLP in one tcgen05 kernel (eval mode, bf16 operands) ---------------------
+    def _tc_ok(self, x) -> bool:
+        if self.tc_dtype != torch.bfloat16 or torch.is_grad_enabled() or len(self.lins) != 2:
+            return False
+        if not (x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16)):
+            return False
+        d = x.shape[1]
+        if d not in _lib.MLP2_WIDTHS or x.shape[0] < ops.FUSED_DENSE_MIN_ROWS:
+            return False
+        if any(tuple(lin.weight.shape) != (d, d) or lin.weight.dtype != torch.float32 for lin in self.lins):
+            return False
+        return all(isinstance(n, (nn.LayerNorm, nn.Identity)) for n in self.normalizations)
+
+    @staticmethod
+    def _ln_tuple(norm):
+        return (norm.weight, norm.bias, norm.eps) if isinstance(norm, nn.LayerNorm) else None
 
     @staticmethod
     def _ln(norm):
@@ -218,22 +246,37 @@ class HalfNLHconv(nn.Module):
                     f.reset_parameters()
 
     def set_agg_dtype(self, dtype: Optional[torch.dtype]):
+        """bf16 storage for the gathered rows also switches the eval-mode MLPs around the aggregation to the tcgen05
+        kernel with bf16 operands (same 1e-2 accuracy class); fp32 / None keeps fp32 numerics end to end."""
         self.agg_dtype = dtype
         if self.attention:
             self.prop.agg_dtype = dtype
+        else:
+            for f in (self.f_enc, self.f_dec):
+                if isinstance(f, MLP):
+                    f.tc_dtype = dtype if dtype == torch.bfloat16 else None
 
     def forward(self, x, edge_index, norm, aggr='add'):
         if self.attention:
             return self.prop(x, edge_index)              # norm and aggr are ignored, as in the reference
         if aggr is None:
             raise ValueError('aggr was not passed!')
-        x = self.f_enc(x, final_relu=True) if isinstance(self.f_enc, MLP) else F.relu(self.f_enc(x))
+        io_dtype = x.dtype
+        if isinstance(self.f_enc, MLP):
+            x = self.f_enc(x, final_relu=True, out_dtype=self.agg_dtype)    # tcgen05 path writes the storage dtype
+        else:
+            x = F.relu(self.f_enc(x))
         x = F.dropout(x, p=self.dropout, training=self.training)
         inc = _resolve(edge_index, x.size(0))
         weight = None
         if norm is not None and not (not norm.requires_grad and inc.weights_all_one(norm)):
             weight = norm
         xs = x if self.agg_dtype is None else x.to(self.agg_dtype)
-        x = ops.segment_reduce(xs, inc, weight, aggr).to(x.dtype)
-        x = self.f_dec(x, final_relu=True) if isinstance(self.f_dec, MLP) else F.relu(self.f_dec(x))
+        x = ops.segment_reduce(xs, inc, weight, aggr)
+        if isinstance(self.f_dec, MLP):
+            if not self.f_dec._tc_ok(x):             # the tcgen05 path reads the storage dtype directly
+                x = x.to(io_dtype)
+            x = self.f_dec(x, final_relu=True, out_dtype=io_dtype)
+        else:
+            x = F.relu(self.f_dec(x.to(io_dtype)))
         return x

@@ -121,6 +121,23 @@ int allset_bias_act_norm(const float* x, const float* bias, int relu, const floa
                          const float* gamma, const float* beta, float eps,
                          int64_t rows, int32_t d, float* out, float* stats, void* stream);
 
+/* Fused two-layer MLP on the tcgen05 tensor cores (bf16 operands, fp32 accumulate in TMEM), eval mode, equal widths
+ * in = hid = out = d in {64, 128}:
+ *     out[r, :] = [relu]( LN1?( relu( LN0?(x[r, :]) W1^T + b1 ) ) W2^T + b2 )
+ * = MLP.forward with num_layers == 2 (src/layers.py:571-579: norm0 -> Linear -> ReLU -> norm -> dropout(eval) -> Linear)
+ * plus the F.relu HalfNLHconv wraps around it (src/layers.py:631,634) when relu_out != 0, in ONE pass over the rows.
+ * x [rows, d] f32|bf16; w1, w2 [d, d] f32 in nn.Linear layout ([out, in]); b1, b2 [d] f32 or NULL;
+ * ln*_gamma NULL = no LayerNorm at that position (Normalization 'None' / InputNorm False); out [rows, d] f32|bf16.
+ * Accuracy is that of bf16 operands (the 1e-2 bar of north_star's bf16 mode), not fp32: callers that need 1e-4
+ * keep the cuBLAS SGEMM + allset_bias_act_norm chain.  status: device int32 or NULL, set to 1 if an internal
+ * mbarrier wait timed out (diagnostic; never in a correct run).  ALLSET_EUNSUPPORTED for other widths. */
+int allset_mlp2_fwd(const void* x, int x_dtype,
+                    const float* ln0_gamma, const float* ln0_beta, float ln0_eps,
+                    const float* w1, const float* b1,
+                    const float* ln1_gamma, const float* ln1_beta, float ln1_eps,
+                    const float* w2, const float* b2, int relu_out,
+                    int64_t rows, int32_t d, void* out, int out_dtype, int32_t* status, void* stream);
+
 /* Backward of allset_bias_act_norm (d in {128,256,512,1024}; ALLSET_EUNSUPPORTED otherwise):
  *   dx [rows, d] = gradient w.r.t. x;  dres [rows, d] or NULL = gradient w.r.t. residual;
  *   partial [blocks, 3, d] = per-CTA column sums of (d gamma, d beta, d bias), blocks =

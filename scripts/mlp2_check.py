@@ -1,0 +1,143 @@
+"""GPU check + timing of the tcgen05 fused MLP (allset_mlp2_fwd) against torch references.
+Run on the GPU box:  timeout 300 python scripts/mlp2_check.py [--time]
+Prints one JSON line per case; exit code 1 if any case is out of tolerance."""
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from allset_b200 import _lib  # noqa: E402
+
+dev = torch.device('cuda:0')
+bad = 0
+
+
+def bf(t):
+    return t.bfloat16().float()
+
+
+def reference(x, w1, b1, w2, b2, ln0, ln1, relu_out, emulate):
+    """emulate=True rounds the GEMM operands to bf16 exactly where the kernel does (fp32 accumulate)."""
+    r = bf if emulate else (lambda t: t)
+    h = x.float()
+    d = h.shape[1]
+    if ln0 is not None:
+        h = F.layer_norm(h, (d,), ln0[0], ln0[1], ln0[2])
+    h = r(h) @ r(w1).t()
+    if b1 is not None:
+        h = h + b1
+    h = F.relu(h)
+    if ln1 is not None:
+        h = F.layer_norm(h, (d,), ln1[0], ln1[1], ln1[2])
+    h = r(h) @ r(w2).t()
+    if b2 is not None:
+        h = h + b2
+    return F.relu(h) if relu_out else h
+
+
+def diagnose(out, ref):
+    err = (out - ref).abs()
+    wrong = err > 1e-2 * (1 + ref.abs())
+    rows, d = out.shape
+    return {'wrong_frac': float(wrong.float().mean()),
+            'wrong_by_col8': [round(float(wrong[:, c:c + 8].float().mean()), 3) for c in range(0, d, 8)],
+            'wrong_by_row_mod8': [round(float(wrong[i::8].float().mean()), 3) for i in range(8)],
+            'wrong_by_row32': [round(float(wrong[i:i + 32].float().mean()), 3) for i in range(0, min(rows, 256), 32)]}
+
+
+def case(name, rows, d, in_dtype, out_dtype, ln0, ln1, bias, relu_out, weights='rand', tol=2e-2):
+    global bad
+    g = torch.Generator(device='cpu').manual_seed(1234 + rows + d)
+    x = torch.randn(rows, d, generator=g).to(dev)
+    if weights == 'identity':
+        x = x.abs()
+        w1 = torch.eye(d, device=dev)
+        w2 = torch.eye(d, device=dev)
+    else:
+        w1 = (torch.randn(d, d, generator=g) / d ** 0.5).to(dev)
+        w2 = (torch.eye(d) if weights == 'w2_identity' else torch.randn(d, d, generator=g) / d ** 0.5).to(dev)
+    b1 = torch.randn(d, generator=g).to(dev) * 0.3 if bias else None
+    b2 = torch.randn(d, generator=g).to(dev) * 0.3 if bias else None
+    mk = lambda: (1 + 0.2 * torch.randn(d, generator=g).to(dev), 0.2 * torch.randn(d, generator=g).to(dev), 1e-5)
+    l0 = mk() if ln0 else None
+    l1 = mk() if ln1 else None
+    xin = x.to(in_dtype).contiguous()
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = _lib.mlp2_fwd(xin, w1, b1, w2, b2, l0, l1, relu_out, out_dtype, status)
+    torch.cuda.synchronize()
+    ref_e = reference(xin, w1, b1, w2, b2, l0, l1, relu_out, True)
+    ref_f = reference(xin, w1, b1, w2, b2, l0, l1, relu_out, False)
+    o = out.float()
+    scale = float(ref_f.abs().max()) + 1e-6
+    e_emul = float((o - ref_e).abs().max()) / scale
+    e_fp32 = float((o - ref_f).abs().max()) / scale
+    ok = bool(torch.isfinite(o).all()) and e_emul < tol and int(status.item()) == 0
+    rec = {'case': name, 'rows': rows, 'd': d, 'in': str(in_dtype), 'out': str(out_dtype), 'status': int(status.item()),
+           'rel_err_vs_bf16_emulation': e_emul, 'rel_err_vs_fp32': e_fp32, 'ok': ok}
+    if not ok:
+        bad += 1
+        rec['diag'] = diagnose(o, ref_e)
+    print(json.dumps(rec), flush=True)
+
+
+def timing(rows, d, in_dtype, out_dtype):
+    x = torch.randn(rows, d, device=dev).to(in_dtype)
+    w1 = torch.randn(d, d, device=dev) / d ** 0.5
+    w2 = torch.randn(d, d, device=dev) / d ** 0.5
+    b = torch.zeros(d, device=dev)
+    ln = (torch.ones(d, device=dev), torch.zeros(d, device=dev), 1e-5)
+    f = lambda: _lib.mlp2_fwd(x, w1, b, w2, b, ln, ln, True, out_dtype)
+    for _ in range(5):
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 30
+    e0.record()
+    for _ in range(n):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    nbytes = rows * d * (x.element_size() + torch.empty(0, dtype=out_dtype).element_size())
+    # the unfused chain this replaces: LN, GEMM, bias+relu+LN, GEMM, bias+relu (fp32, cuBLAS + bias_act_norm)
+    xf = x.float()
+
+    def chain():
+        h = _lib.bias_act_norm(xf, gamma=ln[0], beta=ln[1])
+        h = _lib.bias_act_norm(F.linear(h, w1), b, True, None, ln[0], ln[1])
+        return _lib.bias_act_norm(F.linear(h, w2), b, True)
+    for _ in range(3):
+        chain()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        chain()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_chain = e0.elapsed_time(e1) / 10
+    print(json.dumps({'timing': True, 'rows': rows, 'd': d, 'in': str(in_dtype), 'out': str(out_dtype), 'ms': ms,
+                      'GBps': nbytes / ms / 1e6, 'tflops': 4.0 * rows * d * d / ms / 1e9,
+                      'ms_unfused_fp32_chain': ms_chain}), flush=True)
+
+
+f32, b16 = torch.float32, torch.bfloat16
+case('identity', 128, 128, f32, f32, False, False, False, False, 'identity', tol=1e-6)
+case('identity_d64', 128, 64, f32, f32, False, False, False, False, 'identity', tol=1e-6)
+case('w2_identity', 256, 128, f32, f32, False, False, False, False, 'w2_identity')
+case('rand_nobias', 384, 128, f32, f32, False, False, False, False)
+case('full', 1000, 128, f32, f32, True, True, True, True)
+case('full_bf16out', 128 * 300 + 17, 128, f32, b16, True, True, True, True)
+case('full_bf16in', 128 * 300 + 17, 128, b16, f32, True, True, True, True)
+case('full_bf16_both', 5, 128, b16, b16, True, True, True, False)
+case('noln', 70000, 128, f32, f32, False, False, True, True)
+case('ln0_only', 4096, 128, f32, b16, True, False, True, True)
+case('d64_full', 128 * 700 + 3, 64, f32, f32, True, True, True, True)
+case('d64_bf16', 999, 64, b16, b16, True, True, True, True)
+if '--time' in sys.argv and bad == 0:
+    for ind, outd in ((f32, b16), (b16, f32), (f32, f32), (b16, b16)):
+        timing(1 << 20, 128, ind, outd)
+    timing(1 << 20, 64, f32, b16)
+sys.exit(1 if bad else 0)

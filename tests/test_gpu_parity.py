@@ -699,3 +699,93 @@ def test_fused_dense_training_path_matches_reference_gradients(monkeypatch):
     grads = dict((k, p.grad) for k, p in model.named_parameters() if p.grad is not None)
     for k, g in rec['grads'].items():
         assert_grad_close(grads[k].cpu(), g, k)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 fused two-layer MLP (allset_mlp2_fwd): bf16 operands => the 1e-2 class of north_star's bf16 mode
+# ---------------------------------------------------------------------------------------------------------
+def _mlp_module(d, norm, input_norm, seed):
+    torch.manual_seed(seed)
+    m = ab().MLP(d, d, d, 2, dropout=0.5, Normalization=norm, InputNorm=input_norm)
+    with torch.no_grad():                        # non-trivial LayerNorm parameters and biases
+        for n in m.normalizations:
+            if isinstance(n, torch.nn.LayerNorm):
+                n.weight.add_(0.2 * torch.randn_like(n.weight))
+                n.bias.add_(0.2 * torch.randn_like(n.bias))
+        for lin in m.lins:
+            lin.bias.add_(0.3 * torch.randn_like(lin.bias))
+    return m.eval()
+
+
+@pytest.mark.parametrize('d', [128, 64])
+@pytest.mark.parametrize('norm,input_norm', [('ln', True), ('ln', False), ('None', False)])
+@pytest.mark.parametrize('in_dtype,out_dtype', [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                                (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize('rows', [8192 + 77, 128 * 1200])
+def test_mlp2_tcgen05_vs_oracle(d, norm, input_norm, in_dtype, out_dtype, rows):
+    m = _mlp_module(d, norm, input_norm, seed=rows % 97 + d)
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(rows, d, generator=torch.Generator().manual_seed(rows)).to(in_dtype)
+    ref = F.relu(O.mlp(params, '', x.float()))                       # CPU oracle, fp32
+    m.to(dev())
+    m.tc_dtype = torch.bfloat16
+    with torch.no_grad():
+        assert m._tc_ok(x.to(dev()))
+        out = m(x.to(dev()), final_relu=True, out_dtype=out_dtype)
+    assert out.dtype == out_dtype and out.shape == (rows, d)
+    err = (out.float().cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 1e-2 * max(scale, 1.0), (err, scale)
+    # without the final ReLU (the classifier-style call)
+    with torch.no_grad():
+        out2 = m(x.to(dev())[:9000], final_relu=False)
+    ref2 = O.mlp(params, '', x.float()[:9000])
+    assert (out2.cpu() - ref2).abs().max().item() <= 1e-2 * max(ref2.abs().max().item(), 1.0)
+
+
+def test_mlp2_tcgen05_small_and_ragged_row_counts():
+    from allset_b200 import _lib
+    d = 128
+    m = _mlp_module(d, 'ln', True, seed=5).to(dev())
+    l0, l1 = m.normalizations
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    for rows in (1, 5, 127, 128, 129, 1000):
+        x = torch.randn(rows, d, generator=torch.Generator().manual_seed(rows))
+        status = torch.zeros(1, dtype=torch.int32, device=dev())
+        out = _lib.mlp2_fwd(x.to(dev()), m.lins[0].weight.detach(), m.lins[0].bias.detach(), m.lins[1].weight.detach(),
+                            m.lins[1].bias.detach(), (l0.weight.detach(), l0.bias.detach(), l0.eps),
+                            (l1.weight.detach(), l1.bias.detach(), l1.eps), False, torch.float32, status)
+        ref = O.mlp(params, '', x)
+        assert int(status.item()) == 0
+        assert (out.cpu() - ref).abs().max().item() <= 1e-2 * max(ref.abs().max().item(), 1.0), rows
+    assert _lib.mlp2_fwd(torch.empty(0, d, device=dev()), m.lins[0].weight.detach(), None, m.lins[1].weight.detach(),
+                         None).shape == (0, d)
+    with pytest.raises(RuntimeError, match='not supported'):
+        _lib.mlp2_fwd(torch.zeros(4, 96, device=dev()), torch.zeros(96, 96, device=dev()), None,
+                      torch.zeros(96, 96, device=dev()), None)
+
+
+def test_alldeepsets_bf16_mode_uses_tcgen05_mlps_and_matches_oracle(monkeypatch):
+    """AllDeepSets, d=128, eval, agg_dtype=bf16: every square MLP runs as ONE tcgen05 kernel (counted), the gathered
+    rows are written / read in bf16 directly, and the logits stay within the bf16 bar of the fp32 oracle."""
+    from allset_b200 import _lib, synthetic
+    n, m_e, d = 40000, 10000, 128
+    ei = synthetic.poisson_hypergraph(n, m_e, 12, seed=3, device=dev())
+    args = O.config_namespace(num_features=d, num_classes=7, MLP_hidden=d, Classifier_hidden=64, All_num_layers=2,
+                              PMA=False, aggregate='mean', normalization='ln', deepset_input_norm=True)
+    torch.manual_seed(0)
+    model = ab().SetGNN(args, agg_dtype=torch.bfloat16).to(dev()).eval()
+    data = _Data()
+    data.x = torch.randn(n, d, device=dev())
+    data.edge_index = ei.clone()
+    data.norm = torch.ones(ei.shape[1], dtype=torch.int64, device=dev())
+    calls = []
+    real = _lib.mlp2_fwd
+    monkeypatch.setattr(_lib, 'mlp2_fwd', lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    with torch.no_grad():
+        logits = model(data)
+    assert len(calls) == 8                         # 2 layers x 2 half layers x (f_enc, f_dec)
+    params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref, _ = O.setgnn(params, data.x.cpu(), ei.cpu(), data.norm.cpu(), PMA=False, aggregate='mean')
+    err = (logits.cpu() - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
