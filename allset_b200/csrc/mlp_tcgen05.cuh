@@ -109,10 +109,13 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// bounded wait: a wrong descriptor must not hang the box -- after ~2 s flag the status word and carry on
+// bounded wait: a wrong descriptor must not hang the box -- after ~2 s flag the status word and carry on.
+// SLEEP_NS > 0: back off between polls (producers run far ahead; their polling must not steal issue slots from
+// the epilogue warps on the same scheduler).
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity, int* status) {
-  const long long t0 = clock64();
-  for (;;) {
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -120,9 +123,13 @@ __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity,
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
-    if (clock64() - t0 > 4000000000LL) {
-      if (status != nullptr) atomicExch(status, 1);
-      return;
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    if ((spins & 1023u) == 1023u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) {
+        if (status != nullptr) atomicExch(status, 1);
+        return;
+      }
     }
   }
 }
@@ -444,18 +451,362 @@ __global__ void __launch_bounds__(kThreads, 2) mlp2_tcgen05_kernel(const Params 
   if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
+
+// =================================================================================================================
+// Warp-specialised pipeline, ONE persistent CTA of 16 warps (512 threads x 128 registers = the whole file) per SM
+//   warps 0-7  : two epilogue groups of 4 warps (TMEM lane quadrant = warp & 3).  Group g owns the local tiles
+//                g, g+2, ... and a private set of buffers: A stage g, hidden tile g, accumulators acc1[g] / acc2[g].
+//                Per tile: wait acc1_full -> epi 1 (+b1, ReLU, LayerNorm, bf16) -> hidden tile -> group barrier ->
+//                thread 0 of the group issues GEMM 2 of this tile AND GEMM 1 of the group's next tile -> wait
+//                acc2_full -> epi 2 (+b2, ReLU, convert) -> staged in the hidden buffer -> coalesced stores.
+//                While one group waits for its GEMM 2 the other one is inside its epilogue.
+//   warps 8-15 : producers: rolling register prefetch of the next rows, LayerNorm 0, bf16 A tile (stage = tile & 1)
+// mbarriers per buffer set: a_full (8 producer warps -> issuing thread), a_empty (tcgen05.commit -> producers),
+// acc1_full / acc2_full (tcgen05.commit -> epilogue group).  TMEM: 4*D columns (512 at D = 128).
+// =================================================================================================================
+constexpr int kEpiGroups = 2;
+constexpr int kEpiWarps = 4 * kEpiGroups;
+constexpr int kProdWarps = 8;
+constexpr int kWsThreads = (kEpiWarps + kProdWarps) * 32;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync(int group) {
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+template <int D>
+struct WsLayout {
+  using L = Layout<D>;
+  static constexpr int TMEM_COLS = (4 * D <= 256) ? 256 : 512;
+  template <typename TOut>
+  __host__ __device__ static constexpr int smem_bytes() {
+    return 1024 + 2 * L::W_BYTES + 2 * L::A_BYTES + 2 * L::template buf_bytes<TOut>() + 4 * D * 4 + 256;
+  }
+};
+
+template <typename TIn, int D, int HALF>
+struct Producer {
+  static constexpr int EPC = RowChunk<TIn>::N;
+  static constexpr int LPR = D / EPC;
+  static constexpr int RPI = 32 / LPR;
+  static constexpr int ROWS_PER_WARP = kTileM / kProdWarps;
+
+  __device__ static __forceinline__ void load(uint4 (&buf)[HALF], const unsigned char* xb, long long row0, long long rows,
+                                              int pw, int half, int sub, int cl) {
+#pragma unroll
+    for (int u = 0; u < HALF; ++u) {
+      const int r = pw * ROWS_PER_WARP + (half * HALF + u) * RPI + sub;
+      const long long gr = row0 + r;
+      buf[u] = (gr < rows) ? ld_nc_16(xb + (size_t)gr * (D * sizeof(TIn)) + cl * 16) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  // The HALF rows are reduced in LOCKSTEP (offset loop outermost): shuffles keep program order, so a row-at-a-time
+  // loop serialises 10 dependent ~25-cycle SHFLs per row; here every butterfly step has HALF independent ones.
+  __device__ static __forceinline__ void process(const uint4 (&buf)[HALF], uint32_t sAst, int pw, int half, int sub,
+                                                 int cl, bool has_ln0, float eps0, const float (&g0)[EPC],
+                                                 const float (&be0)[EPC]) {
+    float v[HALF][EPC];
+#pragma unroll
+    for (int u = 0; u < HALF; ++u) RowChunk<TIn>::unpack(buf[u], v[u]);
+    if (has_ln0) {
+      float s[HALF];
+#pragma unroll
+      for (int u = 0; u < HALF; ++u) {
+        s[u] = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) s[u] += v[u][i];
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < HALF; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+      }
+#pragma unroll
+      for (int u = 0; u < HALF; ++u) {
+        const float mean = s[u] * (1.f / D);
+        s[u] = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) { v[u][i] -= mean; s[u] = fmaf(v[u][i], v[u][i], s[u]); }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < HALF; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+      }
+#pragma unroll
+      for (int u = 0; u < HALF; ++u) {
+        const float rstd = rsqrtf(s[u] * (1.f / D) + eps0);
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) v[u][i] = v[u][i] * rstd * g0[i] + be0[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < HALF; ++u) {
+      const int r = pw * ROWS_PER_WARP + (half * HALF + u) * RPI + sub;
+      const uint32_t dst = sAst + sw128_chunk<kTileM>(r, (cl * EPC) >> 3) + (uint32_t)(((cl * EPC) & 7) * 2);
+      if constexpr (EPC == 4) {
+        st_shared8(dst, pack_bf16(v[u][0], v[u][1]), pack_bf16(v[u][2], v[u][3]));
+      } else {
+        st_shared16(dst, pack_bf16(v[u][0], v[u][1]), pack_bf16(v[u][2], v[u][3]), pack_bf16(v[u][4], v[u][5]),
+                    pack_bf16(v[u][6], v[u][7]));
+      }
+    }
+  }
+};
+
+template <typename TIn, typename TOut, int D>
+__global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) {
+  using L = Layout<D>;
+  static_assert(D == 64 || D == 128, "mlp2_ws: widths 64 and 128");
+  constexpr int PASS_BYTES = L::template pass_bytes<TOut>();
+  constexpr int OUT_ROW_BYTES = D * (int)sizeof(TOut);
+  constexpr int NPASS = OUT_ROW_BYTES / PASS_BYTES;
+  constexpr int CPP = PASS_BYTES / (int)sizeof(TOut);
+  constexpr int CHUNKS_PER_ROW = PASS_BYTES / 16;
+  constexpr int BUF = L::template buf_bytes<TOut>();
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t sW1 = raw_addr + pad;
+  const uint32_t sW2 = sW1 + L::W_BYTES;
+  const uint32_t sA0 = sW2 + L::W_BYTES;                 // 2 stages of L::A_BYTES
+  const uint32_t sA1 = sA0 + 2 * L::A_BYTES;             // 2 hidden tiles / output staging buffers of BUF bytes
+  constexpr int PAR_OFF = 2 * L::W_BYTES + 2 * L::A_BYTES + 2 * BUF;
+  float* sPar = reinterpret_cast<float*>(smem + PAR_OFF);                       // b1, g1, be1, b2
+  const uint32_t sBar = sW1 + PAR_OFF + 4 * D * 4;                              // 8 mbarriers, [kind][buffer set]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PAR_OFF + 4 * D * 4 + 128);
+  const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 16, bar_acc1_full = sBar + 32, bar_acc2_full = sBar + 48;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_ln0 = p.ln0_g != nullptr, has_ln1 = p.ln1_g != nullptr;
+
+  // ---- setup ------------------------------------------------------------------------------------------------
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_a_full + 8 * b, kProdWarps);
+      mbar_init(bar_a_empty + 8 * b, 1);
+      mbar_init(bar_acc1_full + 8 * b, 1);
+      mbar_init(bar_acc2_full + 8 * b, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), WsLayout<D>::TMEM_COLS);
+  for (int idx = tid; idx < 2 * D * (D / 8); idx += kWsThreads) {
+    const int which = idx / (D * (D / 8));
+    const int rem = idx - which * (D * (D / 8));
+    const int n = rem / (D / 8), j = rem % (D / 8);
+    const float* w = (which ? p.w2 : p.w1) + (size_t)n * D + j * 8;
+    const float4 lo = *reinterpret_cast<const float4*>(w);
+    const float4 hi = *reinterpret_cast<const float4*>(w + 4);
+    st_shared16((which ? sW2 : sW1) + sw128_chunk<D>(n, j), pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w),
+                pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+  }
+  for (int i = tid; i < D; i += kWsThreads) {
+    sPar[i] = p.b1 ? p.b1[i] : 0.f;
+    sPar[D + i] = has_ln1 ? p.ln1_g[i] : 1.f;
+    sPar[2 * D + i] = (has_ln1 && p.ln1_b) ? p.ln1_b[i] : 0.f;
+    sPar[3 * D + i] = p.b2 ? p.b2[i] : 0.f;
+  }
+  proxy_fence_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long n_tiles = (p.rows + kTileM - 1) / kTileM;
+
+  if (warp >= kEpiWarps) {
+    // ======================= producers =====================================================================
+    using P = Producer<TIn, D, (kTileM / kProdWarps) / (32 / (D / RowChunk<TIn>::N)) / 2>;
+    constexpr int HALF = (kTileM / kProdWarps) / P::RPI / 2;
+    static_assert(HALF >= 1, "producer geometry");
+    const int pw = warp - kEpiWarps;
+    const int sub = lane / P::LPR, cl = lane % P::LPR;
+    float g0[P::EPC], be0[P::EPC];
+#pragma unroll
+    for (int i = 0; i < P::EPC; ++i) {
+      g0[i] = has_ln0 ? p.ln0_g[cl * P::EPC + i] : 1.f;
+      be0[i] = (has_ln0 && p.ln0_b) ? p.ln0_b[cl * P::EPC + i] : 0.f;
+    }
+    const unsigned char* xb = static_cast<const unsigned char*>(p.x);
+    uint4 bufA[HALF], bufB[HALF];
+    long long tile = blockIdx.x;
+    if (tile < n_tiles) {
+      P::load(bufA, xb, tile * kTileM, p.rows, pw, 0, sub, cl);
+      P::load(bufB, xb, tile * kTileM, p.rows, pw, 1, sub, cl);
+    }
+    for (uint32_t it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t st = it & 1u;
+      const long long next = tile + gridDim.x;
+      if (it >= 2) mbar_wait_bounded<128>(bar_a_empty + 8 * st, ((it >> 1) - 1) & 1u, p.status);
+      const uint32_t sAst = sA0 + st * L::A_BYTES;
+      P::process(bufA, sAst, pw, 0, sub, cl, has_ln0, p.eps0, g0, be0);
+      if (next < n_tiles) P::load(bufA, xb, next * kTileM, p.rows, pw, 0, sub, cl);
+      P::process(bufB, sAst, pw, 1, sub, cl, has_ln0, p.eps0, g0, be0);
+      if (next < n_tiles) P::load(bufB, xb, next * kTileM, p.rows, pw, 1, sub, cl);
+      proxy_fence_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_full + 8 * st);
+    }
+  } else {
+    // ======================= epilogue groups: thread = row = TMEM lane ==========================================
+    const int g = warp >> 2;                           // group = buffer index
+    const int r = tid & 127;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tmem_acc1 = tmem_base + g * D, tmem_acc2 = tmem_base + 2 * D + g * D;
+    const uint32_t sH = sA1 + g * BUF;
+    unsigned char* ob = static_cast<unsigned char*>(p.out);
+    const bool issuer = (r == 0);                      // one thread per group issues its tcgen05.mma / commit
+    const uint32_t sAg = sA0 + g * L::A_BYTES;
+    auto gemm1 = [&](uint32_t kk) {                    // GEMM 1 of this group's kk-th tile: A stage g x W1 -> acc1[g]
+      mbar_wait_bounded(bar_a_full + 8 * g, kk & 1u, p.status);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks) {
+        const uint32_t koff = (uint32_t)((ks >> 2) * (kTileM * 128) + (ks & 3) * 32);
+        const uint32_t woff = (uint32_t)((ks >> 2) * (D * 128) + (ks & 3) * 32);
+        umma_bf16(tmem_acc1, smem_desc_sw128(sAg + koff), smem_desc_sw128(sW1 + woff), instr_desc_bf16(kTileM, D),
+                  ks > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_a_empty + 8 * g);
+      umma_commit(bar_acc1_full + 8 * g);
+    };
+    long long tile = blockIdx.x + (long long)g * gridDim.x;
+    if (issuer && tile < n_tiles) gemm1(0);
+    __syncwarp();
+    uint32_t k = 0;                                    // this group's tile counter
+    for (; tile < n_tiles; tile += 2LL * gridDim.x, ++k) {
+      const long long row0 = tile * kTileM;
+      // ---- epilogue 1 ----------------------------------------------------------------------------------------
+      mbar_wait_bounded(bar_acc1_full + 8 * g, k & 1u, p.status);
+      tc_fence_after();
+      const uint32_t t1 = tmem_acc1 + lane_off;
+      float mean = 0.f, rstd = 1.f;
+      if (has_ln1) {
+        float s = 0.f, q = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+          float v[32];
+          tmem_ld32(t1 + c, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float h = fmaxf(v[i] + sPar[c + i], 0.f);
+            s += h;
+            q = fmaf(h, h, q);
+          }
+        }
+        mean = s * (1.f / D);
+        rstd = rsqrtf(fmaxf(q * (1.f / D) - mean * mean, 0.f) + p.eps1);
+      }
+#pragma unroll 1
+      for (int c = 0; c < D; c += 32) {
+        float v[32];
+        tmem_ld32(t1 + c, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float h = fmaxf(v[i] + sPar[c + i], 0.f);
+          v[i] = has_ln1 ? (h - mean) * rstd * sPar[D + c + i] + sPar[2 * D + c + i] : h;
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          st_shared16(sH + sw128_chunk<kTileM>(r, (c >> 3) + q4), pack_bf16(v[8 * q4], v[8 * q4 + 1]),
+                      pack_bf16(v[8 * q4 + 2], v[8 * q4 + 3]), pack_bf16(v[8 * q4 + 4], v[8 * q4 + 5]),
+                      pack_bf16(v[8 * q4 + 6], v[8 * q4 + 7]));
+      }
+      proxy_fence_async();
+      tc_fence_before();
+      epi_bar_sync(g);                           // hidden tile complete, acc1[g] drained by all 128 threads
+      if (issuer) {
+        tc_fence_after();
+        issue_gemm<D>(sH, sW2, tmem_acc2, bar_acc2_full + 8 * g);       // acc2[g] was drained before the last barrier
+        if (tile + 2LL * gridDim.x < n_tiles) gemm1(k + 1);             // runs under epilogue 2 of this tile
+      }
+      __syncwarp();
+      // ---- epilogue 2 ----------------------------------------------------------------------------------------
+      mbar_wait_bounded(bar_acc2_full + 8 * g, k & 1u, p.status);
+      tc_fence_after();
+#pragma unroll 1
+      for (int pass = 0; pass < NPASS; ++pass) {
+        const uint32_t t2 = tmem_acc2 + lane_off + pass * CPP;
+        const uint32_t rowb = sH + (uint32_t)r * PASS_BYTES;
+#pragma unroll 1
+        for (int c = 0; c < CPP; c += 32) {
+          float v[32];
+          tmem_ld32(t2 + c, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] += sPar[3 * D + pass * CPP + c + i];
+            if (p.relu_out) v[i] = fmaxf(v[i], 0.f);
+          }
+          if constexpr (sizeof(TOut) == 2) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int c16 = (c >> 3) + q4;
+              st_shared16(rowb + (uint32_t)((c16 ^ (r & 7)) << 4), pack_bf16(v[8 * q4], v[8 * q4 + 1]),
+                          pack_bf16(v[8 * q4 + 2], v[8 * q4 + 3]), pack_bf16(v[8 * q4 + 4], v[8 * q4 + 5]),
+                          pack_bf16(v[8 * q4 + 6], v[8 * q4 + 7]));
+            }
+          } else {
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8) {
+              const int c16 = (c >> 2) + q8;
+              st_shared16(rowb + (uint32_t)((c16 ^ (r & 7)) << 4), __float_as_uint(v[4 * q8]),
+                          __float_as_uint(v[4 * q8 + 1]), __float_as_uint(v[4 * q8 + 2]), __float_as_uint(v[4 * q8 + 3]));
+            }
+          }
+        }
+        tc_fence_before();                       // (last pass: acc2[g] drained before the barrier below)
+        epi_bar_sync(g);                         // staged
+#pragma unroll
+        for (int idx = r; idx < kTileM * CHUNKS_PER_ROW; idx += 128) {
+          const int rr = idx / CHUNKS_PER_ROW, c16 = idx % CHUNKS_PER_ROW;
+          const uint4 qv = ld_shared16(sH + (uint32_t)rr * PASS_BYTES + (uint32_t)((c16 ^ (rr & 7)) << 4));
+          const long long gr = row0 + rr;
+          if (gr < p.rows)
+            *reinterpret_cast<uint4*>(ob + (size_t)gr * OUT_ROW_BYTES + pass * PASS_BYTES + c16 * 16) = qv;
+        }
+        epi_bar_sync(g);                         // staging buffer (= hidden tile) free again
+      }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, WsLayout<D>::TMEM_COLS);
+}
+
 template <typename TIn, typename TOut, int D>
 int launch(const Params& p, cudaStream_t st) {
-  constexpr int smem = Layout<D>::template smem_bytes<TOut>();
-  cudaError_t e = cudaFuncSetAttribute(mlp2_tcgen05_kernel<TIn, TOut, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return fail(ALLSET_ECUDA, "mlp2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  static const bool use_v1 = (getenv("ALLSET_MLP2_V1") != nullptr);      // first (non-specialised) version, kept for A/B runs
   const long long n_tiles = (p.rows + kTileM - 1) / kTileM;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long grid = 2LL * sms;
+  if (use_v1) {
+    constexpr int smem = Layout<D>::template smem_bytes<TOut>();
+    cudaError_t e = cudaFuncSetAttribute(mlp2_tcgen05_kernel<TIn, TOut, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(ALLSET_ECUDA, "mlp2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    long long grid = 2LL * sms;
+    if (grid > n_tiles) grid = n_tiles;
+    mlp2_tcgen05_kernel<TIn, TOut, D><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    return check_launch("mlp2_fwd");
+  }
+  constexpr int smem = WsLayout<D>::template smem_bytes<TOut>();
+  cudaError_t e = cudaFuncSetAttribute(mlp2_ws_kernel<TIn, TOut, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return fail(ALLSET_ECUDA, "mlp2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  int fits = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fits, mlp2_ws_kernel<TIn, TOut, D>, kWsThreads, smem);
+  if (e != cudaSuccess || fits < 1)
+    return fail(ALLSET_ECUDA, "mlp2_fwd: the 16-warp kernel does not fit one SM (%s)",
+                e != cudaSuccess ? cudaGetErrorString(e) : "0 resident CTAs");
+  long long grid = sms;
   if (grid > n_tiles) grid = n_tiles;
-  mlp2_tcgen05_kernel<TIn, TOut, D><<<(unsigned)grid, kThreads, smem, st>>>(p);
+  mlp2_ws_kernel<TIn, TOut, D><<<(unsigned)grid, kWsThreads, smem, st>>>(p);
   return check_launch("mlp2_fwd");
 }
 

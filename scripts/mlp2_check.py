@@ -124,6 +124,15 @@ def timing(rows, d, in_dtype, out_dtype):
 
 
 f32, b16 = torch.float32, torch.bfloat16
+if '--profile' in sys.argv:          # a handful of launches for ncu
+    x = torch.randn(1 << 20, 128, device=dev)
+    w = torch.randn(128, 128, device=dev) / 128 ** 0.5
+    b = torch.zeros(128, device=dev)
+    ln = (torch.ones(128, device=dev), torch.zeros(128, device=dev), 1e-5)
+    for _ in range(4):
+        _lib.mlp2_fwd(x, w, b, w, b, ln, ln, True, b16)
+    torch.cuda.synchronize()
+    sys.exit(0)
 case('identity', 128, 128, f32, f32, False, False, False, False, 'identity', tol=1e-6)
 case('identity_d64', 128, 64, f32, f32, False, False, False, False, 'identity', tol=1e-6)
 case('w2_identity', 256, 128, f32, f32, False, False, False, False, 'w2_identity')
