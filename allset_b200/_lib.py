@@ -255,18 +255,23 @@ def bias_act_norm_bwd(dy: torch.Tensor, x: torch.Tensor, bias: Optional[torch.Te
 MLP2_WIDTHS = (64, 128)
 
 
-def mlp2_fwd(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor,
+def mlp2_fwd(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: Optional[torch.Tensor],
              b2: Optional[torch.Tensor], ln0=None, ln1=None, relu_out: bool = False,
              out_dtype: Optional[torch.dtype] = None, status: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = [relu]( LN1?( relu( LN0?(x) W1^T + b1 ) ) W2^T + b2 ) in one tcgen05 kernel (bf16 operands, fp32
     accumulate).  x [rows, d] f32|bf16, d in MLP2_WIDTHS; w1, w2 [d, d] f32 ([out, in]); ln0 / ln1 = None or
-    (gamma, beta | None, eps); out_dtype f32 (default) | bf16.  `status`: optional int32[1] diagnostic word."""
+    (gamma, beta | None, eps); out_dtype f32 (default) | bf16.  `status`: optional int32[1] diagnostic word.
+    w2 is None: ONE Linear, out = [relu](LN0?(x) W1^T + b1) (b2 / ln1 must be None)."""
     _need(x, 'x')
     xd = _dtype_code(x)
     if x.dim() != 2:
         raise ValueError('x must be [rows, d]')
     rows, d = x.shape
+    if w2 is None and (b2 is not None or ln1 is not None):
+        raise ValueError('mlp2_fwd: w2 is None (single Linear) excludes b2 / ln1')
     for name, t, shape in (('w1', w1, (d, d)), ('w2', w2, (d, d))):
+        if t is None and name == 'w2':
+            continue
         _need(t, name, torch.float32)
         if tuple(t.shape) != shape:
             raise ValueError('mlp2_fwd: %s must be %s, got %s' % (name, shape, tuple(t.shape)))

@@ -2070,13 +2070,15 @@ int allset_mlp2_fwd(const void* x, int x_dtype, const float* ln0_gamma, const fl
   if (bad_dtype(x_dtype) || bad_dtype(out_dtype)) return fail(ALLSET_EINVAL, "mlp2_fwd: dtype must be 0 (f32) or 1 (bf16)");
   if (d != 64 && d != 128) return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: width %d not supported (64 or 128)", (int)d);
   if (rows == 0) return ALLSET_OK;
-  if (x == nullptr || out == nullptr || w1 == nullptr || w2 == nullptr) return fail(ALLSET_EINVAL, "mlp2_fwd: null pointer");
+  if (x == nullptr || out == nullptr || w1 == nullptr) return fail(ALLSET_EINVAL, "mlp2_fwd: null pointer");
+  const int single = (w2 == nullptr) ? 1 : 0;        // one Linear: out = [relu](LN0?(x) W1^T + b1)
+  if (single && (b2 != nullptr || ln1_gamma != nullptr)) return fail(ALLSET_EINVAL, "mlp2_fwd: w2 == NULL (single Linear) excludes b2 / ln1");
   if ((ln0_beta != nullptr && ln0_gamma == nullptr) || (ln1_beta != nullptr && ln1_gamma == nullptr))
     return fail(ALLSET_EINVAL, "mlp2_fwd: LayerNorm beta without gamma");
   const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w1 | (uintptr_t)w2;
   if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: x, out, w1, w2 must be 16-byte aligned");
-  mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, ln1_gamma, ln1_beta, w2, b2, ln0_eps, ln1_eps, relu_out,
-                 (long long)rows, status};
+  mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, ln1_gamma, ln1_beta, single ? w1 : w2, b2, ln0_eps, ln1_eps, relu_out,
+                 single, (long long)rows, status};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   using bf16 = __nv_bfloat16;
 #define ALLSET_MLP2_CASE(D_)                                                                  \

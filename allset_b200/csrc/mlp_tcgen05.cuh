@@ -15,25 +15,16 @@
 // 2 x 65.5 kFLOP per row -- 170 flop/B, below the bf16 ridge (~250 flop/B), which is why bf16 operands on
 // tcgen05 are the right tool: fp32 SIMT FMA (75 TFLOP/s) would be 3x over the HBM time.
 //
-// Structure (persistent, 2 CTAs of 256 threads per SM, 128-row tiles):
-//   setup   : W1, W2 (fp32 [D, D], nn.Linear layout = K-major "B" operand) -> bf16 in shared memory in the
-//             canonical K-major SWIZZLE_128B UMMA layout (8-row x 128-byte atoms, 16-byte chunk index XOR row&7);
-//             tcgen05.alloc of 2*D TMEM columns (two fp32 accumulators of 128 lanes x D columns).
-//   phase A : all 8 warps load 128 rows (coalesced 16-byte loads, a warp covers whole rows), LayerNorm with
-//             warp shuffles, write the bf16 A tile in the same swizzled layout; fence.proxy.async.
-//   MMA 1   : ONE thread issues D/16 tcgen05.mma (M=128, N=D, K=16, kind::f16, bf16 x bf16 -> fp32 in TMEM)
-//             and tcgen05.commit -> mbarrier.
-//   epi 1   : warps 0-3, thread = row = TMEM lane: tcgen05.ld 32 columns at a time, + b1, ReLU, LayerNorm
-//             (three passes over TMEM: the row lives in TMEM, not in registers), bf16 -> A tile again.
-//   MMA 2   : as MMA 1 into the second accumulator.
-//   epi 2   : + b2, ReLU, convert, stage the tile in shared memory (XOR-swizzled, conflict-free), then all
-//             8 warps write it out with coalesced 16-byte stores.
-// The second resident CTA of the SM overlaps its loads with this CTA's MMA / epilogue phases.
+// Operand layout: W1, W2 (fp32 [D, D], nn.Linear layout = K-major "B" operand) are converted once per CTA to bf16 in
+// shared memory in the canonical K-major SWIZZLE_128B UMMA layout (8-row x 128-byte atoms, 16-byte chunk index XOR
+// row & 7); the activation tiles (128 rows) use the same layout.  One tcgen05.mma is M=128, N=D, K=16 (kind::f16,
+// bf16 x bf16 -> fp32 in TMEM); a GEMM of the tile is D/16 of them + one tcgen05.commit -> mbarrier, issued by ONE
+// thread.  Epilogues read the accumulator with tcgen05.ld.32x32b.x32 (thread = row = TMEM lane).  The pipeline
+// (warp roles, barriers) is described above mlp2_ws_kernel.
 
 namespace mlp5 {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 256;
 
 struct Params {
   const void* x;
@@ -48,6 +39,7 @@ struct Params {
   const float* b2;
   float eps0, eps1;
   int relu_out;
+  int single;       // 1: ONE Linear only (out = [relu](LN0?(x) W1^T + b1)); w2 / b2 / ln1 unused (warp-specialised kernel)
   long long rows;
   int* status;      // device word, set to 1 if an mbarrier wait timed out (debug aid; never in a correct run)
 };
@@ -209,248 +201,6 @@ __device__ __forceinline__ void issue_gemm(uint32_t a_base, uint32_t w_base, uin
   }
   umma_commit(bar);
 }
-
-template <typename TIn, typename TOut, int D>
-__global__ void __launch_bounds__(kThreads, 2) mlp2_tcgen05_kernel(const Params p) {
-  using L = Layout<D>;
-  static_assert(D == 64 || D == 128, "mlp2_tcgen05: widths 64 and 128");
-  constexpr int PASS_BYTES = L::template pass_bytes<TOut>();
-  constexpr int OUT_ROW_BYTES = D * (int)sizeof(TOut);
-  constexpr int NPASS = OUT_ROW_BYTES / PASS_BYTES;
-  constexpr int CPP = PASS_BYTES / (int)sizeof(TOut);       // output columns per pass (multiple of 32)
-  constexpr int CHUNKS_PER_ROW = PASS_BYTES / 16;
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
-  uint8_t* smem = smem_raw + pad;
-  const uint32_t sW1 = raw_addr + pad;
-  const uint32_t sW2 = sW1 + L::W_BYTES;
-  const uint32_t sA = sW2 + L::W_BYTES;
-  float* sPar = reinterpret_cast<float*>(smem + 2 * L::W_BYTES + L::template buf_bytes<TOut>());   // b1, g1, be1, b2
-  const uint32_t sBar = sA + L::template buf_bytes<TOut>() + 4 * D * 4;                           // 2 mbarriers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * L::W_BYTES + L::template buf_bytes<TOut>() + 4 * D * 4 + 16);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool has_ln0 = p.ln0_g != nullptr, has_ln1 = p.ln1_g != nullptr;
-
-  // ---- setup ------------------------------------------------------------------------------------------------
-  if (tid == 0) {
-    mbar_init(sBar, 1);
-    mbar_init(sBar + 8, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), L::TMEM_COLS);
-  // weights: fp32 [D(out) x D(in)] row-major -> bf16, K-major SWIZZLE_128B
-  for (int idx = tid; idx < 2 * D * (D / 8); idx += kThreads) {
-    const int which = idx / (D * (D / 8));
-    const int rem = idx - which * (D * (D / 8));
-    const int n = rem / (D / 8), j = rem % (D / 8);
-    const float* w = (which ? p.w2 : p.w1) + (size_t)n * D + j * 8;
-    const float4 lo = *reinterpret_cast<const float4*>(w);
-    const float4 hi = *reinterpret_cast<const float4*>(w + 4);
-    st_shared16((which ? sW2 : sW1) + sw128_chunk<D>(n, j), pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w),
-                pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
-  }
-  for (int i = tid; i < D; i += kThreads) {
-    sPar[i] = p.b1 ? p.b1[i] : 0.f;
-    sPar[D + i] = has_ln1 ? p.ln1_g[i] : 1.f;
-    sPar[2 * D + i] = (has_ln1 && p.ln1_b) ? p.ln1_b[i] : 0.f;
-    sPar[3 * D + i] = p.b2 ? p.b2[i] : 0.f;
-  }
-  proxy_fence_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_acc1 = tmem_base, tmem_acc2 = tmem_base + D;
-
-  // ---- phase A geometry: a 16-byte chunk per lane, LPR lanes per row ----------------------------------------
-  constexpr int EPC = RowChunk<TIn>::N;
-  constexpr int LPR = D / EPC;              // 32 / 16 / 8 lanes per row
-  constexpr int RPI = 32 / LPR;             // rows per warp instruction
-  constexpr int ROWS_PER_WARP = kTileM / (kThreads / 32);
-  constexpr int ITERS = ROWS_PER_WARP / RPI;
-  constexpr int UB = ITERS < 8 ? ITERS : 8;
-  const int sub = lane / LPR, cl = lane % LPR;
-  float g0[EPC], be0[EPC];
-#pragma unroll
-  for (int i = 0; i < EPC; ++i) {
-    g0[i] = has_ln0 ? p.ln0_g[cl * EPC + i] : 1.f;
-    be0[i] = (has_ln0 && p.ln0_b) ? p.ln0_b[cl * EPC + i] : 0.f;
-  }
-  const unsigned char* xb = static_cast<const unsigned char*>(p.x);
-  unsigned char* ob = static_cast<unsigned char*>(p.out);
-  const long long n_tiles = (p.rows + kTileM - 1) / kTileM;
-  uint32_t parity = 0;
-
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
-    const long long row0 = tile * kTileM;
-
-    // ---- phase A: load rows, LayerNorm 0, bf16 A tile ---------------------------------------------------------
-#pragma unroll
-    for (int it0 = 0; it0 < ITERS; it0 += UB) {
-      uint4 raw[UB];
-#pragma unroll
-      for (int u = 0; u < UB; ++u) {
-        const int r = warp * ROWS_PER_WARP + (it0 + u) * RPI + sub;
-        const long long gr = row0 + r;
-        raw[u] = (gr < p.rows) ? ld_nc_16(xb + (size_t)gr * (D * sizeof(TIn)) + cl * 16) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < UB; ++u) {
-        const int r = warp * ROWS_PER_WARP + (it0 + u) * RPI + sub;
-        float v[EPC];
-        RowChunk<TIn>::unpack(raw[u], v);
-        if (has_ln0) {
-          float s = 0.f;
-#pragma unroll
-          for (int i = 0; i < EPC; ++i) s += v[i];
-#pragma unroll
-          for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          const float mean = s * (1.f / D);
-          float q = 0.f;
-#pragma unroll
-          for (int i = 0; i < EPC; ++i) { v[i] -= mean; q += v[i] * v[i]; }
-#pragma unroll
-          for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-          const float rstd = rsqrtf(q * (1.f / D) + p.eps0);
-#pragma unroll
-          for (int i = 0; i < EPC; ++i) v[i] = v[i] * rstd * g0[i] + be0[i];
-        }
-        // columns [cl*EPC, cl*EPC+EPC): chunk j = cl*EPC/8, byte (cl*EPC % 8) * 2 inside it
-        const uint32_t dst = sA + sw128_chunk<kTileM>(r, (cl * EPC) >> 3) + (uint32_t)(((cl * EPC) & 7) * 2);
-        if constexpr (EPC == 4) {
-          st_shared8(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-        } else {
-          st_shared16(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        }
-      }
-    }
-    proxy_fence_async();
-    tc_fence_before();
-    __syncthreads();                                                        // S1: A tile complete
-
-    // ---- GEMM 1 -------------------------------------------------------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      issue_gemm<D>(sA, sW1, tmem_acc1, sBar);
-    }
-    __syncwarp();
-    if (warp < 4) {
-      // ---- epilogue 1: thread = row = TMEM lane -------------------------------------------------------------
-      mbar_wait_bounded(sBar, parity, p.status);
-      tc_fence_after();
-      const int r = tid;
-      const uint32_t t1 = tmem_acc1 + ((uint32_t)(warp * 32) << 16);
-      float mean = 0.f, rstd = 1.f;
-      if (has_ln1) {
-        float s = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < D; c += 32) {
-          float v[32];
-          tmem_ld32(t1 + c, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s += fmaxf(v[i] + sPar[c + i], 0.f);
-        }
-        mean = s * (1.f / D);
-        float q = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < D; c += 32) {
-          float v[32];
-          tmem_ld32(t1 + c, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float h = fmaxf(v[i] + sPar[c + i], 0.f) - mean;
-            q += h * h;
-          }
-        }
-        rstd = rsqrtf(q * (1.f / D) + p.eps1);
-      }
-#pragma unroll 1
-      for (int c = 0; c < D; c += 32) {
-        float v[32];
-        tmem_ld32(t1 + c, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float h = fmaxf(v[i] + sPar[c + i], 0.f);
-          v[i] = has_ln1 ? (h - mean) * rstd * sPar[D + c + i] + sPar[2 * D + c + i] : h;
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          st_shared16(sA + sw128_chunk<kTileM>(r, (c >> 3) + q4), pack_bf16(v[8 * q4], v[8 * q4 + 1]),
-                      pack_bf16(v[8 * q4 + 2], v[8 * q4 + 3]), pack_bf16(v[8 * q4 + 4], v[8 * q4 + 5]),
-                      pack_bf16(v[8 * q4 + 6], v[8 * q4 + 7]));
-      }
-      proxy_fence_async();
-      tc_fence_before();
-    }
-    __syncthreads();                                                        // S2: hidden tile complete
-
-    // ---- GEMM 2 -------------------------------------------------------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      issue_gemm<D>(sA, sW2, tmem_acc2, sBar + 8);
-    }
-    __syncwarp();
-    if (warp < 4) {
-      mbar_wait_bounded(sBar + 8, parity, p.status);
-      tc_fence_after();
-    }
-    // ---- epilogue 2: + b2, ReLU, convert, stage, coalesced write-out -------------------------------------------
-#pragma unroll 1
-    for (int pass = 0; pass < NPASS; ++pass) {
-      if (warp < 4) {
-        const int r = tid;
-        const uint32_t t2 = tmem_acc2 + ((uint32_t)(warp * 32) << 16) + pass * CPP;
-#pragma unroll 1
-        for (int c = 0; c < CPP; c += 32) {
-          float v[32];
-          tmem_ld32(t2 + c, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] += sPar[3 * D + pass * CPP + c + i];
-            if (p.relu_out) v[i] = fmaxf(v[i], 0.f);
-          }
-          const uint32_t rowb = sA + (uint32_t)r * PASS_BYTES;
-          if constexpr (sizeof(TOut) == 2) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const int c16 = (c >> 3) + q4;
-              st_shared16(rowb + (uint32_t)((c16 ^ (r & 7)) << 4), pack_bf16(v[8 * q4], v[8 * q4 + 1]),
-                          pack_bf16(v[8 * q4 + 2], v[8 * q4 + 3]), pack_bf16(v[8 * q4 + 4], v[8 * q4 + 5]),
-                          pack_bf16(v[8 * q4 + 6], v[8 * q4 + 7]));
-            }
-          } else {
-#pragma unroll
-            for (int q8 = 0; q8 < 8; ++q8) {
-              const int c16 = (c >> 2) + q8;
-              st_shared16(rowb + (uint32_t)((c16 ^ (r & 7)) << 4), __float_as_uint(v[4 * q8]),
-                          __float_as_uint(v[4 * q8 + 1]), __float_as_uint(v[4 * q8 + 2]), __float_as_uint(v[4 * q8 + 3]));
-            }
-          }
-        }
-        tc_fence_before();
-      }
-      __syncthreads();                                                      // S3: staged
-#pragma unroll
-      for (int idx = tid; idx < kTileM * CHUNKS_PER_ROW; idx += kThreads) {
-        const int r = idx / CHUNKS_PER_ROW, c16 = idx % CHUNKS_PER_ROW;
-        const uint4 q = ld_shared16(sA + (uint32_t)r * PASS_BYTES + (uint32_t)((c16 ^ (r & 7)) << 4));
-        const long long gr = row0 + r;
-        if (gr < p.rows)
-          *reinterpret_cast<uint4*>(ob + (size_t)gr * OUT_ROW_BYTES + pass * PASS_BYTES + c16 * 16) = q;
-      }
-      __syncthreads();                                                      // S4: staging buffer free again
-    }
-  }
-
-  // ---- teardown ---------------------------------------------------------------------------------------------
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
-}
-
 
 // =================================================================================================================
 // Warp-specialised pipeline, ONE persistent CTA of 16 warps (512 threads x 128 registers = the whole file) per SM
@@ -684,6 +434,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       // ---- epilogue 1 ----------------------------------------------------------------------------------------
       mbar_wait_bounded(bar_acc1_full + 8 * g, k & 1u, p.status);
       tc_fence_after();
+      const bool has_next = tile + 2LL * gridDim.x < n_tiles;
+      if (!p.single) {
       const uint32_t t1 = tmem_acc1 + lane_off;
       float mean = 0.f, rstd = 1.f;
       if (has_ln1) {
@@ -723,15 +475,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       if (issuer) {
         tc_fence_after();
         issue_gemm<D>(sH, sW2, tmem_acc2, bar_acc2_full + 8 * g);       // acc2[g] was drained before the last barrier
-        if (tile + 2LL * gridDim.x < n_tiles) gemm1(k + 1);             // runs under epilogue 2 of this tile
+        if (has_next) gemm1(k + 1);                                     // runs under epilogue 2 of this tile
       }
       __syncwarp();
       // ---- epilogue 2 ----------------------------------------------------------------------------------------
       mbar_wait_bounded(bar_acc2_full + 8 * g, k & 1u, p.status);
       tc_fence_after();
+      }  // !single
+      const uint32_t tfin = p.single ? tmem_acc1 : tmem_acc2;           // single Linear: acc1 is the result
+      const int bias_off = p.single ? 0 : 3 * D;
 #pragma unroll 1
       for (int pass = 0; pass < NPASS; ++pass) {
-        const uint32_t t2 = tmem_acc2 + lane_off + pass * CPP;
+        const uint32_t t2 = tfin + lane_off + pass * CPP;
         const uint32_t rowb = sH + (uint32_t)r * PASS_BYTES;
 #pragma unroll 1
         for (int c = 0; c < CPP; c += 32) {
@@ -739,7 +494,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
           tmem_ld32(t2 + c, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            v[i] += sPar[3 * D + pass * CPP + c + i];
+            v[i] += sPar[bias_off + pass * CPP + c + i];
             if (p.relu_out) v[i] = fmaxf(v[i], 0.f);
           }
           if constexpr (sizeof(TOut) == 2) {
@@ -759,8 +514,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
             }
           }
         }
-        tc_fence_before();                       // (last pass: acc2[g] drained before the barrier below)
+        tc_fence_before();                       // (last pass: the accumulator is drained before the barrier below)
         epi_bar_sync(g);                         // staged
+        if (p.single && pass == NPASS - 1) {     // acc1[g] drained by all 128 threads: GEMM 1 of the next tile may go
+          if (issuer && has_next) gemm1(k + 1);
+          __syncwarp();
+        }
 #pragma unroll
         for (int idx = r; idx < kTileM * CHUNKS_PER_ROW; idx += 128) {
           const int rr = idx / CHUNKS_PER_ROW, c16 = idx % CHUNKS_PER_ROW;
@@ -782,20 +541,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
 
 template <typename TIn, typename TOut, int D>
 int launch(const Params& p, cudaStream_t st) {
-  static const bool use_v1 = (getenv("ALLSET_MLP2_V1") != nullptr);      // first (non-specialised) version, kept for A/B runs
   const long long n_tiles = (p.rows + kTileM - 1) / kTileM;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (use_v1) {
-    constexpr int smem = Layout<D>::template smem_bytes<TOut>();
-    cudaError_t e = cudaFuncSetAttribute(mlp2_tcgen05_kernel<TIn, TOut, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(ALLSET_ECUDA, "mlp2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    long long grid = 2LL * sms;
-    if (grid > n_tiles) grid = n_tiles;
-    mlp2_tcgen05_kernel<TIn, TOut, D><<<(unsigned)grid, kThreads, smem, st>>>(p);
-    return check_launch("mlp2_fwd");
-  }
   constexpr int smem = WsLayout<D>::template smem_bytes<TOut>();
   cudaError_t e = cudaFuncSetAttribute(mlp2_ws_kernel<TIn, TOut, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return fail(ALLSET_ECUDA, "mlp2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

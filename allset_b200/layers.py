@@ -192,15 +192,25 @@ class PMA(nn.Module):
         b_eff = (self.lin_K.bias.view(H, C) * seed).sum(dim=1)                             # [H]
         score = F.linear(x, w_eff, b_eff)                                                  # [n_src, H]
         fused = self.rFF._fused_ok(x) and ops.fused_dense_ok(x, self.heads * self.hidden)
-        if fused:
-            x_V = ops.bias_act_norm(F.linear(x, self.lin_V.weight), self.lin_V.bias)
+        if self._tc_v_ok(x):
+            # bf16 mode: V = lin_V(x) as ONE tcgen05 kernel that writes the bf16 rows the aggregation gathers
+            v = _lib.mlp2_fwd(x.contiguous(), self.lin_V.weight, self.lin_V.bias, None, None, None, None, False,
+                              torch.bfloat16)
         else:
-            x_V = self.lin_V(x)
-        v = x_V if self.agg_dtype is None else x_V.to(self.agg_dtype)
+            if fused:
+                x_V = ops.bias_act_norm(F.linear(x, self.lin_V.weight), self.lin_V.bias)
+            else:
+                x_V = self.lin_V(x)
+            v = x_V if self.agg_dtype is None else x_V.to(self.agg_dtype)
         want_alpha = isinstance(return_attention_weights, bool)
         out, alpha = ops.pma_aggregate(v, score, self.att_r, inc, H, self.negative_slope, return_alpha=want_alpha)
-        out = out.to(x_V.dtype)                                          # [n_tgt, H*C], seed already added
-        if fused:
+        out = out.to(score.dtype)                                        # [n_tgt, H*C], seed already added
+        if self.rFF._tc_ok(out):
+            # ln0 -> [rFF = Linear, ReLU, Linear on tcgen05, ReLU] -> ln1(residual + .): three passes over the rows
+            out = ops.bias_act_norm(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps)
+            h = self.rFF(out, final_relu=True)
+            out = ops.bias_act_norm(h, residual=out, gamma=self.ln1.weight, beta=self.ln1.bias, eps=self.ln1.eps)
+        elif fused:
             out = ops.bias_act_norm(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps)
             y, bias = self.rFF.forward_fused_open(out)
             out = ops.bias_act_norm(y, bias, relu=True, residual=out, gamma=self.ln1.weight, beta=self.ln1.bias,
@@ -211,6 +221,13 @@ class PMA(nn.Module):
         if want_alpha:
             return out, (edge_index, alpha)
         return out
+
+    def _tc_v_ok(self, x) -> bool:
+        """lin_V on the tensor cores: bf16 mode, eval, square Linear of a width the tcgen05 kernel has."""
+        d = self.heads * self.hidden
+        return (self.agg_dtype == torch.bfloat16 and not torch.is_grad_enabled() and x.is_cuda and x.dim() == 2
+                and x.dtype in (torch.float32, torch.bfloat16) and x.shape[1] == d and d in _lib.MLP2_WIDTHS
+                and x.shape[0] >= ops.FUSED_DENSE_MIN_ROWS and self.lin_V.weight.dtype == torch.float32)
 
     def __repr__(self):
         return '{}({}, {}, heads={})'.format(self.__class__.__name__, self.in_channels, self.out_channels, self.heads)
@@ -251,6 +268,7 @@ class HalfNLHconv(nn.Module):
         self.agg_dtype = dtype
         if self.attention:
             self.prop.agg_dtype = dtype
+            self.prop.rFF.tc_dtype = dtype if dtype == torch.bfloat16 else None
         else:
             for f in (self.f_enc, self.f_dec):
                 if isinstance(f, MLP):

@@ -130,7 +130,9 @@ int allset_bias_act_norm(const float* x, const float* bias, int relu, const floa
  * ln*_gamma NULL = no LayerNorm at that position (Normalization 'None' / InputNorm False); out [rows, d] f32|bf16.
  * Accuracy is that of bf16 operands (the 1e-2 bar of north_star's bf16 mode), not fp32: callers that need 1e-4
  * keep the cuBLAS SGEMM + allset_bias_act_norm chain.  status: device int32 or NULL, set to 1 if an internal
- * mbarrier wait timed out (diagnostic; never in a correct run).  ALLSET_EUNSUPPORTED for other widths. */
+ * mbarrier wait timed out (diagnostic; never in a correct run).  ALLSET_EUNSUPPORTED for other widths.
+ * w2 == NULL selects ONE Linear: out = [relu]( LN0?(x) W1^T + b1 ) (b2 / ln1 must be NULL) -- nn.Linear as used by
+ * PMA.lin_V (src/layers.py:129) and MLP with num_layers == 1. */
 int allset_mlp2_fwd(const void* x, int x_dtype,
                     const float* ln0_gamma, const float* ln0_beta, float ln0_eps,
                     const float* w1, const float* b1,

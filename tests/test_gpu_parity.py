@@ -808,3 +808,58 @@ def test_alldeepsets_bf16_mode_uses_tcgen05_mlps_and_matches_oracle(monkeypatch)
     assert len(calls) == 8 + 8                     # (a) ran 4 half layers x 2 MLPs on the tensor cores, (b) none
     err_storage = (logits_storage.cpu() - ref).abs().max().item()
     assert err_tc <= 2.0 * err_storage + 1e-2 * max(ref.abs().max().item(), 1.0), (err_tc, err_storage)
+
+
+@pytest.mark.parametrize('d,heads', [(128, 8), (128, 4), (64, 4)])
+def test_pma_bf16_mode_runs_lin_v_and_rff_on_tcgen05(d, heads, monkeypatch):
+    """AllSetTransformer half layer in bf16 mode: lin_V (single Linear, bf16 rows out) and rFF (Linear-ReLU-Linear) are
+    tcgen05 launches; on identical inputs the result stays within the bf16 bar of the fp32 oracle."""
+    from allset_b200 import _lib, synthetic
+    n, m_e = 30000, 9000
+    ei = synthetic.poisson_hypergraph(n, m_e, 10, seed=11, device=dev())
+    node, he = ei[0], ei[1] - n
+    torch.manual_seed(3)
+    conv = ab().HalfNLHconv(d, d, d, 2, 0.0, 'ln', True, heads=heads, attention=True)
+    with torch.no_grad():
+        for prm in conv.parameters():
+            if prm.dim() == 1:
+                prm.add_(0.1 * torch.randn_like(prm))
+    params = {k: v.detach().clone() for k, v in conv.state_dict().items()}
+    conv.to(dev()).eval()
+    conv.set_agg_dtype(torch.bfloat16)
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(5))
+    calls = []
+    real = _lib.mlp2_fwd
+    monkeypatch.setattr(_lib, 'mlp2_fwd', lambda *a, **k: (calls.append(a[3] is None), real(*a, **k))[1])
+    inc = ab().Incidence.from_coo(node, he, n_src=n)
+    with torch.no_grad():
+        out = conv(x.to(dev()), inc, None, 'add')
+    assert calls == [True, False]                  # lin_V as a single Linear, then rFF as the two-layer chain
+    ref = O.half_nlh_conv(params, '', x, node.cpu(), he.cpu(), None, 'add', attention=True, heads=heads)
+    assert out.shape == ref.shape
+    err = (out.cpu() - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+
+
+def test_mlp2_single_linear_mode():
+    from allset_b200 import _lib
+    for d in (128, 64):
+        g = torch.Generator().manual_seed(d)
+        x = torch.randn(20000 + 3, d, generator=g)
+        w = torch.randn(d, d, generator=g) / d ** 0.5
+        b = torch.randn(d, generator=g)
+        ln = (1 + 0.1 * torch.randn(d, generator=g), 0.1 * torch.randn(d, generator=g), 1e-5)
+        for in_dt, out_dt, use_ln, relu in ((torch.float32, torch.bfloat16, False, False),
+                                            (torch.bfloat16, torch.float32, True, True),
+                                            (torch.float32, torch.float32, True, False)):
+            xin = x.to(in_dt)
+            ref = F.linear(F.layer_norm(xin.float(), (d,), ln[0], ln[1], ln[2]) if use_ln else xin.float(), w, b)
+            ref = F.relu(ref) if relu else ref
+            lnd = tuple(t.to(dev()) if torch.is_tensor(t) else t for t in ln) if use_ln else None
+            out = _lib.mlp2_fwd(xin.to(dev()), w.to(dev()), b.to(dev()), None, None, lnd, None, relu, out_dt)
+            assert out.dtype == out_dt
+            err = (out.float().cpu() - ref).abs().max().item()
+            assert err <= 1e-2 * max(ref.abs().max().item(), 1.0), (d, in_dt, out_dt, err)
+    with pytest.raises(ValueError):
+        _lib.mlp2_fwd(torch.zeros(8, 128, device=dev()), torch.zeros(128, 128, device=dev()), None, None,
+                      torch.zeros(128, device=dev()))
