@@ -113,8 +113,8 @@ class SetGNN(nn.Module):
     def _relu(conv, x):
         """`F.relu(conv(x))` of reference src/models.py:475,478.  A non-attention half layer already ends in
         relu(f_dec(.)) (src/layers.py:634), so the outer ReLU is the identity (value and gradient) and a full pass
-        over [rows, d]; it is only applied where it does something (PMA ends in a LayerNorm, Identity f_dec)."""
-        if not conv.attention and isinstance(conv.f_dec, MLP):
+        over [rows, d]; it is only applied where it does something (PMA ends in a LayerNorm)."""
+        if not conv.attention:
             return x
         return F.relu(x)
 

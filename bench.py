@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-pma', action='store_true')
+    ap.add_argument('--no-mlp', action='store_true')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'fused', 'nccl'],
                     help='N>1: fused = P2P stores from the kernel epilogue into symmetric memory; nccl = all-gather after')
     ap.add_argument('--replicate-xv', action='store_true',
@@ -449,6 +450,32 @@ def run_b200(a):
                'v2e_gbs': b_ve / (pph[0] * 1e-3) / 1e9, 'e2v_gbs': b_ev / (pph[2] * 1e-3) / 1e9}
         del score_v, score_e
 
+    # ---- the dense glue of the same layer on the tensor cores (row (f)-1): f_enc / f_dec as ONE tcgen05 kernel ------
+    mlp = None
+    if not a.no_mlp and world == 1 and d in (64, 128):
+        from allset_b200 import _lib
+        gw = torch.Generator(device=dev)
+        gw.manual_seed(a.seed + 2)
+        w1 = torch.randn(d, d, device=dev, generator=gw) / d ** 0.5
+        w2 = torch.randn(d, d, device=dev, generator=gw) / d ** 0.5
+        bz = torch.zeros(d, device=dev)
+        ln = (torch.ones(d, device=dev), torch.zeros(d, device=dev), 1e-5)
+        x_rows = plain(x_v)
+        o_dt = x_rows.dtype
+
+        def mlp_step(marks):
+            if marks: marks[0].record()
+            _lib.mlp2_fwd(x_rows, w1, bz, w2, bz, ln, ln, True, o_dt)
+            if marks: marks[1].record()
+
+        m_ms, _ = timed_steps(mlp_step, 1, max(5, a.steps // 5), a.warmup)
+        m_ms /= max(5, a.steps // 5)
+        nbytes = 2 * Nv * d * es
+        mlp = {'kernel': 'mlp2_ws_kernel (tcgen05, bf16 operands): relu(LN -> Linear -> ReLU -> LN -> Linear) over X_v',
+               'rows': Nv, 'ms': m_ms, 'bytes': nbytes, 'gbs': nbytes / (m_ms * 1e-3) / 1e9,
+               'tflops': 4.0 * Nv * d * d / (m_ms * 1e-3) / 1e12, 'rows_per_s': Nv / (m_ms * 1e-3)}
+        del w1, w2
+
     # ---- roofline of the dominant kernel (the segmented-reduce gather kernel; both directions launch it) --------
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.isfile(peaks_path):
@@ -510,6 +537,7 @@ def run_b200(a):
                          'note': 'the V->E segmented reduce alone, without the fused X_e stores to the peers (max over ranks)'},
             'incidence_visits_per_s': 2 * nnz / (ms_per_step * 1e-3),
             'pma': pma,
+            'mlp': mlp,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
