@@ -2075,8 +2075,8 @@ int allset_mlp2_fwd(const void* x, int x_dtype, const float* ln0_gamma, const fl
   if (single && (b2 != nullptr || ln1_gamma != nullptr)) return fail(ALLSET_EINVAL, "mlp2_fwd: w2 == NULL (single Linear) excludes b2 / ln1");
   if ((ln0_beta != nullptr && ln0_gamma == nullptr) || (ln1_beta != nullptr && ln1_gamma == nullptr))
     return fail(ALLSET_EINVAL, "mlp2_fwd: LayerNorm beta without gamma");
-  const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w1 | (uintptr_t)w2;
-  if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: x, out, w1, w2 must be 16-byte aligned");
+  const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)ln0_gamma | (uintptr_t)ln1_gamma;
+  if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: x, out, w1, w2 and the LayerNorm gammas must be 16-byte aligned");
   mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, ln1_gamma, ln1_beta, single ? w1 : w2, b2, ln0_eps, ln1_eps, relu_out,
                  single, (long long)rows, status};
   cudaStream_t st = static_cast<cudaStream_t>(stream);

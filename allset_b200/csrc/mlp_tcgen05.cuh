@@ -149,6 +149,20 @@ __device__ __forceinline__ uint4 ld_shared16(uint32_t addr) {
   return v;
 }
 
+// packed fp32 pairs (sm_100 FADD2 / FFMA2 / FMUL2: two IEEE fp32 results per instruction)
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float b0, float b1) {            // d += b
+  asm("{\n\t.reg .b64 pd, pb;\n\tmov.b64 pd, {%0, %1};\n\tmov.b64 pb, {%2, %3};\n\t"
+      "add.rn.f32x2 pd, pd, pb;\n\tmov.b64 {%0, %1}, pd;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void ffma2p(float& d0, float& d1, float a0, float a1, float b0, float b1) {   // d += a * b
+  asm("{\n\t.reg .b64 pa, pb, pc;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\tmov.b64 pc, {%0, %1};\n\t"
+      "fma.rn.f32x2 pc, pa, pb, pc;\n\tmov.b64 {%0, %1}, pc;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 template <typename T>
 struct RowChunk;   // one 16-byte chunk of a feature row as floats
 template <>
@@ -236,71 +250,99 @@ struct WsLayout {
   }
 };
 
-template <typename TIn, int D, int HALF>
+// Producer geometry: 8 lanes per row, 4 rows per warp instruction.  Lane cl of a row owns the 16-byte chunks
+// cl, cl+8, cl+16, ... (every load instruction still covers 128 contiguous bytes of each of its 4 rows), so a row
+// statistic costs 3 shuffle steps for 4 rows instead of 5 for one, and the per-row scalars are shared by 4 rows.
+// A warp owns 16 rows of the tile = 4 row groups; a "half" = 2 groups (8 rows) = one prefetch buffer.
+template <typename TIn, int D>
 struct Producer {
-  static constexpr int EPC = RowChunk<TIn>::N;
-  static constexpr int LPR = D / EPC;
+  static constexpr int EPC = RowChunk<TIn>::N;          // elements per 16-byte chunk
+  static constexpr int CHUNKS = D / EPC;                // chunks per row: 32 / 16 / 16 / 8
+  static constexpr int LPR = 8;
+  static constexpr int CPL = CHUNKS / LPR;              // chunks per lane: 4 / 2 / 2 / 1
+  static constexpr int EPL = CPL * EPC;                 // elements per lane and row
   static constexpr int RPI = 32 / LPR;
   static constexpr int ROWS_PER_WARP = kTileM / kProdWarps;
+  static constexpr int G = ROWS_PER_WARP / RPI / 2;     // row groups per half
+  static_assert(CPL >= 1 && G == 2, "producer geometry");
+  using Buf = uint4[G][CPL];
 
-  __device__ static __forceinline__ void load(uint4 (&buf)[HALF], const unsigned char* xb, long long row0, long long rows,
+  __device__ static __forceinline__ void load(Buf& buf, const unsigned char* xb, long long row0, long long rows,
                                               int pw, int half, int sub, int cl) {
 #pragma unroll
-    for (int u = 0; u < HALF; ++u) {
-      const int r = pw * ROWS_PER_WARP + (half * HALF + u) * RPI + sub;
+    for (int gi = 0; gi < G; ++gi) {
+      const int r = pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
       const long long gr = row0 + r;
-      buf[u] = (gr < rows) ? ld_nc_16(xb + (size_t)gr * (D * sizeof(TIn)) + cl * 16) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+        buf[gi][j] = (gr < rows) ? ld_nc_16(xb + (size_t)gr * (D * sizeof(TIn)) + (cl + LPR * j) * 16)
+                                 : make_uint4(0, 0, 0, 0);
     }
   }
-  // The HALF rows are reduced in LOCKSTEP (offset loop outermost): shuffles keep program order, so a row-at-a-time
-  // loop serialises 10 dependent ~25-cycle SHFLs per row; here every butterfly step has HALF independent ones.
-  __device__ static __forceinline__ void process(const uint4 (&buf)[HALF], uint32_t sAst, int pw, int half, int sub,
-                                                 int cl, bool has_ln0, float eps0, const float (&g0)[EPC],
-                                                 const float (&be0)[EPC]) {
-    float v[HALF][EPC];
+  // LayerNorm 0 WITHOUT its affine part (gamma / beta are folded into W1 / b1 at setup), the G row groups in lockstep.
+  __device__ static __forceinline__ void process(const Buf& buf, uint32_t sAst, int pw, int half, int sub, int cl,
+                                                 bool has_ln0, float eps0) {
+    float v[G][EPL];
 #pragma unroll
-    for (int u = 0; u < HALF; ++u) RowChunk<TIn>::unpack(buf[u], v[u]);
+    for (int gi = 0; gi < G; ++gi) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        float t[EPC];
+        RowChunk<TIn>::unpack(buf[gi][j], t);
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) v[gi][j * EPC + e] = t[e];
+      }
+    }
     if (has_ln0) {
-      float s[HALF];
+      float s[G];
 #pragma unroll
-      for (int u = 0; u < HALF; ++u) {
-        s[u] = 0.f;
+      for (int gi = 0; gi < G; ++gi) {
+        float a0 = v[gi][0], a1 = v[gi][1];
 #pragma unroll
-        for (int i = 0; i < EPC; ++i) s[u] += v[u][i];
+        for (int e = 2; e < EPL; e += 2) fadd2(a0, a1, v[gi][e], v[gi][e + 1]);
+        s[gi] = a0 + a1;
       }
 #pragma unroll
       for (int o = LPR / 2; o > 0; o >>= 1) {
 #pragma unroll
-        for (int u = 0; u < HALF; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+        for (int gi = 0; gi < G; ++gi) s[gi] += __shfl_xor_sync(0xffffffffu, s[gi], o);
       }
 #pragma unroll
-      for (int u = 0; u < HALF; ++u) {
-        const float mean = s[u] * (1.f / D);
-        s[u] = 0.f;
+      for (int gi = 0; gi < G; ++gi) {
+        const float nm = -s[gi] * (1.f / D);
+        float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < EPC; ++i) { v[u][i] -= mean; s[u] = fmaf(v[u][i], v[u][i], s[u]); }
+        for (int e = 0; e < EPL; e += 2) {
+          fadd2(v[gi][e], v[gi][e + 1], nm, nm);
+          ffma2p(q0, q1, v[gi][e], v[gi][e + 1], v[gi][e], v[gi][e + 1]);
+        }
+        s[gi] = q0 + q1;
       }
 #pragma unroll
       for (int o = LPR / 2; o > 0; o >>= 1) {
 #pragma unroll
-        for (int u = 0; u < HALF; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+        for (int gi = 0; gi < G; ++gi) s[gi] += __shfl_xor_sync(0xffffffffu, s[gi], o);
       }
 #pragma unroll
-      for (int u = 0; u < HALF; ++u) {
-        const float rstd = rsqrtf(s[u] * (1.f / D) + eps0);
+      for (int gi = 0; gi < G; ++gi) {
+        const float rstd = rsqrtf(s[gi] * (1.f / D) + eps0);
 #pragma unroll
-        for (int i = 0; i < EPC; ++i) v[u][i] = v[u][i] * rstd * g0[i] + be0[i];
+        for (int e = 0; e < EPL; e += 2) fmul2(v[gi][e], v[gi][e + 1], rstd);
       }
     }
 #pragma unroll
-    for (int u = 0; u < HALF; ++u) {
-      const int r = pw * ROWS_PER_WARP + (half * HALF + u) * RPI + sub;
-      const uint32_t dst = sAst + sw128_chunk<kTileM>(r, (cl * EPC) >> 3) + (uint32_t)(((cl * EPC) & 7) * 2);
-      if constexpr (EPC == 4) {
-        st_shared8(dst, pack_bf16(v[u][0], v[u][1]), pack_bf16(v[u][2], v[u][3]));
-      } else {
-        st_shared16(dst, pack_bf16(v[u][0], v[u][1]), pack_bf16(v[u][2], v[u][3]), pack_bf16(v[u][4], v[u][5]),
-                    pack_bf16(v[u][6], v[u][7]));
+    for (int gi = 0; gi < G; ++gi) {
+      const int r = pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int col = (cl + LPR * j) * EPC;                  // first column of this chunk
+        const uint32_t dst = sAst + sw128_chunk<kTileM>(r, col >> 3) + (uint32_t)((col & 7) * 2);
+        const float* w = &v[gi][j * EPC];
+        if constexpr (EPC == 4) {
+          st_shared8(dst, pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]));
+        } else {
+          st_shared16(dst, pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+        }
       }
     }
   }
@@ -326,7 +368,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
   const uint32_t sA0 = sW2 + L::W_BYTES;                 // 2 stages of L::A_BYTES
   const uint32_t sA1 = sA0 + 2 * L::A_BYTES;             // 2 hidden tiles / output staging buffers of BUF bytes
   constexpr int PAR_OFF = 2 * L::W_BYTES + 2 * L::A_BYTES + 2 * BUF;
-  float* sPar = reinterpret_cast<float*>(smem + PAR_OFF);                       // b1, g1, be1, b2
+  float* sPar = reinterpret_cast<float*>(smem + PAR_OFF);                       // folded biases b1', b2'
   const uint32_t sBar = sW1 + PAR_OFF + 4 * D * 4;                              // 8 mbarriers, [kind][buffer set]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PAR_OFF + 4 * D * 4 + 128);
   const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 16, bar_acc1_full = sBar + 32, bar_acc2_full = sBar + 48;
@@ -346,21 +388,38 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), WsLayout<D>::TMEM_COLS);
+  // weights -> bf16 K-major SWIZZLE_128B, with the LayerNorm in front of each Linear folded in:
+  //   LN(x) W^T + b = n(x) (W diag(gamma))^T + (b + W beta),  n(x) = (x - mean) * rstd
   for (int idx = tid; idx < 2 * D * (D / 8); idx += kWsThreads) {
     const int which = idx / (D * (D / 8));
     const int rem = idx - which * (D * (D / 8));
     const int n = rem / (D / 8), j = rem % (D / 8);
     const float* w = (which ? p.w2 : p.w1) + (size_t)n * D + j * 8;
-    const float4 lo = *reinterpret_cast<const float4*>(w);
-    const float4 hi = *reinterpret_cast<const float4*>(w + 4);
+    float4 lo = *reinterpret_cast<const float4*>(w);
+    float4 hi = *reinterpret_cast<const float4*>(w + 4);
+    const float* gam = which ? p.ln1_g : p.ln0_g;
+    if (gam != nullptr) {
+      const float4 gl = *reinterpret_cast<const float4*>(gam + j * 8);
+      const float4 gh = *reinterpret_cast<const float4*>(gam + j * 8 + 4);
+      lo.x *= gl.x; lo.y *= gl.y; lo.z *= gl.z; lo.w *= gl.w;
+      hi.x *= gh.x; hi.y *= gh.y; hi.z *= gh.z; hi.w *= gh.w;
+    }
     st_shared16((which ? sW2 : sW1) + sw128_chunk<D>(n, j), pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w),
                 pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
   }
-  for (int i = tid; i < D; i += kWsThreads) {
-    sPar[i] = p.b1 ? p.b1[i] : 0.f;
-    sPar[D + i] = has_ln1 ? p.ln1_g[i] : 1.f;
-    sPar[2 * D + i] = (has_ln1 && p.ln1_b) ? p.ln1_b[i] : 0.f;
-    sPar[3 * D + i] = p.b2 ? p.b2[i] : 0.f;
+  // biases: sPar[0..D) = b1 + W1 beta0, sPar[D..2D) = b2 + W2 beta1 (one warp per output row, fp32)
+  for (int n = warp; n < 2 * D; n += kWsThreads / 32) {
+    const int which = n / D, row = n - which * D;
+    const float* bias = which ? p.b2 : p.b1;
+    const float* beta = which ? (has_ln1 ? p.ln1_b : nullptr) : (has_ln0 ? p.ln0_b : nullptr);
+    float acc = 0.f;
+    if (beta != nullptr && !(which && p.single)) {
+      const float* w = (which ? p.w2 : p.w1) + (size_t)row * D;
+      for (int kk = lane; kk < D; kk += 32) acc = fmaf(w[kk], beta[kk], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (lane == 0) sPar[n] = (bias ? bias[row] : 0.f) + acc;
   }
   proxy_fence_async();
   tc_fence_before();
@@ -371,19 +430,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
 
   if (warp >= kEpiWarps) {
     // ======================= producers =====================================================================
-    using P = Producer<TIn, D, (kTileM / kProdWarps) / (32 / (D / RowChunk<TIn>::N)) / 2>;
-    constexpr int HALF = (kTileM / kProdWarps) / P::RPI / 2;
-    static_assert(HALF >= 1, "producer geometry");
+    using P = Producer<TIn, D>;
     const int pw = warp - kEpiWarps;
     const int sub = lane / P::LPR, cl = lane % P::LPR;
-    float g0[P::EPC], be0[P::EPC];
-#pragma unroll
-    for (int i = 0; i < P::EPC; ++i) {
-      g0[i] = has_ln0 ? p.ln0_g[cl * P::EPC + i] : 1.f;
-      be0[i] = (has_ln0 && p.ln0_b) ? p.ln0_b[cl * P::EPC + i] : 0.f;
-    }
     const unsigned char* xb = static_cast<const unsigned char*>(p.x);
-    uint4 bufA[HALF], bufB[HALF];
+    typename P::Buf bufA, bufB;
     long long tile = blockIdx.x;
     if (tile < n_tiles) {
       P::load(bufA, xb, tile * kTileM, p.rows, pw, 0, sub, cl);
@@ -392,11 +443,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     for (uint32_t it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t st = it & 1u;
       const long long next = tile + gridDim.x;
-      if (it >= 2) mbar_wait_bounded<128>(bar_a_empty + 8 * st, ((it >> 1) - 1) & 1u, p.status);
+      if (it >= 2) mbar_wait_bounded<256>(bar_a_empty + 8 * st, ((it >> 1) - 1) & 1u, p.status);
       const uint32_t sAst = sA0 + st * L::A_BYTES;
-      P::process(bufA, sAst, pw, 0, sub, cl, has_ln0, p.eps0, g0, be0);
+      P::process(bufA, sAst, pw, 0, sub, cl, has_ln0, p.eps0);
       if (next < n_tiles) P::load(bufA, xb, next * kTileM, p.rows, pw, 0, sub, cl);
-      P::process(bufB, sAst, pw, 1, sub, cl, has_ln0, p.eps0, g0, be0);
+      P::process(bufB, sAst, pw, 1, sub, cl, has_ln0, p.eps0);
       if (next < n_tiles) P::load(bufB, xb, next * kTileM, p.rows, pw, 1, sub, cl);
       proxy_fence_async();
       __syncwarp();
@@ -439,29 +490,40 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       const uint32_t t1 = tmem_acc1 + lane_off;
       float mean = 0.f, rstd = 1.f;
       if (has_ln1) {
-        float s = 0.f, q = 0.f;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 1
         for (int c = 0; c < D; c += 32) {
           float v[32];
           tmem_ld32(t1 + c, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float h = fmaxf(v[i] + sPar[c + i], 0.f);
-            s += h;
-            q = fmaf(h, h, q);
+          for (int i = 0; i < 32; i += 2) {
+            fadd2(v[i], v[i + 1], sPar[c + i], sPar[c + i + 1]);
+            v[i] = fmaxf(v[i], 0.f);
+            v[i + 1] = fmaxf(v[i + 1], 0.f);
+            fadd2(s0, s1, v[i], v[i + 1]);
+            ffma2p(q0, q1, v[i], v[i + 1], v[i], v[i + 1]);
           }
         }
-        mean = s * (1.f / D);
-        rstd = rsqrtf(fmaxf(q * (1.f / D) - mean * mean, 0.f) + p.eps1);
+        mean = (s0 + s1) * (1.f / D);
+        rstd = rsqrtf(fmaxf((q0 + q1) * (1.f / D) - mean * mean, 0.f) + p.eps1);
       }
+      const float nmr = -mean * rstd;              // LayerNorm 1 without its affine part (folded into W2 / b2)
 #pragma unroll 1
       for (int c = 0; c < D; c += 32) {
         float v[32];
         tmem_ld32(t1 + c, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float h = fmaxf(v[i] + sPar[c + i], 0.f);
-          v[i] = has_ln1 ? (h - mean) * rstd * sPar[D + c + i] + sPar[2 * D + c + i] : h;
+        for (int i = 0; i < 32; i += 2) {
+          fadd2(v[i], v[i + 1], sPar[c + i], sPar[c + i + 1]);
+          float h0 = fmaxf(v[i], 0.f), h1 = fmaxf(v[i + 1], 0.f);
+          if (has_ln1) {
+            v[i] = nmr;
+            v[i + 1] = nmr;
+            ffma2(v[i], v[i + 1], rstd, h0, h1);
+          } else {
+            v[i] = h0;
+            v[i + 1] = h1;
+          }
         }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
@@ -483,7 +545,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       tc_fence_after();
       }  // !single
       const uint32_t tfin = p.single ? tmem_acc1 : tmem_acc2;           // single Linear: acc1 is the result
-      const int bias_off = p.single ? 0 : 3 * D;
+      const int bias_off = p.single ? 0 : D;
 #pragma unroll 1
       for (int pass = 0; pass < NPASS; ++pass) {
         const uint32_t t2 = tfin + lane_off + pass * CPP;
@@ -493,9 +555,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
           float v[32];
           tmem_ld32(t2 + c, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] += sPar[bias_off + pass * CPP + c + i];
-            if (p.relu_out) v[i] = fmaxf(v[i], 0.f);
+          for (int i = 0; i < 32; i += 2) {
+            fadd2(v[i], v[i + 1], sPar[bias_off + pass * CPP + c + i], sPar[bias_off + pass * CPP + c + i + 1]);
+            if (p.relu_out) {
+              v[i] = fmaxf(v[i], 0.f);
+              v[i + 1] = fmaxf(v[i + 1], 0.f);
+            }
           }
           if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
