@@ -44,6 +44,8 @@ SIGNATURES = {
     'allset_bias_act_norm_bwd': (_c.c_int, [_p, _p, _p, _c.c_int, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
     'allset_mlp2_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _c.c_int, _i64, _i32,
                                    _p, _c.c_int, _p, _p]),
+    'allset_pma_tail_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _f32, _c.c_int, _i64, _i32,
+                                       _p, _c.c_int, _p, _p]),
     'allset_segreduce_bwd_w': (_c.c_int, [_p, _p, _c.c_int, _i32, _p, _p, _p, _i64, _p, _p]),
     'allset_pma_fwd': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
                                   _p, _i32, _i32, _p, _p, _p]),
@@ -298,6 +300,36 @@ def mlp2_fwd(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: 
         _check(lib().allset_mlp2_fwd(_ptr(x), xd, _ptr(g[0]), _ptr(b[0]), float(eps[0]), _ptr(w1), _ptr(b1),
                                      _ptr(g[1]), _ptr(b[1]), float(eps[1]), _ptr(w2), _ptr(b2), 1 if relu_out else 0,
                                      rows, d, _ptr(out), od, _ptr(status), _stream()), 'allset_mlp2_fwd')
+    return out
+
+
+def pma_tail_fwd(x: torch.Tensor, ln0, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor,
+                 b2: Optional[torch.Tensor], ln1, relu_final: bool = False,
+                 out_dtype: Optional[torch.dtype] = None, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = [relu]( LN1( y + relu( relu(y W1^T + b1) W2^T + b2 ) ) ), y = LN0(x): PMA's ln0 / rFF / residual / ln1 in one
+    tcgen05 kernel.  x [rows, d] f32|bf16, d in MLP2_WIDTHS; ln0, ln1 = (gamma, beta | None, eps)."""
+    _need(x, 'x')
+    xd = _dtype_code(x)
+    if x.dim() != 2:
+        raise ValueError('x must be [rows, d]')
+    rows, d = x.shape
+    for name, t in (('w1', w1), ('w2', w2)):
+        _need(t, name, torch.float32)
+        if tuple(t.shape) != (d, d):
+            raise ValueError('pma_tail_fwd: %s must be %s, got %s' % (name, (d, d), tuple(t.shape)))
+    for name, t in (('b1', b1), ('b2', b2), ('ln0 gamma', ln0[0]), ('ln0 beta', ln0[1]), ('ln1 gamma', ln1[0]),
+                    ('ln1 beta', ln1[1])):
+        _need(t, name, torch.float32, optional=name not in ('ln0 gamma', 'ln1 gamma'))
+        if t is not None and t.numel() != d:
+            raise ValueError('pma_tail_fwd: %s must have %d entries' % (name, d))
+    out = torch.empty((rows, d), dtype=torch.float32 if out_dtype is None else out_dtype, device=x.device)
+    od = _dtype_code(out)
+    _need(status, 'status', torch.int32, optional=True)
+    with torch.cuda.device(x.device):
+        _check(lib().allset_pma_tail_fwd(_ptr(x), xd, _ptr(ln0[0]), _ptr(ln0[1]), float(ln0[2]), _ptr(w1), _ptr(b1),
+                                         _ptr(w2), _ptr(b2), _ptr(ln1[0]), _ptr(ln1[1]), float(ln1[2]),
+                                         1 if relu_final else 0, rows, d, _ptr(out), od, _ptr(status), _stream()),
+               'allset_pma_tail_fwd')
     return out
 
 

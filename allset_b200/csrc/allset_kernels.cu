@@ -1866,6 +1866,24 @@ namespace {
 #include "mlp_tcgen05.cuh"
 }  // namespace
 
+namespace {
+template <bool TAIL>
+int mlp2_dispatch(const mlp5::Params& p, int x_dtype, int out_dtype, int32_t d, cudaStream_t st) {
+  using bf16 = __nv_bfloat16;
+#define ALLSET_MLP2_CASE(D_)                                                                                    \
+  if (d == D_) {                                                                                                \
+    if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_F32) return mlp5::launch<float, float, D_, TAIL>(p, st);   \
+    if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_BF16) return mlp5::launch<float, bf16, D_, TAIL>(p, st);   \
+    if (x_dtype == ALLSET_BF16 && out_dtype == ALLSET_F32) return mlp5::launch<bf16, float, D_, TAIL>(p, st);   \
+    return mlp5::launch<bf16, bf16, D_, TAIL>(p, st);                                                           \
+  }
+  ALLSET_MLP2_CASE(64)
+  ALLSET_MLP2_CASE(128)
+#undef ALLSET_MLP2_CASE
+  return fail(ALLSET_EUNSUPPORTED, "mlp2: width %d not supported", (int)d);
+}
+}  // namespace
+
 extern "C" {
 
 int allset_version(void) { return ALLSET_ABI_VERSION; }
@@ -2078,21 +2096,27 @@ int allset_mlp2_fwd(const void* x, int x_dtype, const float* ln0_gamma, const fl
   const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)ln0_gamma | (uintptr_t)ln1_gamma;
   if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: x, out, w1, w2 and the LayerNorm gammas must be 16-byte aligned");
   mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, ln1_gamma, ln1_beta, single ? w1 : w2, b2, ln0_eps, ln1_eps, relu_out,
-                 single, (long long)rows, status};
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  using bf16 = __nv_bfloat16;
-#define ALLSET_MLP2_CASE(D_)                                                                  \
-  if (d == D_) {                                                                              \
-    if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_F32) return mlp5::launch<float, float, D_>(p, st);   \
-    if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_BF16) return mlp5::launch<float, bf16, D_>(p, st);   \
-    if (x_dtype == ALLSET_BF16 && out_dtype == ALLSET_F32) return mlp5::launch<bf16, float, D_>(p, st);   \
-    return mlp5::launch<bf16, bf16, D_>(p, st);                                               \
-  }
-  ALLSET_MLP2_CASE(64)
-  ALLSET_MLP2_CASE(128)
-#undef ALLSET_MLP2_CASE
-  return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: unreachable");
+                 single, (long long)rows, status, 0, 0, nullptr, nullptr, 0.f};
+  return mlp2_dispatch<false>(p, x_dtype, out_dtype, d, static_cast<cudaStream_t>(stream));
 }
+
+int allset_pma_tail_fwd(const void* x, int x_dtype, const float* ln0_gamma, const float* ln0_beta, float ln0_eps,
+                        const float* w1, const float* b1, const float* w2, const float* b2, const float* ln1_gamma,
+                        const float* ln1_beta, float ln1_eps, int relu_final, int64_t rows, int32_t d, void* out,
+                        int out_dtype, int32_t* status, void* stream) {
+  if (rows < 0 || d <= 0) return fail(ALLSET_EINVAL, "pma_tail_fwd: bad size");
+  if (bad_dtype(x_dtype) || bad_dtype(out_dtype)) return fail(ALLSET_EINVAL, "pma_tail_fwd: dtype must be 0 (f32) or 1 (bf16)");
+  if (d != 64 && d != 128) return fail(ALLSET_EUNSUPPORTED, "pma_tail_fwd: width %d not supported (64 or 128)", (int)d);
+  if (rows == 0) return ALLSET_OK;
+  if (x == nullptr || out == nullptr || w1 == nullptr || w2 == nullptr || ln0_gamma == nullptr || ln1_gamma == nullptr)
+    return fail(ALLSET_EINVAL, "pma_tail_fwd: null pointer");
+  const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)ln0_gamma;
+  if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "pma_tail_fwd: x, out, w1, w2, ln0_gamma must be 16-byte aligned");
+  mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, nullptr, nullptr, w2, b2, ln0_eps, 1e-5f, 1,
+                 0, (long long)rows, status, 1, relu_final, ln1_gamma, ln1_beta, ln1_eps};
+  return mlp2_dispatch<true>(p, x_dtype, out_dtype, d, static_cast<cudaStream_t>(stream));
+}
+
 
 int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32_t d, const int32_t* rowptr,
                            const int32_t* col, const float* tgt_scale, int64_t n_tgt, float* grad_w,

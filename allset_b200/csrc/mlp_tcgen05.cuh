@@ -42,6 +42,13 @@ struct Params {
   int single;       // 1: ONE Linear only (out = [relu](LN0?(x) W1^T + b1)); w2 / b2 / ln1 unused (warp-specialised kernel)
   long long rows;
   int* status;      // device word, set to 1 if an mbarrier wait timed out (debug aid; never in a correct run)
+  // tail != 0 (PMA tail, src/layers.py:155-157):  out = [relu_final]( LNf( y + relu(MLP(y)) ) ), y = LN0(x) WITH its
+  // affine part; ln1 must be absent, ln0 present.  lnf_* = the LayerNorm after the residual (PMA.ln1).
+  int tail;
+  int relu_final;
+  const float* lnf_g;
+  const float* lnf_b;
+  float epsf;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -87,6 +94,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// the reverse: each thread writes 32 consecutive fp32 columns of its TMEM lane
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in
 // bits [0,14), leading byte offset (unused for swizzled K-major, canonical value 1) in [16,30), stride byte
@@ -246,7 +271,7 @@ struct WsLayout {
   static constexpr int TMEM_COLS = (4 * D <= 256) ? 256 : 512;
   template <typename TOut>
   __host__ __device__ static constexpr int smem_bytes() {
-    return 1024 + 2 * L::W_BYTES + 2 * L::A_BYTES + 2 * L::template buf_bytes<TOut>() + 4 * D * 4 + 256;
+    return 1024 + 2 * L::W_BYTES + 2 * L::A_BYTES + 2 * L::template buf_bytes<TOut>() + 6 * D * 4 + 256 + 4 * kTileM * 8;
   }
 };
 
@@ -280,8 +305,9 @@ struct Producer {
     }
   }
   // LayerNorm 0 WITHOUT its affine part (gamma / beta are folded into W1 / b1 at setup), the G row groups in lockstep.
-  __device__ static __forceinline__ void process(const Buf& buf, uint32_t sAst, int pw, int half, int sub, int cl,
-                                                 bool has_ln0, float eps0) {
+  using Packed = uint32_t[G][EPL / 2];          // the normalised rows of one half as bf16 pairs
+  __device__ static __forceinline__ void compute(const Buf& buf, Packed& pk, float2 (&stats)[G], bool has_ln0,
+                                                 float eps0) {
     float v[G][EPL];
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
@@ -308,8 +334,11 @@ struct Producer {
         for (int gi = 0; gi < G; ++gi) s[gi] += __shfl_xor_sync(0xffffffffu, s[gi], o);
       }
 #pragma unroll
+      float mean_[G];
+#pragma unroll
       for (int gi = 0; gi < G; ++gi) {
         const float nm = -s[gi] * (1.f / D);
+        mean_[gi] = -nm;
         float q0 = 0.f, q1 = 0.f;
 #pragma unroll
         for (int e = 0; e < EPL; e += 2) {
@@ -328,27 +357,38 @@ struct Producer {
         const float rstd = rsqrtf(s[gi] * (1.f / D) + eps0);
 #pragma unroll
         for (int e = 0; e < EPL; e += 2) fmul2(v[gi][e], v[gi][e + 1], rstd);
+        stats[gi] = make_float2(mean_[gi], rstd);   // PMA tail: the epilogue re-derives the residual from x with these
       }
     }
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
+#pragma unroll
+      for (int e = 0; e < EPL; e += 2) pk[gi][e / 2] = pack_bf16(v[gi][e], v[gi][e + 1]);
+    }
+  }
+  // the only part that needs the A stage to be free: EPL/2 registers per row -> swizzled shared memory
+  __device__ static __forceinline__ void store(const Packed& pk, const float2 (&stats)[G], float2* stat, uint32_t sAst,
+                                               int pw, int half, int sub, int cl) {
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
       const int r = pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
+      if (stat != nullptr && cl == 0) stat[r] = stats[gi];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         const int col = (cl + LPR * j) * EPC;                  // first column of this chunk
         const uint32_t dst = sAst + sw128_chunk<kTileM>(r, col >> 3) + (uint32_t)((col & 7) * 2);
-        const float* w = &v[gi][j * EPC];
+        const uint32_t* w = &pk[gi][j * EPC / 2];
         if constexpr (EPC == 4) {
-          st_shared8(dst, pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]));
+          st_shared8(dst, w[0], w[1]);
         } else {
-          st_shared16(dst, pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+          st_shared16(dst, w[0], w[1], w[2], w[3]);
         }
       }
     }
   }
 };
 
-template <typename TIn, typename TOut, int D>
+template <typename TIn, typename TOut, int D, bool TAIL>
 __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) {
   using L = Layout<D>;
   static_assert(D == 64 || D == 128, "mlp2_ws: widths 64 and 128");
@@ -368,9 +408,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
   const uint32_t sA0 = sW2 + L::W_BYTES;                 // 2 stages of L::A_BYTES
   const uint32_t sA1 = sA0 + 2 * L::A_BYTES;             // 2 hidden tiles / output staging buffers of BUF bytes
   constexpr int PAR_OFF = 2 * L::W_BYTES + 2 * L::A_BYTES + 2 * BUF;
-  float* sPar = reinterpret_cast<float*>(smem + PAR_OFF);                       // folded biases b1', b2'
-  const uint32_t sBar = sW1 + PAR_OFF + 4 * D * 4;                              // 8 mbarriers, [kind][buffer set]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PAR_OFF + 4 * D * 4 + 128);
+  float* sPar = reinterpret_cast<float*>(smem + PAR_OFF);     // b1', b2' (folded) | tail: gamma0, beta0, gamma_f, beta_f
+  const uint32_t sBar = sW1 + PAR_OFF + 6 * D * 4;            // 8 mbarriers, [kind][buffer set]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PAR_OFF + 6 * D * 4 + 128);
+  float2* sStat = reinterpret_cast<float2*>(smem + PAR_OFF + 6 * D * 4 + 256);   // tail: (mean0, rstd0) [group][k & 1][row]
   const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 16, bar_acc1_full = sBar + 32, bar_acc2_full = sBar + 48;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -390,6 +431,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), WsLayout<D>::TMEM_COLS);
   // weights -> bf16 K-major SWIZZLE_128B, with the LayerNorm in front of each Linear folded in:
   //   LN(x) W^T + b = n(x) (W diag(gamma))^T + (b + W beta),  n(x) = (x - mean) * rstd
+#pragma unroll 4
   for (int idx = tid; idx < 2 * D * (D / 8); idx += kWsThreads) {
     const int which = idx / (D * (D / 8));
     const int rem = idx - which * (D * (D / 8));
@@ -407,19 +449,33 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     st_shared16((which ? sW2 : sW1) + sw128_chunk<D>(n, j), pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w),
                 pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
   }
-  // biases: sPar[0..D) = b1 + W1 beta0, sPar[D..2D) = b2 + W2 beta1 (one warp per output row, fp32)
-  for (int n = warp; n < 2 * D; n += kWsThreads / 32) {
-    const int which = n / D, row = n - which * D;
+  // biases: sPar[0..D) = b1 + W1 beta0, sPar[D..2D) = b2 + W2 beta1 (fp32; 4 threads per output row, independent
+  // 16-byte loads so the whole fold is one round trip to L2)
+  for (int n = tid >> 2; n < 2 * D; n += kWsThreads / 4) {
+    const int which = n / D, row = n - which * D, part = tid & 3;
     const float* bias = which ? p.b2 : p.b1;
     const float* beta = which ? (has_ln1 ? p.ln1_b : nullptr) : (has_ln0 ? p.ln0_b : nullptr);
     float acc = 0.f;
     if (beta != nullptr && !(which && p.single)) {
-      const float* w = (which ? p.w2 : p.w1) + (size_t)row * D;
-      for (int kk = lane; kk < D; kk += 32) acc = fmaf(w[kk], beta[kk], acc);
+      const float* w = (which ? p.w2 : p.w1) + (size_t)row * D + part * (D / 4);
+      const float* bt = beta + part * (D / 4);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      for (int kk = 0; kk < D / 4; kk += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + kk);
+        acc = fmaf(wv.x, bt[kk], fmaf(wv.y, bt[kk + 1], fmaf(wv.z, bt[kk + 2], fmaf(wv.w, bt[kk + 3], acc))));
+      }
     }
-    if (lane == 0) sPar[n] = (bias ? bias[row] : 0.f) + acc;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0) sPar[n] = (bias ? bias[row] : 0.f) + acc;
+  }
+  if (TAIL) {
+    for (int i = tid; i < D; i += kWsThreads) {
+      sPar[2 * D + i] = p.ln0_g[i];
+      sPar[3 * D + i] = p.ln0_b ? p.ln0_b[i] : 0.f;
+      sPar[4 * D + i] = p.lnf_g ? p.lnf_g[i] : 1.f;
+      sPar[5 * D + i] = p.lnf_b ? p.lnf_b[i] : 0.f;
+    }
   }
   proxy_fence_async();
   tc_fence_before();
@@ -443,12 +499,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     for (uint32_t it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t st = it & 1u;
       const long long next = tile + gridDim.x;
-      if (it >= 2) mbar_wait_bounded<256>(bar_a_empty + 8 * st, ((it >> 1) - 1) & 1u, p.status);
       const uint32_t sAst = sA0 + st * L::A_BYTES;
-      P::process(bufA, sAst, pw, 0, sub, cl, has_ln0, p.eps0);
+      float2* stat = TAIL ? sStat + (st * 2 + ((it >> 1) & 1u)) * kTileM : nullptr;
+      // all the arithmetic happens BEFORE the stage is known to be free; only the shared-memory stores wait for it
+      typename P::Packed pkA, pkB;
+      float2 stA[P::G] = {}, stB[P::G] = {};
+      P::compute(bufA, pkA, stA, has_ln0, p.eps0);
       if (next < n_tiles) P::load(bufA, xb, next * kTileM, p.rows, pw, 0, sub, cl);
-      P::process(bufB, sAst, pw, 1, sub, cl, has_ln0, p.eps0);
+      P::compute(bufB, pkB, stB, has_ln0, p.eps0);
       if (next < n_tiles) P::load(bufB, xb, next * kTileM, p.rows, pw, 1, sub, cl);
+      if (it >= 2) mbar_wait_bounded<200>(bar_a_empty + 8 * st, ((it >> 1) - 1) & 1u, p.status);
+      P::store(pkA, stA, stat, sAst, pw, 0, sub, cl);     // (this sStat slot was read at the top of tile k-2's epilogue)
+      P::store(pkB, stB, stat, sAst, pw, 1, sub, cl);
       proxy_fence_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a_full + 8 * st);
@@ -479,6 +541,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     long long tile = blockIdx.x + (long long)g * gridDim.x;
     if (issuer && tile < n_tiles) gemm1(0);
     __syncwarp();
+    if (TAIL) epi_bar_sync(g);                         // every thread of the group is ordered after the issuer's a_full acquire
     uint32_t k = 0;                                    // this group's tile counter
     for (; tile < n_tiles; tile += 2LL * gridDim.x, ++k) {
       const long long row0 = tile * kTileM;
@@ -486,11 +549,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       mbar_wait_bounded(bar_acc1_full + 8 * g, k & 1u, p.status);
       tc_fence_after();
       const bool has_next = tile + 2LL * gridDim.x < n_tiles;
+      // PMA tail: this row's (mean0, rstd0).  Read NOW: GEMM 1 of the group's next tile is issued after epilogue 1, its
+      // commit frees the A stage, and from then on the producers may write the statistics of tile k+2 into this slot.
+      float2 st0 = make_float2(0.f, 1.f);
+      if (TAIL) st0 = sStat[(g * 2 + (k & 1u)) * kTileM + r];
       if (!p.single) {
       const uint32_t t1 = tmem_acc1 + lane_off;
       float mean = 0.f, rstd = 1.f;
       if (has_ln1) {
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};      // 2 independent packed chains each
 #pragma unroll 1
         for (int c = 0; c < D; c += 32) {
           float v[32];
@@ -500,12 +567,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
             fadd2(v[i], v[i + 1], sPar[c + i], sPar[c + i + 1]);
             v[i] = fmaxf(v[i], 0.f);
             v[i + 1] = fmaxf(v[i + 1], 0.f);
-            fadd2(s0, s1, v[i], v[i + 1]);
-            ffma2p(q0, q1, v[i], v[i + 1], v[i], v[i + 1]);
+            fadd2(sa[i & 2], sa[(i & 2) + 1], v[i], v[i + 1]);
+            ffma2p(qa[i & 2], qa[(i & 2) + 1], v[i], v[i + 1], v[i], v[i + 1]);
           }
         }
-        mean = (s0 + s1) * (1.f / D);
-        rstd = rsqrtf(fmaxf((q0 + q1) * (1.f / D) - mean * mean, 0.f) + p.eps1);
+        const float ssum = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+        const float qsum = (qa[0] + qa[1]) + (qa[2] + qa[3]);
+        mean = ssum * (1.f / D);
+        rstd = rsqrtf(fmaxf(qsum * (1.f / D) - mean * mean, 0.f) + p.eps1);
       }
       const float nmr = -mean * rstd;              // LayerNorm 1 without its affine part (folded into W2 / b2)
 #pragma unroll 1
@@ -546,6 +615,49 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       }  // !single
       const uint32_t tfin = p.single ? tmem_acc1 : tmem_acc2;           // single Linear: acc1 is the result
       const int bias_off = p.single ? 0 : D;
+      float rstdf = 1.f, nmrf = 0.f;
+      if constexpr (TAIL) {
+        // ---- PMA tail, pass 1: z = LN0(x) + relu(acc2 + b2') -> back into acc2[g] (TMEM), row statistics of z ---------
+        // (mean0, rstd0) were written by the producers before their a_full arrive; the issuer acquired that barrier
+        // before GEMM 1 of this tile and has been through a group barrier with every thread here since (waiting on
+        // a_full again would be wrong: the producers may already have completed the NEXT phase of that barrier).
+        const float nmr0 = -st0.x * st0.y;
+        const long long gr = row0 + r;
+        const unsigned char* xrow = static_cast<const unsigned char*>(p.x) + (size_t)(gr < p.rows ? gr : 0) * (D * sizeof(TIn));
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+          float v[32], xf[32];
+          constexpr int XC = RowChunk<TIn>::N;
+#pragma unroll
+          for (int j = 0; j < 32 / XC; ++j) {
+            const uint4 q = (gr < p.rows) ? ld_nc_16(xrow + (size_t)(c + j * XC) * sizeof(TIn)) : make_uint4(0, 0, 0, 0);
+            float t[XC];
+            RowChunk<TIn>::unpack(q, t);
+#pragma unroll
+            for (int e = 0; e < XC; ++e) xf[j * XC + e] = t[e];
+          }
+          tmem_ld32(tmem_acc2 + lane_off + c, v);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            fadd2(v[i], v[i + 1], sPar[D + c + i], sPar[D + c + i + 1]);
+            v[i] = fmaxf(v[i], 0.f);
+            v[i + 1] = fmaxf(v[i + 1], 0.f);
+            float t0 = nmr0, t1 = nmr0;
+            ffma2(t0, t1, st0.y, xf[i], xf[i + 1]);                                  // (x - mean0) * rstd0
+            float y0 = sPar[3 * D + c + i], y1 = sPar[3 * D + c + i + 1];
+            ffma2p(y0, y1, t0, t1, sPar[2 * D + c + i], sPar[2 * D + c + i + 1]);    // * gamma0 + beta0
+            fadd2(v[i], v[i + 1], y0, y1);                                           // z = y + relu(h)
+            fadd2(sa[i & 2], sa[(i & 2) + 1], v[i], v[i + 1]);
+            ffma2p(qa[i & 2], qa[(i & 2) + 1], v[i], v[i + 1], v[i], v[i + 1]);
+          }
+          tmem_st32(tmem_acc2 + lane_off + c, v);
+        }
+        tmem_wait_st();
+        const float mf = ((sa[0] + sa[1]) + (sa[2] + sa[3])) * (1.f / D);
+        rstdf = rsqrtf(fmaxf(((qa[0] + qa[1]) + (qa[2] + qa[3])) * (1.f / D) - mf * mf, 0.f) + p.epsf);
+        nmrf = -mf * rstdf;
+      }
 #pragma unroll 1
       for (int pass = 0; pass < NPASS; ++pass) {
         const uint32_t t2 = tfin + lane_off + pass * CPP;
@@ -556,10 +668,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
           tmem_ld32(t2 + c, v);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            fadd2(v[i], v[i + 1], sPar[bias_off + pass * CPP + c + i], sPar[bias_off + pass * CPP + c + i + 1]);
-            if (p.relu_out) {
-              v[i] = fmaxf(v[i], 0.f);
-              v[i + 1] = fmaxf(v[i + 1], 0.f);
+            const int cc = pass * CPP + c + i;
+            if constexpr (TAIL) {                  // LNf(z): (z - mean) * rstd * gamma_f + beta_f, then the outer ReLU
+              float t0 = nmrf, t1 = nmrf;
+              ffma2(t0, t1, rstdf, v[i], v[i + 1]);
+              v[i] = sPar[5 * D + cc];
+              v[i + 1] = sPar[5 * D + cc + 1];
+              ffma2p(v[i], v[i + 1], t0, t1, sPar[4 * D + cc], sPar[4 * D + cc + 1]);
+              if (p.relu_final) {
+                v[i] = fmaxf(v[i], 0.f);
+                v[i + 1] = fmaxf(v[i + 1], 0.f);
+              }
+            } else {
+              fadd2(v[i], v[i + 1], sPar[bias_off + cc], sPar[bias_off + cc + 1]);
+              if (p.relu_out) {
+                v[i] = fmaxf(v[i], 0.f);
+                v[i + 1] = fmaxf(v[i + 1], 0.f);
+              }
             }
           }
           if constexpr (sizeof(TOut) == 2) {
@@ -604,23 +729,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
   if (warp == 1) tmem_dealloc(tmem_base, WsLayout<D>::TMEM_COLS);
 }
 
-template <typename TIn, typename TOut, int D>
+template <typename TIn, typename TOut, int D, bool TAIL>
 int launch(const Params& p, cudaStream_t st) {
   const long long n_tiles = (p.rows + kTileM - 1) / kTileM;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   constexpr int smem = WsLayout<D>::template smem_bytes<TOut>();
-  cudaError_t e = cudaFuncSetAttribute(mlp2_ws_kernel<TIn, TOut, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(mlp2_ws_kernel<TIn, TOut, D, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return fail(ALLSET_ECUDA, "mlp2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int fits = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fits, mlp2_ws_kernel<TIn, TOut, D>, kWsThreads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fits, mlp2_ws_kernel<TIn, TOut, D, TAIL>, kWsThreads, smem);
   if (e != cudaSuccess || fits < 1)
     return fail(ALLSET_ECUDA, "mlp2_fwd: the 16-warp kernel does not fit one SM (%s)",
                 e != cudaSuccess ? cudaGetErrorString(e) : "0 resident CTAs");
   long long grid = sms;
   if (grid > n_tiles) grid = n_tiles;
-  mlp2_ws_kernel<TIn, TOut, D><<<(unsigned)grid, kWsThreads, smem, st>>>(p);
+  mlp2_ws_kernel<TIn, TOut, D, TAIL><<<(unsigned)grid, kWsThreads, smem, st>>>(p);
   return check_launch("mlp2_fwd");
 }
 

@@ -180,7 +180,9 @@ class PMA(nn.Module):
         self.ln1.reset_parameters()
         nn.init.xavier_uniform_(self.att_r)
 
-    def forward(self, x, edge_index, size=None, return_attention_weights=None):
+    def forward(self, x, edge_index, size=None, return_attention_weights=None, relu_out: bool = False):
+        """`relu_out` (extension, default off = reference behaviour): also apply the ReLU SetGNN.forward wraps around
+        every half layer (reference src/models.py:475,478), inside the fused tail kernel where there is one."""
         assert x.dim() == 2, 'Static graphs not supported in `GATConv`.'
         H, C = self.heads, self.hidden
         inc = _resolve(edge_index, x.size(0))
@@ -204,20 +206,26 @@ class PMA(nn.Module):
             v = x_V if self.agg_dtype is None else x_V.to(self.agg_dtype)
         want_alpha = isinstance(return_attention_weights, bool)
         out, alpha = ops.pma_aggregate(v, score, self.att_r, inc, H, self.negative_slope, return_alpha=want_alpha)
-        out = out.to(score.dtype)                                        # [n_tgt, H*C], seed already added
+        applied_relu = False
         if self.rFF._tc_ok(out):
-            # ln0 -> [rFF = Linear, ReLU, Linear on tcgen05, ReLU] -> ln1(residual + .): three passes over the rows
-            out = ops.bias_act_norm(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps)
-            h = self.rFF(out, final_relu=True)
-            out = ops.bias_act_norm(h, residual=out, gamma=self.ln1.weight, beta=self.ln1.bias, eps=self.ln1.eps)
+            # bf16 mode: ln0 -> rFF -> ln1(residual + relu(.)) [-> the caller's ReLU] as ONE tcgen05 kernel reading the
+            # aggregated rows in their storage dtype
+            l0, l1 = self.rFF.lins
+            out = _lib.pma_tail_fwd(out.contiguous(), (self.ln0.weight, self.ln0.bias, self.ln0.eps), l0.weight, l0.bias,
+                                    l1.weight, l1.bias, (self.ln1.weight, self.ln1.bias, self.ln1.eps),
+                                    relu_final=relu_out, out_dtype=score.dtype)
+            applied_relu = relu_out
         elif fused:
+            out = out.to(score.dtype)                                    # [n_tgt, H*C], seed already added
             out = ops.bias_act_norm(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps)
             y, bias = self.rFF.forward_fused_open(out)
             out = ops.bias_act_norm(y, bias, relu=True, residual=out, gamma=self.ln1.weight, beta=self.ln1.bias,
                                     eps=self.ln1.eps)                    # ln1(out + relu(rFF(out))), one pass
         else:
-            out = self.ln0(out)
+            out = self.ln0(out.to(score.dtype))
             out = self.ln1(out + F.relu(self.rFF(out)))
+        if relu_out and not applied_relu:
+            out = F.relu(out)
         if want_alpha:
             return out, (edge_index, alpha)
         return out
@@ -274,9 +282,11 @@ class HalfNLHconv(nn.Module):
                 if isinstance(f, MLP):
                     f.tc_dtype = dtype if dtype == torch.bfloat16 else None
 
-    def forward(self, x, edge_index, norm, aggr='add'):
+    def forward(self, x, edge_index, norm, aggr='add', relu_out: bool = False):
+        """`relu_out` (extension): fold SetGNN.forward's `F.relu(conv(.))` (reference src/models.py:475,478) into the
+        layer -- the identity for a non-attention layer, which already ends in relu(f_dec(.))."""
         if self.attention:
-            return self.prop(x, edge_index)              # norm and aggr are ignored, as in the reference
+            return self.prop(x, edge_index, relu_out=relu_out)       # norm and aggr are ignored, as in the reference
         if aggr is None:
             raise ValueError('aggr was not passed!')
         io_dtype = x.dtype

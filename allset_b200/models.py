@@ -109,15 +109,6 @@ class SetGNN(nn.Module):
         setattr(edge_index, _ATTR, (edge_index._version, n_nodes, v2e, e2v))
         return v2e, e2v
 
-    @staticmethod
-    def _relu(conv, x):
-        """`F.relu(conv(x))` of reference src/models.py:475,478.  A non-attention half layer already ends in
-        relu(f_dec(.)) (src/layers.py:634), so the outer ReLU is the identity (value and gradient) and a full pass
-        over [rows, d]; it is only applied where it does something (PMA ends in a LayerNorm)."""
-        if not conv.attention:
-            return x
-        return F.relu(x)
-
     def forward(self, data):
         """data.x [N, F]; data.edge_index [2, nnz] int64 (row 0 node id, row 1 hyperedge id, any base);
         data.norm [nnz] per-incidence weights (int64 ones by default).  Returns node logits [N, num_classes]."""
@@ -144,9 +135,9 @@ class SetGNN(nn.Module):
         else:
             x = F.dropout(x, p=0.2, training=self.training)     # input dropout, hard-coded in the reference
             for i, _ in enumerate(self.V2EConvs):
-                x = self._relu(self.V2EConvs[i], self.V2EConvs[i](x, v2e, norm, self.aggr))
+                x = self.V2EConvs[i](x, v2e, norm, self.aggr, relu_out=True)      # = F.relu(conv(.)), :475
                 x = F.dropout(x, p=self.dropout, training=self.training)
-                x = self._relu(self.E2VConvs[i], self.E2VConvs[i](x, e2v, norm, self.aggr))
+                x = self.E2VConvs[i](x, e2v, norm, self.aggr, relu_out=True)      # :478
                 x = F.dropout(x, p=self.dropout, training=self.training)
             x = self.classifier(x)
         return x

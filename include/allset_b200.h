@@ -140,6 +140,21 @@ int allset_mlp2_fwd(const void* x, int x_dtype,
                     const float* w2, const float* b2, int relu_out,
                     int64_t rows, int32_t d, void* out, int out_dtype, int32_t* status, void* stream);
 
+/* PMA's dense tail as ONE tcgen05 kernel (bf16 operands, fp32 accumulate and residual), equal widths d in {64, 128}:
+ *     y   = LN0(x)                                   (PMA.ln0 on `out + att_r`, src/layers.py:155)
+ *     out = [relu]( LN1( y + relu( rFF(y) ) ) )      (src/layers.py:157; rFF = Linear -> ReLU -> Linear, no norms,
+ *                                                     src/layers.py:76-80; the optional ReLU is the one SetGNN.forward
+ *                                                     applies to every half layer, src/models.py:475,478)
+ * x [rows, d] f32|bf16 (the aggregated rows in their storage dtype); w1, w2 [d, d] f32 ([out, in]); b1, b2, ln*_beta
+ * [d] f32 or NULL; out [rows, d] f32|bf16.  The residual y is re-derived from x in fp32 by the epilogue and z = y +
+ * relu(.) makes a round trip through TMEM (tcgen05.st / tcgen05.ld) between the statistics pass and the write pass.
+ * Replaces: dtype conversion, LayerNorm pass, 2 SGEMMs, 2 glue passes, ReLU pass.  status as in allset_mlp2_fwd. */
+int allset_pma_tail_fwd(const void* x, int x_dtype,
+                        const float* ln0_gamma, const float* ln0_beta, float ln0_eps,
+                        const float* w1, const float* b1, const float* w2, const float* b2,
+                        const float* ln1_gamma, const float* ln1_beta, float ln1_eps, int relu_final,
+                        int64_t rows, int32_t d, void* out, int out_dtype, int32_t* status, void* stream);
+
 /* Backward of allset_bias_act_norm (d in {128,256,512,1024}; ALLSET_EUNSUPPORTED otherwise):
  *   dx [rows, d] = gradient w.r.t. x;  dres [rows, d] or NULL = gradient w.r.t. residual;
  *   partial [blocks, 3, d] = per-CTA column sums of (d gamma, d beta, d bias), blocks =

@@ -145,7 +145,31 @@ case('noln', 70000, 128, f32, f32, False, False, True, True)
 case('ln0_only', 4096, 128, f32, b16, True, False, True, True)
 case('d64_full', 128 * 700 + 3, 64, f32, f32, True, True, True, True)
 case('d64_bf16', 999, 64, b16, b16, True, True, True, True)
+def timing_tail(rows, d, in_dtype, out_dtype):
+    x = torch.randn(rows, d, device=dev).to(in_dtype)
+    w1 = torch.randn(d, d, device=dev) / d ** 0.5
+    w2 = torch.randn(d, d, device=dev) / d ** 0.5
+    b = torch.zeros(d, device=dev)
+    ln = (torch.ones(d, device=dev), torch.zeros(d, device=dev), 1e-5)
+    f = lambda: _lib.pma_tail_fwd(x, ln, w1, b, w2, b, ln, True, out_dtype)
+    for _ in range(5):
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(30):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 30
+    nbytes = rows * d * (x.element_size() + torch.empty(0, dtype=out_dtype).element_size())
+    print(json.dumps({'timing': 'pma_tail', 'rows': rows, 'd': d, 'in': str(in_dtype), 'out': str(out_dtype), 'ms': ms,
+                      'GBps': nbytes / ms / 1e6}), flush=True)
+
+
 if '--time' in sys.argv and bad == 0:
+    timing_tail(1 << 20, 128, b16, f32)
+    timing_tail(1 << 20, 128, f32, f32)
     for ind, outd in ((f32, b16), (b16, f32), (f32, f32), (b16, b16)):
         timing(1 << 20, 128, ind, outd)
     timing(1 << 20, 64, f32, b16)

@@ -828,13 +828,17 @@ def test_pma_bf16_mode_runs_lin_v_and_rff_on_tcgen05(d, heads, monkeypatch):
     conv.to(dev()).eval()
     conv.set_agg_dtype(torch.bfloat16)
     x = torch.randn(n, d, generator=torch.Generator().manual_seed(5))
-    calls = []
-    real = _lib.mlp2_fwd
+    calls, tails = [], []
+    real, real_tail = _lib.mlp2_fwd, _lib.pma_tail_fwd
     monkeypatch.setattr(_lib, 'mlp2_fwd', lambda *a, **k: (calls.append(a[3] is None), real(*a, **k))[1])
+    monkeypatch.setattr(_lib, 'pma_tail_fwd', lambda *a, **k: (tails.append(a[0].dtype), real_tail(*a, **k))[1])
     inc = ab().Incidence.from_coo(node, he, n_src=n)
     with torch.no_grad():
         out = conv(x.to(dev()), inc, None, 'add')
-    assert calls == [True, False]                  # lin_V as a single Linear, then rFF as the two-layer chain
+        out_relu = conv(x.to(dev()), inc, None, 'add', relu_out=True)
+    assert calls == [True, True]                   # lin_V as a single Linear (once per forward)
+    assert tails == [torch.bfloat16] * 2           # ln0 / rFF / residual / ln1 as one kernel on the bf16 rows
+    assert torch.equal(out_relu, torch.relu(out))
     ref = O.half_nlh_conv(params, '', x, node.cpu(), he.cpu(), None, 'add', attention=True, heads=heads)
     assert out.shape == ref.shape
     err = (out.cpu() - ref).abs().max().item()
@@ -863,3 +867,30 @@ def test_mlp2_single_linear_mode():
     with pytest.raises(ValueError):
         _lib.mlp2_fwd(torch.zeros(8, 128, device=dev()), torch.zeros(128, 128, device=dev()), None, None,
                       torch.zeros(128, device=dev()))
+
+
+@pytest.mark.parametrize('d', [128, 64])
+@pytest.mark.parametrize('in_dtype,out_dtype', [(torch.bfloat16, torch.float32), (torch.float32, torch.float32),
+                                                (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16)])
+def test_pma_tail_tcgen05_vs_torch(d, in_dtype, out_dtype):
+    """y = LN0(x); out = [relu](LN1(y + relu(rFF(y)))) -- reference src/layers.py:155-157 -- in one kernel."""
+    from allset_b200 import _lib
+    g = torch.Generator().manual_seed(d + 7)
+    w1 = torch.randn(d, d, generator=g) / d ** 0.5
+    w2 = torch.randn(d, d, generator=g) / d ** 0.5
+    b1, b2 = 0.3 * torch.randn(d, generator=g), 0.3 * torch.randn(d, generator=g)
+    ln0 = (1 + 0.2 * torch.randn(d, generator=g), 0.2 * torch.randn(d, generator=g), 1e-5)
+    ln1 = (1 + 0.2 * torch.randn(d, generator=g), 0.2 * torch.randn(d, generator=g), 1e-5)
+    to = lambda t: t.to(dev()) if torch.is_tensor(t) else t
+    for rows, relu_final in ((1, False), (127, True), (128 * 37 + 5, False), (128 * 600, True)):
+        x = (torch.randn(rows, d, generator=g) * 1.5 + 0.3).to(in_dtype)
+        y = F.layer_norm(x.float(), (d,), ln0[0], ln0[1], ln0[2])
+        h = F.linear(F.relu(F.linear(y, w1, b1)), w2, b2)
+        ref = F.layer_norm(y + F.relu(h), (d,), ln1[0], ln1[1], ln1[2])
+        ref = F.relu(ref) if relu_final else ref
+        status = torch.zeros(1, dtype=torch.int32, device=dev())
+        out = _lib.pma_tail_fwd(x.to(dev()), tuple(map(to, ln0)), to(w1), to(b1), to(w2), to(b2), tuple(map(to, ln1)),
+                                relu_final, out_dtype, status)
+        assert int(status.item()) == 0 and out.dtype == out_dtype
+        err = (out.float().cpu() - ref).abs().max().item()
+        assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), (rows, err)
