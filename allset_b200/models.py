@@ -109,6 +109,17 @@ class SetGNN(nn.Module):
         setattr(edge_index, _ATTR, (edge_index._version, n_nodes, v2e, e2v))
         return v2e, e2v
 
+    def _half(self, conv, x, inc, norm):
+        """`F.relu(conv(x, ...))` of reference src/models.py:475,478.  A non-attention half layer already ends in
+        relu(f_dec(.)) (src/layers.py:634): the outer ReLU is the identity (value and gradient) and a full pass over
+        [rows, d], so it is skipped.  A PMA half layer ends in a LayerNorm: the ReLU is applied here, except in bf16
+        eval mode where it is folded into the fused tail kernel (a forward hook on the layer then sees post-ReLU rows)."""
+        if not conv.attention:
+            return conv(x, inc, norm, self.aggr)
+        if conv.agg_dtype == torch.bfloat16 and not torch.is_grad_enabled():
+            return conv(x, inc, norm, self.aggr, relu_out=True)
+        return F.relu(conv(x, inc, norm, self.aggr))
+
     def forward(self, data):
         """data.x [N, F]; data.edge_index [2, nnz] int64 (row 0 node id, row 1 hyperedge id, any base);
         data.norm [nnz] per-incidence weights (int64 ones by default).  Returns node logits [N, num_classes]."""
@@ -135,9 +146,9 @@ class SetGNN(nn.Module):
         else:
             x = F.dropout(x, p=0.2, training=self.training)     # input dropout, hard-coded in the reference
             for i, _ in enumerate(self.V2EConvs):
-                x = self.V2EConvs[i](x, v2e, norm, self.aggr, relu_out=True)      # = F.relu(conv(.)), :475
+                x = self._half(self.V2EConvs[i], x, v2e, norm)                    # = F.relu(conv(.)), :475
                 x = F.dropout(x, p=self.dropout, training=self.training)
-                x = self.E2VConvs[i](x, e2v, norm, self.aggr, relu_out=True)      # :478
+                x = self._half(self.E2VConvs[i], x, e2v, norm)                    # :478
                 x = F.dropout(x, p=self.dropout, training=self.training)
             x = self.classifier(x)
         return x
