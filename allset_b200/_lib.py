@@ -43,7 +43,8 @@ SIGNATURES = {
     'allset_bias_act_norm_bwd_blocks': (_i32, [_i64]),
     'allset_bias_act_norm_bwd': (_c.c_int, [_p, _p, _p, _c.c_int, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
     'allset_mlp2_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _c.c_int, _i64, _i32,
-                                   _p, _c.c_int, _p, _p]),
+                                   _p, _c.c_int, _i64, _p, _p]),
+    'allset_pma_fwd_strided': (_c.c_int, [_p, _i64, _p, _i64, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64, _p, _p, _p]),
     'allset_pma_tail_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _f32, _c.c_int, _i64, _i32,
                                        _p, _c.c_int, _p, _p]),
     'allset_segreduce_bwd_w': (_c.c_int, [_p, _p, _c.c_int, _i32, _p, _p, _p, _i64, _p, _p]),
@@ -259,7 +260,8 @@ MLP2_WIDTHS = (64, 128)
 
 def mlp2_fwd(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: Optional[torch.Tensor],
              b2: Optional[torch.Tensor], ln0=None, ln1=None, relu_out: bool = False,
-             out_dtype: Optional[torch.dtype] = None, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+             out_dtype: Optional[torch.dtype] = None, status: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = [relu]( LN1?( relu( LN0?(x) W1^T + b1 ) ) W2^T + b2 ) in one tcgen05 kernel (bf16 operands, fp32
     accumulate).  x [rows, d] f32|bf16, d in MLP2_WIDTHS; w1, w2 [d, d] f32 ([out, in]); ln0 / ln1 = None or
     (gamma, beta | None, eps); out_dtype f32 (default) | bf16.  `status`: optional int32[1] diagnostic word.
@@ -292,14 +294,21 @@ def mlp2_fwd(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: 
         _need(b[i], 'ln%d beta' % i, torch.float32, optional=True)
         if g[i].numel() != d or (b[i] is not None and b[i].numel() != d):
             raise ValueError('mlp2_fwd: LayerNorm %d parameters must have %d entries' % (i, d))
-    out_dtype = torch.float32 if out_dtype is None else out_dtype
-    out = torch.empty((rows, d), dtype=out_dtype, device=x.device)
+    if out is None:
+        out_dtype = torch.float32 if out_dtype is None else out_dtype
+        out = torch.empty((rows, d), dtype=out_dtype, device=x.device)
+        pitch = 0
+    else:
+        # a [rows, d] view with unit column stride and a row pitch (e.g. the value part of packed PMA records)
+        if not out.is_cuda or tuple(out.shape) != (rows, d) or out.stride(1) != 1:
+            raise ValueError('mlp2_fwd: out must be a CUDA [rows, d] view with unit column stride')
+        pitch = out.stride(0) * out.element_size()
     od = _dtype_code(out)
     _need(status, 'status', torch.int32, optional=True)
     with torch.cuda.device(x.device):
         _check(lib().allset_mlp2_fwd(_ptr(x), xd, _ptr(g[0]), _ptr(b[0]), float(eps[0]), _ptr(w1), _ptr(b1),
                                      _ptr(g[1]), _ptr(b[1]), float(eps[1]), _ptr(w2), _ptr(b2), 1 if relu_out else 0,
-                                     rows, d, _ptr(out), od, _ptr(status), _stream()), 'allset_mlp2_fwd')
+                                     rows, d, _ptr(out), od, pitch, _ptr(status), _stream()), 'allset_mlp2_fwd')
     return out
 
 
@@ -391,6 +400,41 @@ def pma_fwd_bcast(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: i
         raise Unsupported(lib().allset_last_error().decode())
     _check(code, 'allset_pma_fwd_bcast')
     return out
+
+
+def packed_pma_records(n_src: int, d: int, H: int, dtype: torch.dtype, device) -> tuple:
+    """One [values | scores] record per source row: returns (buf uint8 [n_src, d*es + H*4], values view [n_src, d] of
+    `dtype`, scores view [n_src, H] float32).  Both views have unit column stride and the record size as row pitch."""
+    es = torch.empty(0, dtype=dtype).element_size()
+    rowb = d * es
+    buf = torch.empty((n_src, rowb + H * 4), dtype=torch.uint8, device=device)
+    return buf, buf[:, :rowb].view(dtype), buf[:, rowb:].view(torch.float32)
+
+
+def pma_fwd_strided(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: int, C: int, slope: float,
+                    rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, want_stats: bool = False):
+    """pma_fwd over strided sources (views with unit column stride and a row pitch, e.g. packed_pma_records): stream
+    kernel only -- raises Unsupported where it does not apply.  -> (out [n_tgt, H*C] dense, stats | None)."""
+    for name, t, cols in (('v', v, H * C), ('score', score, H)):
+        if not t.is_cuda or t.dim() != 2 or t.shape[1] != cols or t.stride(1) != 1:
+            raise ValueError('pma_fwd_strided: %s must be a CUDA [n_src, %d] view with unit column stride' % (name, cols))
+    if score.dtype != torch.float32 or score.shape[0] != v.shape[0]:
+        raise ValueError('pma_fwd_strided: score must be float32 [n_src, H]')
+    _need(seed, 'seed', torch.float32)
+    _need(rowptr, 'rowptr', torch.int32)
+    _need(col, 'col', torch.int32)
+    out = torch.empty((n_tgt, H * C), dtype=v.dtype, device=v.device)
+    stats = torch.empty((n_tgt, H, 2), dtype=torch.float32, device=v.device) if want_stats else None
+    if n_tgt == 0:
+        return out, stats
+    with torch.cuda.device(v.device):
+        code = lib().allset_pma_fwd_strided(_ptr(v), v.stride(0) * v.element_size(), _ptr(score), score.stride(0) * 4,
+                                            _ptr(seed), _dtype_code(v), H, C, float(slope), _ptr(rowptr), _ptr(col),
+                                            n_tgt, _ptr(out), _ptr(stats), _stream())
+    if code == EUNSUPPORTED:
+        raise Unsupported(lib().allset_last_error().decode())
+    _check(code, 'allset_pma_fwd_strided')
+    return out, stats
 
 
 def segreduce_bwd_w(x: torch.Tensor, grad_out: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int,

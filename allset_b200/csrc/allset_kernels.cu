@@ -407,7 +407,7 @@ __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
 constexpr int kStreamBarCount = ALLSET_STREAM_COPY == 0 ? 32 : 1;
 template <int ROWB, bool HINT>
 __device__ __forceinline__ void stage_rows(uint32_t dst, const unsigned char* __restrict__ src, int my_row_id, int n,
-                                           uint32_t bar, int lane, uint64_t policy) {
+                                           uint32_t bar, int lane, uint64_t policy, size_t pitch = ROWB) {
 #if ALLSET_STREAM_COPY == 0
   constexpr int CPR = ROWB / 16;                      // 16-byte chunks per row
   const int total = n * CPR;
@@ -416,15 +416,15 @@ __device__ __forceinline__ void stage_rows(uint32_t dst, const unsigned char* __
     const int q = q0 + lane;
     const int row = q / CPR, ch = q % CPR;
     const int idx = __shfl_sync(0xffffffffu, my_row_id, row & 31);
-    if (q < total) cp_async16<HINT>(dst + (uint32_t)q * 16u, src + (size_t)idx * ROWB + (size_t)ch * 16, policy);
+    if (q < total) cp_async16<HINT>(dst + (uint32_t)q * 16u, src + (size_t)idx * pitch + (size_t)ch * 16, policy);
   }
 #else
-  if (lane < n) bulk_g2s(dst + (uint32_t)lane * ROWB, src + (size_t)my_row_id * ROWB, ROWB, bar);
+  if (lane < n) bulk_g2s(dst + (uint32_t)lane * ROWB, src + (size_t)my_row_id * pitch, ROWB, bar);
 #endif
 }
 // same for a small per-row side record of `sb` bytes (sb % 16 == 0)
 __device__ __forceinline__ void stage_side(uint32_t dst, const unsigned char* __restrict__ src, int my_row_id, int n,
-                                           uint32_t sb, uint32_t bar, int lane, uint64_t policy) {
+                                           uint32_t sb, uint32_t bar, int lane, uint64_t policy, size_t pitch) {
 #if ALLSET_STREAM_COPY == 0
   const int cpr = (int)(sb / 16u);
   const int total = n * cpr;
@@ -432,10 +432,10 @@ __device__ __forceinline__ void stage_side(uint32_t dst, const unsigned char* __
     const int q = q0 + lane;
     const int row = q / cpr, ch = q % cpr;
     const int idx = __shfl_sync(0xffffffffu, my_row_id, row & 31);
-    if (q < total) cp_async16<true>(dst + (uint32_t)q * 16u, src + (size_t)idx * sb + (size_t)ch * 16, policy);
+    if (q < total) cp_async16<true>(dst + (uint32_t)q * 16u, src + (size_t)idx * pitch + (size_t)ch * 16, policy);
   }
 #else
-  if (lane < n) bulk_g2s(dst + (uint32_t)lane * sb, src + (size_t)my_row_id * sb, sb, bar);
+  if (lane < n) bulk_g2s(dst + (uint32_t)lane * sb, src + (size_t)my_row_id * pitch, sb, bar);
 #endif
 }
 
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1)
 pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, const float* __restrict__ seed,
                   const int* __restrict__ rowptr, const int* __restrict__ col, long long n_tgt, int H, int C,
                   float slope, int seg_per_warp, int stages, T* __restrict__ out, float* __restrict__ stats,
-                  PeerOuts peers) {
+                  PeerOuts peers, long long v_pitch, long long s_pitch) {
   using LR = LaneRow<T, LB>;
   constexpr int ES = LR::ES, NA = LR::NA, CH = LR::CH, CB = LR::CB, EPC = LR::EPC;
   constexpr int ROWB = LB * 32;
@@ -839,8 +839,10 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)n * (ROWB + SB));
     __syncwarp();
 #endif
-    stage_rows<ROWB, true>(ring + (uint32_t)st * (RPS * ROWB), reinterpret_cast<const unsigned char*>(v), pf_idx, n, bar, lane, pol_rows);
-    stage_side(sring + (uint32_t)st * RPS * SB, reinterpret_cast<const unsigned char*>(score), pf_idx, n, SB, bar, lane, pol_side);
+    stage_rows<ROWB, true>(ring + (uint32_t)st * (RPS * ROWB), reinterpret_cast<const unsigned char*>(v), pf_idx, n, bar, lane, pol_rows,
+                           (size_t)v_pitch);
+    stage_side(sring + (uint32_t)st * RPS * SB, reinterpret_cast<const unsigned char*>(score), pf_idx, n, SB, bar, lane,
+               s_pitch == v_pitch ? pol_rows : pol_side, (size_t)s_pitch);
 #if ALLSET_STREAM_COPY == 0
     cp_async_arrive(bar);
 #endif
@@ -1826,7 +1828,7 @@ int make_peers(void* out, void* const* peer_outs, int n_peers, PeerOuts* po) {
 template <typename T, int LB>
 int launch_pma_stream(const StreamPlan& p, const T* v, const float* score, const float* seed, const int* rowptr,
                       const int* col, long long n_tgt, int H, int C, float slope, T* out, float* stats,
-                      const PeerOuts& peers, cudaStream_t st) {
+                      const PeerOuts& peers, cudaStream_t st, long long v_pitch, long long s_pitch) {
   static size_t configured[2] = {0, 0};
   const int b = peers.n > 0 ? 1 : 0;
   auto kern = b ? pma_stream_kernel<T, LB, true> : pma_stream_kernel<T, LB, false>;
@@ -1836,21 +1838,23 @@ int launch_pma_stream(const StreamPlan& p, const T* v, const float* score, const
     configured[b] = p.smem;
   }
   kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(v, score, seed, rowptr, col, n_tgt, H, C, slope, p.seg_per_warp,
-                                                    p.stages, out, stats, peers);
+                                                    p.stages, out, stats, peers,
+                                                    v_pitch > 0 ? v_pitch : (long long)LB * 32,
+                                                    s_pitch > 0 ? s_pitch : (long long)H * 4);
   return ALLSET_OK;
 }
 
 template <typename T>
 int pma_stream_typed(const StreamPlan& p, const void* v, const float* score, const float* seed, const int* rowptr,
                      const int* col, long long n_tgt, int H, int C, float slope, void* out, float* stats,
-                     const PeerOuts& peers, cudaStream_t st) {
+                     const PeerOuts& peers, cudaStream_t st, long long v_pitch, long long s_pitch) {
   const T* vi = static_cast<const T*>(v);
   T* oi = static_cast<T*>(out);
   switch (p.lane_bytes) {
-    case 4: return launch_pma_stream<T, 4>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st);
-    case 8: return launch_pma_stream<T, 8>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st);
-    case 16: return launch_pma_stream<T, 16>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st);
-    default: return launch_pma_stream<T, 32>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st);
+    case 4: return launch_pma_stream<T, 4>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st, v_pitch, s_pitch);
+    case 8: return launch_pma_stream<T, 8>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st, v_pitch, s_pitch);
+    case 16: return launch_pma_stream<T, 16>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st, v_pitch, s_pitch);
+    default: return launch_pma_stream<T, 32>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st, v_pitch, s_pitch);
   }
 }
 
@@ -2083,7 +2087,7 @@ int allset_bias_act_norm_bwd(const float* dy, const float* x, const float* bias,
 int allset_mlp2_fwd(const void* x, int x_dtype, const float* ln0_gamma, const float* ln0_beta, float ln0_eps,
                     const float* w1, const float* b1, const float* ln1_gamma, const float* ln1_beta, float ln1_eps,
                     const float* w2, const float* b2, int relu_out, int64_t rows, int32_t d, void* out, int out_dtype,
-                    int32_t* status, void* stream) {
+                    int64_t out_pitch, int32_t* status, void* stream) {
   if (rows < 0 || d <= 0) return fail(ALLSET_EINVAL, "mlp2_fwd: bad size");
   if (bad_dtype(x_dtype) || bad_dtype(out_dtype)) return fail(ALLSET_EINVAL, "mlp2_fwd: dtype must be 0 (f32) or 1 (bf16)");
   if (d != 64 && d != 128) return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: width %d not supported (64 or 128)", (int)d);
@@ -2095,8 +2099,12 @@ int allset_mlp2_fwd(const void* x, int x_dtype, const float* ln0_gamma, const fl
     return fail(ALLSET_EINVAL, "mlp2_fwd: LayerNorm beta without gamma");
   const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)ln0_gamma | (uintptr_t)ln1_gamma;
   if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "mlp2_fwd: x, out, w1, w2 and the LayerNorm gammas must be 16-byte aligned");
+  const int64_t dense_pitch = (int64_t)d * elem_bytes(out_dtype);
+  if (out_pitch == 0) out_pitch = dense_pitch;
+  if (out_pitch < dense_pitch || out_pitch % 16 != 0)
+    return fail(ALLSET_EINVAL, "mlp2_fwd: out_pitch must be 0 or a multiple of 16 >= the row size");
   mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, ln1_gamma, ln1_beta, single ? w1 : w2, b2, ln0_eps, ln1_eps, relu_out,
-                 single, (long long)rows, status, 0, 0, nullptr, nullptr, 0.f};
+                 single, (long long)rows, status, 0, 0, nullptr, nullptr, 0.f, (long long)out_pitch};
   return mlp2_dispatch<false>(p, x_dtype, out_dtype, d, static_cast<cudaStream_t>(stream));
 }
 
@@ -2113,7 +2121,8 @@ int allset_pma_tail_fwd(const void* x, int x_dtype, const float* ln0_gamma, cons
   const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)ln0_gamma;
   if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "pma_tail_fwd: x, out, w1, w2, ln0_gamma must be 16-byte aligned");
   mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, nullptr, nullptr, w2, b2, ln0_eps, 1e-5f, 1,
-                 0, (long long)rows, status, 1, relu_final, ln1_gamma, ln1_beta, ln1_eps};
+                 0, (long long)rows, status, 1, relu_final, ln1_gamma, ln1_beta, ln1_eps,
+                 (long long)d * elem_bytes(out_dtype)};
   return mlp2_dispatch<true>(p, x_dtype, out_dtype, d, static_cast<cudaStream_t>(stream));
 }
 
@@ -2142,8 +2151,13 @@ int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32
 static int pma_fwd_impl(const void* v, const float* score, const float* seed, int dtype, int32_t H, int32_t C,
                         float slope, const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
                         const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out, float* stats,
-                        void* const* peer_outs, int32_t n_peers, void* stream) {
+                        void* const* peer_outs, int32_t n_peers, void* stream, int64_t v_pitch = 0,
+                        int64_t s_pitch = 0) {
   if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "pma_fwd: unknown dtype %d", dtype);
+  const bool strided = v_pitch != 0 || s_pitch != 0;       // rows / scores with a byte pitch: stream kernel only
+  if (strided && (v_pitch < (int64_t)H * C * elem_bytes(dtype) || s_pitch < (int64_t)H * 4 || v_pitch % 16 != 0 ||
+                  s_pitch % 16 != 0))
+    return fail(ALLSET_EINVAL, "pma_fwd_strided: pitches must cover a row / a score record and be multiples of 16");
   if (H <= 0 || C <= 0 || n_tgt < 0 || n_long < 0) return fail(ALLSET_EINVAL, "pma_fwd: bad size");
   if (!(slope > 0.f)) return fail(ALLSET_EINVAL, "pma_fwd: negative_slope must be > 0");
   if (n_tgt >= INT32_MAX) return fail(ALLSET_ERANGE, "pma_fwd: rows do not fit int32");
@@ -2168,14 +2182,17 @@ static int pma_fwd_impl(const void* v, const float* score, const float* seed, in
     if (int rc = make_peers(out, peer_outs, n_peers, &peers)) return rc;
     if (sp.ok) {
       const int rc = dtype == ALLSET_F32
-          ? pma_stream_typed<float>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, peers, st)
-          : pma_stream_typed<__nv_bfloat16>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, peers, st);
+          ? pma_stream_typed<float>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, peers, st, v_pitch, s_pitch)
+          : pma_stream_typed<__nv_bfloat16>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, peers, st, v_pitch, s_pitch);
       if (rc != ALLSET_OK) return rc;
       return check_launch("pma_fwd(stream)");
     }
     if (n_peers > 0)
       return fail(ALLSET_EUNSUPPORTED, "pma_fwd_bcast: shape not eligible for the fused-exchange stream kernel; use "
                                        "pma_fwd + an all-gather");
+    if (strided)
+      return fail(ALLSET_EUNSUPPORTED, "pma_fwd_strided: shape not eligible for the stream kernel (see "
+                                       "allset_stream_eligible); use dense arrays with allset_pma_fwd");
   }
   Shape sh = plan(d, elem_bytes(dtype), v, out);
   if (sh.vector && C % (16 / elem_bytes(dtype)) != 0) {   // a 16-byte chunk would straddle two heads
@@ -2204,6 +2221,14 @@ int allset_pma_fwd(const void* v, const float* score, const float* seed, int dty
                    void* stream) {
   return pma_fwd_impl(v, score, seed, dtype, H, C, slope, rowptr, col, n_tgt, long_ids, n_long, long_threshold, out,
                       stats, nullptr, 0, stream);
+}
+
+int allset_pma_fwd_strided(const void* v, int64_t v_pitch, const float* score, int64_t s_pitch, const float* seed,
+                           int dtype, int32_t H, int32_t C, float slope, const int32_t* rowptr, const int32_t* col,
+                           int64_t n_tgt, void* out, float* stats, void* stream) {
+  if (v_pitch <= 0 || s_pitch <= 0) return fail(ALLSET_EINVAL, "pma_fwd_strided: pitches must be positive");
+  return pma_fwd_impl(v, score, seed, dtype, H, C, slope, rowptr, col, n_tgt, nullptr, 0, 0, out, stats, nullptr, 0, stream,
+                      v_pitch, s_pitch);
 }
 
 int allset_pma_fwd_bcast(const void* v, const float* score, const float* seed, int dtype, int32_t H, int32_t C,

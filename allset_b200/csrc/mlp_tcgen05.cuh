@@ -49,6 +49,7 @@ struct Params {
   const float* lnf_g;
   const float* lnf_b;
   float epsf;
+  long long out_pitch;   // bytes between output rows (>= D * sizeof(TOut), multiple of 16); lets lin_V write packed records
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -716,7 +717,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
           const uint4 qv = ld_shared16(sH + (uint32_t)rr * PASS_BYTES + (uint32_t)((c16 ^ (rr & 7)) << 4));
           const long long gr = row0 + rr;
           if (gr < p.rows)
-            *reinterpret_cast<uint4*>(ob + (size_t)gr * OUT_ROW_BYTES + pass * PASS_BYTES + c16 * 16) = qv;
+            *reinterpret_cast<uint4*>(ob + (size_t)gr * (size_t)p.out_pitch + pass * PASS_BYTES + c16 * 16) = qv;
         }
         epi_bar_sync(g);                         // staging buffer (= hidden tile) free again
       }

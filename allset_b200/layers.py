@@ -194,18 +194,34 @@ class PMA(nn.Module):
         b_eff = (self.lin_K.bias.view(H, C) * seed).sum(dim=1)                             # [H]
         score = F.linear(x, w_eff, b_eff)                                                  # [n_src, H]
         fused = self.rFF._fused_ok(x) and ops.fused_dense_ok(x, self.heads * self.hidden)
+        want_alpha = isinstance(return_attention_weights, bool)
+        out = None
         if self._tc_v_ok(x):
             # bf16 mode: V = lin_V(x) as ONE tcgen05 kernel that writes the bf16 rows the aggregation gathers
-            v = _lib.mlp2_fwd(x.contiguous(), self.lin_V.weight, self.lin_V.bias, None, None, None, None, False,
-                              torch.bfloat16)
+            xc = x.contiguous()
+            if not want_alpha and self._packed_ok(xc, inc):
+                # scores too large for L2: one packed [values | scores] record per source row, so that a gather touches
+                # one contiguous record per incidence instead of a row plus a 32-byte score in another 128-byte line
+                _, v, s = _lib.packed_pma_records(xc.shape[0], H * C, H, torch.bfloat16, xc.device)
+                _lib.mlp2_fwd(xc, self.lin_V.weight, self.lin_V.bias, None, None, None, None, False, out=v)
+                s.copy_(score)
+                t = inc.by_tgt
+                try:
+                    out, _ = _lib.pma_fwd_strided(v, s, self.att_r.detach().float().reshape(-1).contiguous(), H, C,
+                                                  self.negative_slope, t.rowptr, t.col, t.n_tgt)
+                    alpha = None
+                except _lib.Unsupported:
+                    v = v.contiguous()
+            else:
+                v = _lib.mlp2_fwd(xc, self.lin_V.weight, self.lin_V.bias, None, None, None, None, False, torch.bfloat16)
         else:
             if fused:
                 x_V = ops.bias_act_norm(F.linear(x, self.lin_V.weight), self.lin_V.bias)
             else:
                 x_V = self.lin_V(x)
             v = x_V if self.agg_dtype is None else x_V.to(self.agg_dtype)
-        want_alpha = isinstance(return_attention_weights, bool)
-        out, alpha = ops.pma_aggregate(v, score, self.att_r, inc, H, self.negative_slope, return_alpha=want_alpha)
+        if out is None:
+            out, alpha = ops.pma_aggregate(v, score, self.att_r, inc, H, self.negative_slope, return_alpha=want_alpha)
         applied_relu = False
         if self.rFF._tc_ok(out):
             # bf16 mode: ln0 -> rFF -> ln1(residual + relu(.)) [-> the caller's ReLU] as ONE tcgen05 kernel reading the
@@ -229,6 +245,17 @@ class PMA(nn.Module):
         if want_alpha:
             return out, (edge_index, alpha)
         return out
+
+    PACKED_MIN_SCORE_BYTES = 96 << 20        # below this the fp32 scores stay resident in the 126 MB L2: keep them apart
+
+    def _packed_ok(self, x, inc) -> bool:
+        t = inc.by_tgt
+        H, d = self.heads, self.heads * self.hidden
+        if x.shape[0] * H * 4 < self.PACKED_MIN_SCORE_BYTES or H % 4 != 0:
+            return False
+        if t.long_ids is not None and t.long_ids.numel() > 0:
+            return False
+        return bool(_lib.lib().allset_stream_eligible(_lib.BF16, d, t.n_tgt))
 
     def _tc_v_ok(self, x) -> bool:
         """lin_V on the tensor cores: bf16 mode, eval, square Linear of a width the tcgen05 kernel has."""

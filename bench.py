@@ -448,6 +448,29 @@ def run_b200(a):
         pma = {'value': Me / (p_ms / a.steps * 1e-3), 'unit': UNIT, 'heads': H, 'ms_per_step': p_ms / a.steps,
                'v2e_ms': pph[0], 'e2v_ms': pph[2], 'exchange_x_e_ms': pph[1], 'exchange_x_v_ms': pph[3],
                'v2e_gbs': b_ve / (pph[0] * 1e-3) / 1e9, 'e2v_gbs': b_ev / (pph[2] * 1e-3) / 1e9}
+        if world == 1 and H % 4 == 0:
+            # V->E again with ONE packed [values | scores] record per vertex (what PMA.forward builds in bf16 mode when
+            # the scores do not fit L2): same kernel, contiguous records
+            from allset_b200 import _lib
+            try:
+                _, pv, ps = _lib.packed_pma_records(Nv, d, H, dtype, dev)
+                pv.copy_(plain(x_v))
+                ps.copy_(score_v)
+                e = sh.e_csr
+
+                def packed_step(marks):
+                    if marks: marks[0].record()
+                    _lib.pma_fwd_strided(pv, ps, seed, H, d // H, 0.2, e.rowptr, e.col, e.n_tgt)
+                    if marks: marks[1].record()
+
+                pk_ms, _ = timed_steps(packed_step, 1, max(5, a.steps // 5), a.warmup)
+                pk_ms /= max(5, a.steps // 5)
+                pma['v2e_packed_ms'] = pk_ms
+                pma['v2e_packed_gbs'] = b_ve / (pk_ms * 1e-3) / 1e9
+                del pv, ps
+            except _lib.Unsupported as exc:
+                pma['v2e_packed_ms'] = None
+                pma['v2e_packed_note'] = str(exc)
         del score_v, score_e
 
     # ---- the dense glue of the same layer on the tensor cores (row (f)-1): f_enc / f_dec as ONE tcgen05 kernel ------

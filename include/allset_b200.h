@@ -131,6 +131,8 @@ int allset_bias_act_norm(const float* x, const float* bias, int relu, const floa
  * Accuracy is that of bf16 operands (the 1e-2 bar of north_star's bf16 mode), not fp32: callers that need 1e-4
  * keep the cuBLAS SGEMM + allset_bias_act_norm chain.  status: device int32 or NULL, set to 1 if an internal
  * mbarrier wait timed out (diagnostic; never in a correct run).  ALLSET_EUNSUPPORTED for other widths.
+ * out_pitch: bytes between output rows, 0 = dense (lets PMA.lin_V write the value part of packed [values | scores]
+ * records for allset_pma_fwd_strided).
  * w2 == NULL selects ONE Linear: out = [relu]( LN0?(x) W1^T + b1 ) (b2 / ln1 must be NULL) -- nn.Linear as used by
  * PMA.lin_V (src/layers.py:129) and MLP with num_layers == 1. */
 int allset_mlp2_fwd(const void* x, int x_dtype,
@@ -138,7 +140,8 @@ int allset_mlp2_fwd(const void* x, int x_dtype,
                     const float* w1, const float* b1,
                     const float* ln1_gamma, const float* ln1_beta, float ln1_eps,
                     const float* w2, const float* b2, int relu_out,
-                    int64_t rows, int32_t d, void* out, int out_dtype, int32_t* status, void* stream);
+                    int64_t rows, int32_t d, void* out, int out_dtype, int64_t out_pitch,
+                    int32_t* status, void* stream);
 
 /* PMA's dense tail as ONE tcgen05 kernel (bf16 operands, fp32 accumulate and residual), equal widths d in {64, 128}:
  *     y   = LN0(x)                                   (PMA.ln0 on `out + att_r`, src/layers.py:155)
@@ -186,6 +189,17 @@ int allset_pma_fwd(const void* v, const float* score, const float* seed, int dty
                    const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
                    const int32_t* long_ids, int32_t n_long, int32_t long_threshold,
                    void* out, float* stats, void* stream);
+
+/* allset_pma_fwd with STRIDED sources: value row i at (char*)v + i * v_pitch, its H fp32 scores at (char*)score +
+ * i * s_pitch (both pitches in bytes, multiples of 16).  With v_pitch == s_pitch and score == v + H*C*sizeof(T) the
+ * source is ONE packed record per row [values | scores]: a gather then touches one contiguous 16-byte-granular record
+ * per incidence instead of a row plus a 32-byte score in another 128-byte line (the V->E direction of a large graph is
+ * DRAM-bound on exactly that).  Stream kernel only: ALLSET_EUNSUPPORTED when allset_stream_eligible() says no or the
+ * graph has long segments; out is dense [n_tgt, H*C]. */
+int allset_pma_fwd_strided(const void* v, int64_t v_pitch, const float* score, int64_t s_pitch, const float* seed,
+                           int dtype, int32_t H, int32_t C, float slope,
+                           const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
+                           void* out, float* stats, void* stream);
 
 /* allset_pma_fwd with the fused exchange of allset_segreduce_fwd_bcast (same contract for out / peer_outs). */
 int allset_pma_fwd_bcast(const void* v, const float* score, const float* seed, int dtype,

@@ -894,3 +894,53 @@ def test_pma_tail_tcgen05_vs_torch(d, in_dtype, out_dtype):
         assert int(status.item()) == 0 and out.dtype == out_dtype
         err = (out.float().cpu() - ref).abs().max().item()
         assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), (rows, err)
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+def test_pma_strided_packed_records_equal_dense(dtype):
+    """allset_pma_fwd_strided over packed [values | scores] records == allset_pma_fwd over separate arrays, bit for bit
+    (same kernel, same summation order), and an ineligible (small) graph is refused, not silently mis-handled."""
+    from allset_b200 import _lib, synthetic
+    n, m_e, d, H = 200000, 70000, 128, 8
+    ei = synthetic.poisson_hypergraph(n, m_e, 8, seed=21, device=dev())
+    inc = ab().Incidence.from_coo(ei[0], ei[1] - n, n_src=n)
+    t = inc.by_tgt
+    g = torch.Generator(device=dev()).manual_seed(4)
+    v = torch.randn(n, d, device=dev(), generator=g).to(dtype)
+    score = torch.randn(n, H, device=dev(), generator=g)
+    seed = torch.randn(d, device=dev(), generator=g)
+    dense, dstats = _lib.pma_fwd(v, score, seed, H, d // H, 0.2, t.rowptr, t.col, t.n_tgt, want_stats=True)
+    buf, pv, ps = _lib.packed_pma_records(n, d, H, dtype, dev())
+    assert buf.shape[1] == d * v.element_size() + H * 4 and pv.stride(1) == 1 and ps.stride(1) == 1
+    pv.copy_(v)
+    ps.copy_(score)
+    packed, pstats = _lib.pma_fwd_strided(pv, ps, seed, H, d // H, 0.2, t.rowptr, t.col, t.n_tgt, want_stats=True)
+    assert torch.equal(packed, dense) and torch.equal(pstats, dstats)
+    ref, _ = O.aggregate_pma(v.float().cpu().view(n, H, -1)[:, :, :], score.cpu(), seed.cpu().view(1, H, -1),
+                             ei[0].cpu(), (ei[1] - n).cpu())
+    tol = BF16 if dtype == torch.bfloat16 else FP32
+    torch.testing.assert_close(packed.float().cpu(), ref.reshape(-1, d), **tol)
+    small = ab().Incidence.from_coo(ei[0][:5000], ei[1][:5000] - n, n_src=n).by_tgt
+    with pytest.raises(_lib.Unsupported):
+        _lib.pma_fwd_strided(pv, ps, seed, H, d // H, 0.2, small.rowptr, small.col, small.n_tgt)
+
+
+def test_pma_module_packed_path_matches_unpacked(monkeypatch):
+    from allset_b200 import _lib, synthetic, layers
+    n, m_e, d, H = 200000, 70000, 128, 8
+    ei = synthetic.poisson_hypergraph(n, m_e, 8, seed=22, device=dev())
+    inc = ab().Incidence.from_coo(ei[0], ei[1] - n, n_src=n)
+    torch.manual_seed(1)
+    conv = ab().HalfNLHconv(d, d, d, 2, 0.0, 'ln', True, heads=H, attention=True).to(dev()).eval()
+    conv.set_agg_dtype(torch.bfloat16)
+    x = torch.randn(n, d, device=dev())
+    used = []
+    real = _lib.pma_fwd_strided
+    monkeypatch.setattr(_lib, 'pma_fwd_strided', lambda *a, **k: (used.append(1), real(*a, **k))[1])
+    with torch.no_grad():
+        plain_out = conv(x, inc, None, 'add')
+        assert not used                               # 6.4 MB of scores: stays on separate arrays
+        monkeypatch.setattr(layers.PMA, 'PACKED_MIN_SCORE_BYTES', 0)
+        packed_out = conv(x, inc, None, 'add')
+    assert used == [1]
+    assert torch.equal(packed_out, plain_out)
