@@ -246,12 +246,16 @@ class PMA(nn.Module):
             return out, (edge_index, alpha)
         return out
 
-    PACKED_MIN_SCORE_BYTES = 96 << 20        # below this the fp32 scores stay resident in the 126 MB L2: keep them apart
+    # Packed [values | scores] records for the gather (allset_pma_fwd_strided) are OFF by default: measured on the
+    # 10 M-vertex graph they are slower (4.03 vs 3.85 ms V->E) -- HBM fills L2 in 64-byte units, so a 288-byte record
+    # costs the same 320 bytes as a 256-byte row plus a 32-byte score elsewhere, and it straddles three 128-byte lines.
+    # Set to a byte count (e.g. 96 << 20 = "scores do not fit L2") to enable.
+    PACKED_MIN_SCORE_BYTES = None
 
     def _packed_ok(self, x, inc) -> bool:
         t = inc.by_tgt
         H, d = self.heads, self.heads * self.hidden
-        if x.shape[0] * H * 4 < self.PACKED_MIN_SCORE_BYTES or H % 4 != 0:
+        if self.PACKED_MIN_SCORE_BYTES is None or x.shape[0] * H * 4 < self.PACKED_MIN_SCORE_BYTES or H % 4 != 0:
             return False
         if t.long_ids is not None and t.long_ids.numel() > 0:
             return False

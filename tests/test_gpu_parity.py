@@ -920,7 +920,8 @@ def test_pma_strided_packed_records_equal_dense(dtype):
                              ei[0].cpu(), (ei[1] - n).cpu())
     tol = BF16 if dtype == torch.bfloat16 else FP32
     torch.testing.assert_close(packed.float().cpu(), ref.reshape(-1, d), **tol)
-    small = ab().Incidence.from_coo(ei[0][:5000], ei[1][:5000] - n, n_src=n).by_tgt
+    keep = (ei[1] - n) < 3000                        # 3000 hyperedges: below one wave of the stream kernel
+    small = ab().Incidence.from_coo(ei[0][keep], ei[1][keep] - n, n_src=n).by_tgt
     with pytest.raises(_lib.Unsupported):
         _lib.pma_fwd_strided(pv, ps, seed, H, d // H, 0.2, small.rowptr, small.col, small.n_tgt)
 
@@ -939,7 +940,7 @@ def test_pma_module_packed_path_matches_unpacked(monkeypatch):
     monkeypatch.setattr(_lib, 'pma_fwd_strided', lambda *a, **k: (used.append(1), real(*a, **k))[1])
     with torch.no_grad():
         plain_out = conv(x, inc, None, 'add')
-        assert not used                               # 6.4 MB of scores: stays on separate arrays
+        assert not used                               # off by default (measured slower)
         monkeypatch.setattr(layers.PMA, 'PACKED_MIN_SCORE_BYTES', 0)
         packed_out = conv(x, inc, None, 'add')
     assert used == [1]
