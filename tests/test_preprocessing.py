@@ -90,3 +90,52 @@ def test_large_graph_on_gpu_feeds_setgnn_layout():
     covered[ei[0][single]] = True
     assert bool(covered.all())
     assert norm.dtype == torch.int64 and bool((norm == 1).all())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# expand_edge_index (--exclude_self): fixtures from the reference's own function (oracle/make_golden_expand.py)
+# ---------------------------------------------------------------------------------------------------------
+def _expand_cases():
+    return load_golden('expand_edge_index.pt')
+
+
+@pytest.mark.parametrize('i', range(5))
+def test_expand_edge_index_matches_reference(i):
+    c = _expand_cases()[i]
+    mine = P.expand_edge_index(c['edge_index'], c['n_x'], c['n_he'], edge_th=c['edge_th'])
+    ref = c['expanded']
+    # same node row element for element, same (node, new hyperedge id) pairs; the order of one node's hyperedges is left
+    # to an unstable argsort by the reference (preprocessing.py:141)
+    assert mine.dtype == ref.dtype and same_incidences(mine, ref), c['name']
+
+
+def test_expand_edge_index_counts_and_semantics():
+    c = _expand_cases()[1]
+    ei, n = c['edge_index'], c['n_x']
+    out = P.expand_edge_index(ei, n, c['n_he'])
+    sizes = torch.bincount(ei[1] - n)
+    sizes = sizes[sizes > 0]
+    assert out.shape[1] == int((sizes * (sizes - 1)).clamp(min=0).sum() + (sizes == 1).sum())   # s(s-1), singletons kept
+    assert int(out[1].min()) == n and int(out[1].max()) == n + int(sizes.sum()) - 1             # one new id per member
+    new_sizes = torch.bincount(out[1] - n)
+    assert bool(((new_sizes >= 1)).all())
+    # through preprocess(): ExtractV2E -> Add_Self_Loops -> expand
+    g = load_golden('preprocessing.pt')[2]
+    ei2, norm2, tot2 = P.preprocess(g['raw'], g['n_x'], g['num_hyperedges'], exclude_self=True)
+    assert ei2.shape[1] == norm2.numel() and tot2 == int(ei2[1].max()) - g['n_x'] + 1
+    assert bool((ei2[0, 1:] >= ei2[0, :-1]).all())
+
+
+@pytest.mark.gpu
+def test_expand_edge_index_on_gpu_large():
+    from allset_b200 import synthetic
+    dev = torch.device('cuda:0')
+    c = _expand_cases()[0]
+    mine = P.expand_edge_index(c['edge_index'].to(dev), c['n_x'], c['n_he'])
+    assert mine.is_cuda and same_incidences(mine.cpu(), c['expanded'])
+    n, m = 300_000, 60_000
+    v2e = synthetic.poisson_hypergraph(n, m, 10, seed=5, device=dev)
+    out = P.expand_edge_index(v2e, n, m)
+    sizes = torch.bincount(v2e[1] - n, minlength=m)
+    assert out.shape[1] == int((sizes * (sizes - 1)).sum() + (sizes == 1).sum())
+    assert bool((out[0, 1:] >= out[0, :-1]).all())
