@@ -116,7 +116,11 @@ class ReplicatedRows(object):
         # sends each row ONCE instead of world-1 times (a multimem.st is an ordinary st.global on that address).
         self.multicast_ptr = 0
         if multicast is None:
-            multicast = os.environ.get('ALLSET_MULTICAST', '1') != '0'
+            # a multicast store also comes back into the sender's own replica: 1x egress instead of (world-1)x, but
+            # world/(world-1) of the ingress.  Measured: slower than per-peer stores at world 2 (2.71 vs 2.64 ms per step),
+            # faster at 8 (1.13 vs 1.17).  ALLSET_MULTICAST=1 / 0 forces it on / off.
+            env = os.environ.get('ALLSET_MULTICAST')
+            multicast = (env == '1') if env in ('0', '1') else self.world >= 4
         if multicast:
             try:
                 self.multicast_ptr = int(getattr(self.handle, 'multicast_ptr', 0) or 0)
