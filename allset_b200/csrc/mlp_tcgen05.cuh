@@ -705,21 +705,25 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
             }
           }
         }
-        tc_fence_before();                       // (last pass: the accumulator is drained before the barrier below)
-        epi_bar_sync(g);                         // staged
-        if (p.single && pass == NPASS - 1) {     // acc1[g] drained by all 128 threads: GEMM 1 of the next tile may go
+        tc_fence_before();                       // (last pass: the accumulator is drained before the barriers below)
+        // A warp stages and stores only ITS OWN 32 rows (its TMEM lane quadrant), so __syncwarp orders the staging
+        // writes before the coalesced reads; group barriers remain only where other warps' data is involved.
+        if (p.single && pass == NPASS - 1) {     // acc1[g] must be drained by all 128 threads before GEMM 1 of the next tile
+          epi_bar_sync(g);
           if (issuer && has_next) gemm1(k + 1);
-          __syncwarp();
         }
+        __syncwarp();
+        const int wrow = (warp & 3) * 32;
 #pragma unroll
-        for (int idx = r; idx < kTileM * CHUNKS_PER_ROW; idx += 128) {
-          const int rr = idx / CHUNKS_PER_ROW, c16 = idx % CHUNKS_PER_ROW;
+        for (int idx = lane; idx < 32 * CHUNKS_PER_ROW; idx += 32) {
+          const int rr = wrow + idx / CHUNKS_PER_ROW, c16 = idx % CHUNKS_PER_ROW;
           const uint4 qv = ld_shared16(sH + (uint32_t)rr * PASS_BYTES + (uint32_t)((c16 ^ (rr & 7)) << 4));
           const long long gr = row0 + rr;
           if (gr < p.rows)
             *reinterpret_cast<uint4*>(ob + (size_t)gr * (size_t)p.out_pitch + pass * PASS_BYTES + c16 * 16) = qv;
         }
-        epi_bar_sync(g);                         // staging buffer (= hidden tile) free again
+        if (pass == NPASS - 1) epi_bar_sync(g);  // the staging buffer is the hidden tile: every warp done before epilogue 1
+        else __syncwarp();                       // of the next tile overwrites it; between passes only this warp's rows
       }
     }
   }
