@@ -135,13 +135,21 @@ __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity,
   long long t0 = 0;
   for (uint32_t spins = 0;; ++spins) {
     uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
+    if (SLEEP_NS > 0) {
+      // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the hint expires
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity), "r"((uint32_t)SLEEP_NS)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
     if (ok) return;
-    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     if ((spins & 1023u) == 1023u) {
       if (t0 == 0) t0 = clock64();
       else if (clock64() - t0 > 4000000000LL) {
@@ -509,7 +517,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       if (next < n_tiles) P::load(bufA, xb, next * kTileM, p.rows, pw, 0, sub, cl);
       P::compute(bufB, pkB, stB, has_ln0, p.eps0);
       if (next < n_tiles) P::load(bufB, xb, next * kTileM, p.rows, pw, 1, sub, cl);
-      if (it >= 2) mbar_wait_bounded<200>(bar_a_empty + 8 * st, ((it >> 1) - 1) & 1u, p.status);
+      if (it >= 2) mbar_wait_bounded<2000>(bar_a_empty + 8 * st, ((it >> 1) - 1) & 1u, p.status);
       P::store(pkA, stA, stat, sAst, pw, 0, sub, cl);     // (this sStat slot was read at the top of tile k-2's epilogue)
       P::store(pkB, stB, stat, sAst, pw, 1, sub, cl);
       proxy_fence_async();
