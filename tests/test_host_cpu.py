@@ -147,3 +147,44 @@ def test_synthetic_generators_follow_reference_layout():
     x = torch.randn(5000, 4)
     out = O.aggregate_sum_mean(x, ei[0], ei[1] - 5000, None, 'sum')
     assert out.shape == (1000, 4)
+
+
+def test_packed_pma_record_views_layout_cpu():
+    """[values | scores] records: both views alias one buffer with the record size as row pitch (no CUDA needed)."""
+    from allset_b200 import _lib
+    buf, v, s = _lib.packed_pma_records(10, 128, 8, torch.bfloat16, 'cpu')
+    assert buf.shape == (10, 128 * 2 + 8 * 4) and buf.dtype == torch.uint8
+    assert v.shape == (10, 128) and v.dtype == torch.bfloat16 and v.stride() == (144, 1)
+    assert s.shape == (10, 8) and s.dtype == torch.float32 and s.stride() == (72, 1)
+    v.fill_(1.0)
+    s.fill_(2.0)
+    assert v.untyped_storage().data_ptr() == buf.untyped_storage().data_ptr() == s.untyped_storage().data_ptr()
+    assert s.data_ptr() - v.data_ptr() == 256 and float(v.float().sum()) == 1280.0 and float(s.sum()) == 160.0
+    buf32, v32, s32 = _lib.packed_pma_records(3, 64, 4, torch.float32, 'cpu')
+    assert buf32.shape == (3, 64 * 4 + 16) and v32.stride() == (68, 1) and s32.stride() == (68, 1)
+
+
+def test_tensor_core_paths_are_cuda_eval_bf16_only():
+    """The tcgen05 paths need CUDA rows, no_grad, bf16 mode and a square 64/128-wide two-layer MLP; anything else takes
+    the fp32 path (or raises for non-CUDA inputs further down) -- never a silent CPU computation of the product path."""
+    import allset_b200
+    m = allset_b200.MLP(128, 128, 128, 2, dropout=0.0, Normalization='ln', InputNorm=True)
+    x = torch.randn(9000, 128)
+    with torch.no_grad():
+        assert not m._tc_ok(x)                       # tc_dtype unset
+        m.tc_dtype = torch.bfloat16
+        assert not m._tc_ok(x)                       # CPU rows
+    conv = allset_b200.HalfNLHconv(128, 128, 128, 2, 0.0, 'ln', True, heads=8, attention=True)
+    conv.set_agg_dtype(torch.bfloat16)
+    assert conv.prop.rFF.tc_dtype == torch.bfloat16 and conv.prop.agg_dtype == torch.bfloat16
+    with torch.no_grad():
+        assert not conv.prop._tc_v_ok(x)
+    conv.set_agg_dtype(None)
+    assert conv.prop.rFF.tc_dtype is None
+    ds = allset_b200.HalfNLHconv(128, 128, 128, 2, 0.0, 'ln', True, heads=1, attention=False)
+    ds.set_agg_dtype(torch.bfloat16)
+    assert ds.f_enc.tc_dtype == torch.bfloat16 and ds.f_dec.tc_dtype == torch.bfloat16
+    odd = allset_b200.MLP(128, 64, 128, 2, dropout=0.0, Normalization='ln', InputNorm=True)
+    odd.tc_dtype = torch.bfloat16
+    with torch.no_grad():
+        assert not odd._tc_ok(x)                     # not square
