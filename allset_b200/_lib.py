@@ -47,6 +47,7 @@ SIGNATURES = {
     'allset_pma_fwd_strided': (_c.c_int, [_p, _i64, _p, _i64, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64, _p, _p, _p]),
     'allset_pma_tail_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _f32, _c.c_int, _i64, _i32,
                                        _p, _c.c_int, _p, _p]),
+    'allset_linear_score_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _p, _p, _i32, _i64, _i32, _p, _c.c_int, _i64, _p, _p, _p]),
     'allset_segreduce_bwd_w': (_c.c_int, [_p, _p, _c.c_int, _i32, _p, _p, _p, _i64, _p, _p]),
     'allset_pma_fwd': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
                                   _p, _i32, _i32, _p, _p, _p]),
@@ -340,6 +341,37 @@ def pma_tail_fwd(x: torch.Tensor, ln0, w1: torch.Tensor, b1: Optional[torch.Tens
                                          1 if relu_final else 0, rows, d, _ptr(out), od, _ptr(status), _stream()),
                'allset_pma_tail_fwd')
     return out
+
+
+def linear_score_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], w_eff: torch.Tensor,
+                     b_eff: Optional[torch.Tensor], out_dtype: Optional[torch.dtype] = None,
+                     out: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None):
+    """-> (out = x W^T + b  [rows, d] (tcgen05, bf16 operands), score = x w_eff^T + b_eff  [rows, H] f32 (fp32 FMAs)) in
+    one launch: PMA.lin_V and the folded lin_K score.  `out` may be a pitched [rows, d] view (see mlp2_fwd)."""
+    _need(x, 'x')
+    xd = _dtype_code(x)
+    rows, d = x.shape
+    _need(w, 'w', torch.float32)
+    _need(b, 'b', torch.float32, optional=True)
+    _need(w_eff, 'w_eff', torch.float32)
+    _need(b_eff, 'b_eff', torch.float32, optional=True)
+    H = w_eff.shape[0]
+    if tuple(w.shape) != (d, d) or w_eff.dim() != 2 or w_eff.shape[1] != d or (b_eff is not None and b_eff.numel() != H):
+        raise ValueError('linear_score_fwd: shape mismatch')
+    if out is None:
+        out = torch.empty((rows, d), dtype=torch.float32 if out_dtype is None else out_dtype, device=x.device)
+        pitch = 0
+    else:
+        if not out.is_cuda or tuple(out.shape) != (rows, d) or out.stride(1) != 1:
+            raise ValueError('linear_score_fwd: out must be a CUDA [rows, d] view with unit column stride')
+        pitch = out.stride(0) * out.element_size()
+    score = torch.empty((rows, H), dtype=torch.float32, device=x.device)
+    _need(status, 'status', torch.int32, optional=True)
+    with torch.cuda.device(x.device):
+        _check(lib().allset_linear_score_fwd(_ptr(x), xd, _ptr(w), _ptr(b), _ptr(w_eff), _ptr(b_eff), H, rows, d, _ptr(out),
+                                             _dtype_code(out), pitch, _ptr(score), _ptr(status), _stream()),
+               'allset_linear_score_fwd')
+    return out, score
 
 
 class Unsupported(RuntimeError):

@@ -1871,15 +1871,15 @@ namespace {
 }  // namespace
 
 namespace {
-template <bool TAIL>
+template <int MODE>
 int mlp2_dispatch(const mlp5::Params& p, int x_dtype, int out_dtype, int32_t d, cudaStream_t st) {
   using bf16 = __nv_bfloat16;
 #define ALLSET_MLP2_CASE(D_)                                                                                    \
   if (d == D_) {                                                                                                \
-    if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_F32) return mlp5::launch<float, float, D_, TAIL>(p, st);   \
-    if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_BF16) return mlp5::launch<float, bf16, D_, TAIL>(p, st);   \
-    if (x_dtype == ALLSET_BF16 && out_dtype == ALLSET_F32) return mlp5::launch<bf16, float, D_, TAIL>(p, st);   \
-    return mlp5::launch<bf16, bf16, D_, TAIL>(p, st);                                                           \
+    if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_F32) return mlp5::launch<float, float, D_, MODE>(p, st);   \
+    if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_BF16) return mlp5::launch<float, bf16, D_, MODE>(p, st);   \
+    if (x_dtype == ALLSET_BF16 && out_dtype == ALLSET_F32) return mlp5::launch<bf16, float, D_, MODE>(p, st);   \
+    return mlp5::launch<bf16, bf16, D_, MODE>(p, st);                                                           \
   }
   ALLSET_MLP2_CASE(64)
   ALLSET_MLP2_CASE(128)
@@ -2104,8 +2104,9 @@ int allset_mlp2_fwd(const void* x, int x_dtype, const float* ln0_gamma, const fl
   if (out_pitch < dense_pitch || out_pitch % 16 != 0)
     return fail(ALLSET_EINVAL, "mlp2_fwd: out_pitch must be 0 or a multiple of 16 >= the row size");
   mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, ln1_gamma, ln1_beta, single ? w1 : w2, b2, ln0_eps, ln1_eps, relu_out,
-                 single, (long long)rows, status, 0, 0, nullptr, nullptr, 0.f, (long long)out_pitch};
-  return mlp2_dispatch<false>(p, x_dtype, out_dtype, d, static_cast<cudaStream_t>(stream));
+                 single, (long long)rows, status, 0, 0, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, 0,
+                 (long long)out_pitch};
+  return mlp2_dispatch<0>(p, x_dtype, out_dtype, d, static_cast<cudaStream_t>(stream));
 }
 
 int allset_pma_tail_fwd(const void* x, int x_dtype, const float* ln0_gamma, const float* ln0_beta, float ln0_eps,
@@ -2121,11 +2122,33 @@ int allset_pma_tail_fwd(const void* x, int x_dtype, const float* ln0_gamma, cons
   const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)ln0_gamma;
   if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "pma_tail_fwd: x, out, w1, w2, ln0_gamma must be 16-byte aligned");
   mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, nullptr, nullptr, w2, b2, ln0_eps, 1e-5f, 1,
-                 0, (long long)rows, status, 1, relu_final, ln1_gamma, ln1_beta, ln1_eps,
+                 0, (long long)rows, status, 1, relu_final, ln1_gamma, ln1_beta, ln1_eps, nullptr, nullptr, nullptr, 0,
                  (long long)d * elem_bytes(out_dtype)};
-  return mlp2_dispatch<true>(p, x_dtype, out_dtype, d, static_cast<cudaStream_t>(stream));
+  return mlp2_dispatch<1>(p, x_dtype, out_dtype, d, static_cast<cudaStream_t>(stream));
 }
 
+
+int allset_linear_score_fwd(const void* x, int x_dtype, const float* w, const float* b, const float* w_eff,
+                            const float* b_eff, int32_t heads, int64_t rows, int32_t d, void* out, int out_dtype,
+                            int64_t out_pitch, float* score, int32_t* status, void* stream) {
+  if (rows < 0 || d <= 0 || heads <= 0) return fail(ALLSET_EINVAL, "linear_score_fwd: bad size");
+  if (bad_dtype(x_dtype) || bad_dtype(out_dtype)) return fail(ALLSET_EINVAL, "linear_score_fwd: dtype must be 0 (f32) or 1 (bf16)");
+  if (d != 64 && d != 128) return fail(ALLSET_EUNSUPPORTED, "linear_score_fwd: width %d not supported (64 or 128)", (int)d);
+  if ((int64_t)heads * d * 4 > 4096) return fail(ALLSET_EUNSUPPORTED, "linear_score_fwd: heads * d must be <= 1024");
+  if (rows == 0) return ALLSET_OK;
+  if (x == nullptr || out == nullptr || w == nullptr || w_eff == nullptr || score == nullptr)
+    return fail(ALLSET_EINVAL, "linear_score_fwd: null pointer");
+  const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w;
+  if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "linear_score_fwd: x, out, w must be 16-byte aligned");
+  const int64_t dense_pitch = (int64_t)d * elem_bytes(out_dtype);
+  if (out_pitch == 0) out_pitch = dense_pitch;
+  if (out_pitch < dense_pitch || out_pitch % 16 != 0)
+    return fail(ALLSET_EINVAL, "linear_score_fwd: out_pitch must be 0 or a multiple of 16 >= the row size");
+  mlp5::Params p{x, out, nullptr, nullptr, w, b, nullptr, nullptr, w, nullptr, 1e-5f, 1e-5f, 0,
+                 1, (long long)rows, status, 0, 0, nullptr, nullptr, 0.f, w_eff, b_eff, score, (int)heads,
+                 (long long)out_pitch};
+  return mlp2_dispatch<2>(p, x_dtype, out_dtype, d, static_cast<cudaStream_t>(stream));
+}
 
 int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32_t d, const int32_t* rowptr,
                            const int32_t* col, const float* tgt_scale, int64_t n_tgt, float* grad_w,

@@ -49,6 +49,12 @@ struct Params {
   const float* lnf_g;
   const float* lnf_b;
   float epsf;
+  // MODE 2 (PMA.lin_V + the folded lin_K score, src/layers.py:128-130): single Linear AND, in fp32 on the CUDA cores
+  // of the producer warps, score[r, h] = <x[r, :], w_eff[h, :]> + b_eff[h] for H heads
+  const float* w_eff;    // [H, D] f32
+  const float* b_eff;    // [H] f32 or NULL
+  float* score;          // [rows, H] f32
+  int heads;
   long long out_pitch;   // bytes between output rows (>= D * sizeof(TOut), multiple of 16); lets lin_V write packed records
 };
 
@@ -314,6 +320,60 @@ struct Producer {
     }
   }
   // LayerNorm 0 WITHOUT its affine part (gamma / beta are folded into W1 / b1 at setup), the G row groups in lockstep.
+  // PMA score of the rows of one half, fp32 on the CUDA cores: lane cl of a row holds EPL of its D elements; 8 heads at
+  // a time are reduced over the 8 lanes of the row by a TRANSPOSED butterfly (4 + 2 + 1 shuffles: each step a lane keeps
+  // half of its partial sums and adds the partner's), after which lane cl owns head hb + cl and stores it.
+  __device__ static __forceinline__ void score(const Buf& buf, const float* sWe, const float* sBe, int H, float* out,
+                                               long long row0, long long rows, int pw, int half, int sub, int cl) {
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+      float x[EPL];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        float t[EPC];
+        RowChunk<TIn>::unpack(buf[gi][j], t);
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) x[j * EPC + e] = t[e];
+      }
+      const long long gr = row0 + pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
+      for (int hb = 0; hb < H; hb += 8) {
+        float a[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          float a0 = 0.f, a1 = 0.f;
+          if (hb + h < H) {
+            const float* w = sWe + (hb + h) * D;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+              const float* wc = w + (cl + LPR * j) * EPC;
+#pragma unroll
+              for (int e = 0; e < EPC; e += 2) ffma2p(a0, a1, x[j * EPC + e], x[j * EPC + e + 1], wc[e], wc[e + 1]);
+            }
+          }
+          a[h] = a0 + a1;
+        }
+        // transposed butterfly over the 8 lanes of the row
+        float b4[4], b2[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = (cl & 4) ? a[i] : a[i + 4];
+          const float keep = (cl & 4) ? a[i + 4] : a[i];
+          b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = (cl & 2) ? b4[i] : b4[i + 2];
+          const float keep = (cl & 2) ? b4[i + 2] : b4[i];
+          b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        const float send = (cl & 1) ? b2[0] : b2[1];
+        const float keep = (cl & 1) ? b2[1] : b2[0];
+        const float total = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        if (gr < rows && hb + cl < H) out[gr * H + hb + cl] = total + sBe[hb + cl];
+      }
+    }
+  }
+
   using Packed = uint32_t[G][EPL / 2];          // the normalised rows of one half as bf16 pairs
   __device__ static __forceinline__ void compute(const Buf& buf, Packed& pk, float2 (&stats)[G], bool has_ln0,
                                                  float eps0) {
@@ -397,8 +457,10 @@ struct Producer {
   }
 };
 
-template <typename TIn, typename TOut, int D, bool TAIL>
+template <typename TIn, typename TOut, int D, int MODE>
 __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) {
+  constexpr bool TAIL = (MODE == 1);
+  constexpr bool SCORE = (MODE == 2);
   using L = Layout<D>;
   static_assert(D == 64 || D == 128, "mlp2_ws: widths 64 and 128");
   constexpr int PASS_BYTES = L::template pass_bytes<TOut>();
@@ -478,6 +540,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (part == 0) sPar[n] = (bias ? bias[row] : 0.f) + acc;
   }
+  if (SCORE) {        // w_eff [H, D] fp32 lives where the tail's row statistics would (H * D * 4 <= 4 KB)
+    float* sWe = reinterpret_cast<float*>(sStat);
+    for (int i = tid; i < p.heads * D; i += kWsThreads) sWe[i] = p.w_eff[i];
+    for (int i = tid; i < p.heads; i += kWsThreads) sPar[2 * D + i] = p.b_eff ? p.b_eff[i] : 0.f;
+  }
   if (TAIL) {
     for (int i = tid; i < D; i += kWsThreads) {
       sPar[2 * D + i] = p.ln0_g[i];
@@ -513,8 +580,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       // all the arithmetic happens BEFORE the stage is known to be free; only the shared-memory stores wait for it
       typename P::Packed pkA, pkB;
       float2 stA[P::G] = {}, stB[P::G] = {};
+      if (SCORE) P::score(bufA, reinterpret_cast<const float*>(sStat), sPar + 2 * D, p.heads, p.score, tile * kTileM,
+                          p.rows, pw, 0, sub, cl);
       P::compute(bufA, pkA, stA, has_ln0, p.eps0);
       if (next < n_tiles) P::load(bufA, xb, next * kTileM, p.rows, pw, 0, sub, cl);
+      if (SCORE) P::score(bufB, reinterpret_cast<const float*>(sStat), sPar + 2 * D, p.heads, p.score, tile * kTileM,
+                          p.rows, pw, 1, sub, cl);
       P::compute(bufB, pkB, stB, has_ln0, p.eps0);
       if (next < n_tiles) P::load(bufB, xb, next * kTileM, p.rows, pw, 1, sub, cl);
       if (it >= 2) mbar_wait_bounded<2000>(bar_a_empty + 8 * st, ((it >> 1) - 1) & 1u, p.status);
@@ -742,23 +813,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
   if (warp == 1) tmem_dealloc(tmem_base, WsLayout<D>::TMEM_COLS);
 }
 
-template <typename TIn, typename TOut, int D, bool TAIL>
+template <typename TIn, typename TOut, int D, int MODE>
 int launch(const Params& p, cudaStream_t st) {
   const long long n_tiles = (p.rows + kTileM - 1) / kTileM;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   constexpr int smem = WsLayout<D>::template smem_bytes<TOut>();
-  cudaError_t e = cudaFuncSetAttribute(mlp2_ws_kernel<TIn, TOut, D, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(mlp2_ws_kernel<TIn, TOut, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return fail(ALLSET_ECUDA, "mlp2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int fits = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fits, mlp2_ws_kernel<TIn, TOut, D, TAIL>, kWsThreads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fits, mlp2_ws_kernel<TIn, TOut, D, MODE>, kWsThreads, smem);
   if (e != cudaSuccess || fits < 1)
     return fail(ALLSET_ECUDA, "mlp2_fwd: the 16-warp kernel does not fit one SM (%s)",
                 e != cudaSuccess ? cudaGetErrorString(e) : "0 resident CTAs");
   long long grid = sms;
   if (grid > n_tiles) grid = n_tiles;
-  mlp2_ws_kernel<TIn, TOut, D, TAIL><<<(unsigned)grid, kWsThreads, smem, st>>>(p);
+  mlp2_ws_kernel<TIn, TOut, D, MODE><<<(unsigned)grid, kWsThreads, smem, st>>>(p);
   return check_launch("mlp2_fwd");
 }
 

@@ -192,18 +192,30 @@ class PMA(nn.Module):
         seed = self.att_r.view(H, C)
         w_eff = (self.lin_K.weight.view(H, C, -1) * seed.unsqueeze(-1)).sum(dim=1)         # [H, in]
         b_eff = (self.lin_K.bias.view(H, C) * seed).sum(dim=1)                             # [H]
-        score = F.linear(x, w_eff, b_eff)                                                  # [n_src, H]
         fused = self.rFF._fused_ok(x) and ops.fused_dense_ok(x, self.heads * self.hidden)
         want_alpha = isinstance(return_attention_weights, bool)
         out = None
-        if self._tc_v_ok(x):
-            # bf16 mode: V = lin_V(x) as ONE tcgen05 kernel that writes the bf16 rows the aggregation gathers
+        tc_v = self._tc_v_ok(x)
+        tc_score = tc_v and H * H * C <= 1024               # w_eff must fit the kernel's 4 KB side buffer
+        score = None if tc_score else F.linear(x, w_eff, b_eff)                            # [n_src, H]
+        if tc_v:
+            # bf16 mode: V = lin_V(x) as ONE tcgen05 kernel that writes the bf16 rows the aggregation gathers; the same
+            # launch computes the fp32 scores in its producer warps (no second pass over x)
             xc = x.contiguous()
+            w_eff_c, b_eff_c = w_eff.contiguous(), b_eff.contiguous()
+
+            def lin_v(out_view=None):
+                if tc_score:
+                    return _lib.linear_score_fwd(xc, self.lin_V.weight, self.lin_V.bias, w_eff_c, b_eff_c,
+                                                 out_dtype=torch.bfloat16, out=out_view)
+                return _lib.mlp2_fwd(xc, self.lin_V.weight, self.lin_V.bias, None, None, None, None, False,
+                                     torch.bfloat16, out=out_view), score
+
             if not want_alpha and self._packed_ok(xc, inc):
                 # scores too large for L2: one packed [values | scores] record per source row, so that a gather touches
                 # one contiguous record per incidence instead of a row plus a 32-byte score in another 128-byte line
                 _, v, s = _lib.packed_pma_records(xc.shape[0], H * C, H, torch.bfloat16, xc.device)
-                _lib.mlp2_fwd(xc, self.lin_V.weight, self.lin_V.bias, None, None, None, None, False, out=v)
+                _, score = lin_v(v)
                 s.copy_(score)
                 t = inc.by_tgt
                 try:
@@ -213,7 +225,7 @@ class PMA(nn.Module):
                 except _lib.Unsupported:
                     v = v.contiguous()
             else:
-                v = _lib.mlp2_fwd(xc, self.lin_V.weight, self.lin_V.bias, None, None, None, None, False, torch.bfloat16)
+                v, score = lin_v()
         else:
             if fused:
                 x_V = ops.bias_act_norm(F.linear(x, self.lin_V.weight), self.lin_V.bias)

@@ -158,6 +158,19 @@ int allset_pma_tail_fwd(const void* x, int x_dtype,
                         const float* ln1_gamma, const float* ln1_beta, float ln1_eps, int relu_final,
                         int64_t rows, int32_t d, void* out, int out_dtype, int32_t* status, void* stream);
 
+/* PMA's two projections of the source rows in ONE launch (equal widths d in {64, 128}, heads * d <= 1024):
+ *     out[r, :]   = x[r, :] W^T + b                      -- V = lin_V(x), src/layers.py:129, on tcgen05 (bf16 operands)
+ *     score[r, h] = <x[r, :], w_eff[h, :]> + b_eff[h]    -- (lin_K(x).view(-1, H, C) * att_r).sum(-1), src/layers.py:128,130,
+ *                                                           with lin_K folded into w_eff[h, :] = sum_c att_r[h, c] W_K[hC+c, :]
+ *                                                           (one seed per head makes the score linear in x); fp32 FMAs
+ *                                                           in the producer warps while they hold the row for the GEMM
+ * x [rows, d] f32|bf16; W [d, d], w_eff [heads, d], b, b_eff f32; out f32|bf16 with out_pitch as in allset_mlp2_fwd;
+ * score [rows, heads] f32 dense.  Replaces a skinny cuBLAS GEMM that re-reads x. */
+int allset_linear_score_fwd(const void* x, int x_dtype, const float* w, const float* b,
+                            const float* w_eff, const float* b_eff, int32_t heads,
+                            int64_t rows, int32_t d, void* out, int out_dtype, int64_t out_pitch,
+                            float* score, int32_t* status, void* stream);
+
 /* Backward of allset_bias_act_norm (d in {128,256,512,1024}; ALLSET_EUNSUPPORTED otherwise):
  *   dx [rows, d] = gradient w.r.t. x;  dres [rows, d] or NULL = gradient w.r.t. residual;
  *   partial [blocks, 3, d] = per-CTA column sums of (d gamma, d beta, d bias), blocks =

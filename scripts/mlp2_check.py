@@ -167,7 +167,31 @@ def timing_tail(rows, d, in_dtype, out_dtype):
                       'GBps': nbytes / ms / 1e6}), flush=True)
 
 
+def timing_score(rows, d, H):
+    x = torch.randn(rows, d, device=dev)
+    w = torch.randn(d, d, device=dev) / d ** 0.5
+    b = torch.zeros(d, device=dev)
+    we = torch.randn(H, d, device=dev) / d ** 0.5
+    be = torch.zeros(H, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = {}
+    for name, f in (('fused', lambda: _lib.linear_score_fwd(x, w, b, we, be, out_dtype=b16)),
+                    ('separate', lambda: (_lib.mlp2_fwd(x, w, b, None, None, None, None, False, b16), F.linear(x, we, be)))):
+        for _ in range(5):
+            f()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(30):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name + '_ms'] = e0.elapsed_time(e1) / 30
+    res.update({'timing': 'linear_score', 'rows': rows, 'd': d, 'H': H})
+    print(json.dumps(res), flush=True)
+
+
 if '--time' in sys.argv and bad == 0:
+    timing_score(1 << 20, 128, 8)
     timing_tail(1 << 20, 128, b16, f32)
     timing_tail(1 << 20, 128, f32, f32)
     for ind, outd in ((f32, b16), (b16, f32), (f32, f32), (b16, b16)):

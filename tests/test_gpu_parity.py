@@ -828,15 +828,16 @@ def test_pma_bf16_mode_runs_lin_v_and_rff_on_tcgen05(d, heads, monkeypatch):
     conv.to(dev()).eval()
     conv.set_agg_dtype(torch.bfloat16)
     x = torch.randn(n, d, generator=torch.Generator().manual_seed(5))
-    calls, tails = [], []
-    real, real_tail = _lib.mlp2_fwd, _lib.pma_tail_fwd
-    monkeypatch.setattr(_lib, 'mlp2_fwd', lambda *a, **k: (calls.append(a[3] is None), real(*a, **k))[1])
+    calls, tails, plain = [], [], []
+    real, real_tail, real_plain = _lib.linear_score_fwd, _lib.pma_tail_fwd, _lib.mlp2_fwd
+    monkeypatch.setattr(_lib, 'linear_score_fwd', lambda *a, **k: (calls.append(a[3].shape[0]), real(*a, **k))[1])
     monkeypatch.setattr(_lib, 'pma_tail_fwd', lambda *a, **k: (tails.append(a[0].dtype), real_tail(*a, **k))[1])
+    monkeypatch.setattr(_lib, 'mlp2_fwd', lambda *a, **k: (plain.append(1), real_plain(*a, **k))[1])
     inc = ab().Incidence.from_coo(node, he, n_src=n)
     with torch.no_grad():
         out = conv(x.to(dev()), inc, None, 'add')
         out_relu = conv(x.to(dev()), inc, None, 'add', relu_out=True)
-    assert calls == [True, True]                   # lin_V as a single Linear (once per forward)
+    assert calls == [heads, heads] and not plain   # lin_V + the folded lin_K score in one launch (once per forward)
     assert tails == [torch.bfloat16] * 2           # ln0 / rFF / residual / ln1 as one kernel on the bf16 rows
     assert torch.equal(out_relu, torch.relu(out))
     ref = O.half_nlh_conv(params, '', x, node.cpu(), he.cpu(), None, 'add', attention=True, heads=heads)
@@ -945,3 +946,28 @@ def test_pma_module_packed_path_matches_unpacked(monkeypatch):
         packed_out = conv(x, inc, None, 'add')
     assert used == [1]
     assert torch.equal(packed_out, plain_out)
+
+
+@pytest.mark.parametrize('d,H', [(128, 8), (128, 4), (128, 1), (64, 12), (64, 16), (128, 3)])
+@pytest.mark.parametrize('in_dtype', [torch.float32, torch.bfloat16])
+def test_linear_score_tcgen05_vs_torch(d, H, in_dtype):
+    """out = x W^T + b on tcgen05 (bf16 class) and score = x w_eff^T + b_eff in fp32 FMAs (1e-4 class) in one launch."""
+    from allset_b200 import _lib
+    g = torch.Generator().manual_seed(d * 31 + H)
+    w = torch.randn(d, d, generator=g) / d ** 0.5
+    b = 0.3 * torch.randn(d, generator=g)
+    w_eff = torch.randn(H, d, generator=g) / d ** 0.5
+    b_eff = 0.3 * torch.randn(H, generator=g)
+    for rows in (3, 128 * 9 + 77, 128 * 500):
+        x = torch.randn(rows, d, generator=g).to(in_dtype)
+        status = torch.zeros(1, dtype=torch.int32, device=dev())
+        out, score = _lib.linear_score_fwd(x.to(dev()), w.to(dev()), b.to(dev()), w_eff.to(dev()), b_eff.to(dev()),
+                                           out_dtype=torch.bfloat16, status=status)
+        assert int(status.item()) == 0 and out.dtype == torch.bfloat16 and score.shape == (rows, H)
+        ref_out = F.linear(x.float(), w, b)
+        ref_score = F.linear(x.float().double(), w_eff.double(), b_eff.double()).float()
+        assert (out.float().cpu() - ref_out).abs().max().item() <= 1e-2 * max(ref_out.abs().max().item(), 1.0)
+        torch.testing.assert_close(score.cpu(), ref_score, rtol=1e-4, atol=1e-4)
+    with pytest.raises(RuntimeError, match='heads'):
+        _lib.linear_score_fwd(torch.zeros(4, 128, device=dev()), torch.zeros(128, 128, device=dev()), None,
+                              torch.zeros(16, 128, device=dev()), None)
