@@ -325,50 +325,68 @@ struct Producer {
   // half of its partial sums and adds the partner's), after which lane cl owns head hb + cl and stores it.
   __device__ static __forceinline__ void score(const Buf& buf, const float* sWe, const float* sBe, int H, float* out,
                                                long long row0, long long rows, int pw, int half, int sub, int cl) {
+    float x[G][EPL];
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
-      float x[EPL];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         float t[EPC];
         RowChunk<TIn>::unpack(buf[gi][j], t);
 #pragma unroll
-        for (int e = 0; e < EPC; ++e) x[j * EPC + e] = t[e];
+        for (int e = 0; e < EPC; ++e) x[gi][j * EPC + e] = t[e];
       }
-      const long long gr = row0 + pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
-      for (int hb = 0; hb < H; hb += 8) {
-        float a[8];
+    }
+    for (int hb = 0; hb < H; hb += 8) {
+      float a[G][8];
 #pragma unroll
-        for (int h = 0; h < 8; ++h) {
-          float a0 = 0.f, a1 = 0.f;
-          if (hb + h < H) {
-            const float* w = sWe + (hb + h) * D;
+      for (int h = 0; h < 8; ++h) {
+        float a0[G], a1[G];
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-              const float* wc = w + (cl + LPR * j) * EPC;
+        for (int gi = 0; gi < G; ++gi) a0[gi] = a1[gi] = 0.f;
+        if (hb + h < H) {
+          const float* w = sWe + (hb + h) * D;
 #pragma unroll
-              for (int e = 0; e < EPC; e += 2) ffma2p(a0, a1, x[j * EPC + e], x[j * EPC + e + 1], wc[e], wc[e + 1]);
+          for (int j = 0; j < CPL; ++j) {
+            float wc[EPC];                                    // one shared-memory read of w_eff serves both row groups
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) wc[e] = w[(cl + LPR * j) * EPC + e];
+#pragma unroll
+            for (int gi = 0; gi < G; ++gi) {
+#pragma unroll
+              for (int e = 0; e < EPC; e += 2)
+                ffma2p(a0[gi], a1[gi], x[gi][j * EPC + e], x[gi][j * EPC + e + 1], wc[e], wc[e + 1]);
             }
           }
-          a[h] = a0 + a1;
-        }
-        // transposed butterfly over the 8 lanes of the row
-        float b4[4], b2[2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float send = (cl & 4) ? a[i] : a[i + 4];
-          const float keep = (cl & 4) ? a[i + 4] : a[i];
-          b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
         }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float send = (cl & 2) ? b4[i] : b4[i + 2];
-          const float keep = (cl & 2) ? b4[i + 2] : b4[i];
-          b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        for (int gi = 0; gi < G; ++gi) a[gi][h] = a0[gi] + a1[gi];
+      }
+      // transposed butterfly over the 8 lanes of the row, both row groups in lockstep
+      float b4[G][4], b2[G][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+          const float send = (cl & 4) ? a[gi][i] : a[gi][i + 4];
+          const float keep = (cl & 4) ? a[gi][i + 4] : a[gi][i];
+          b4[gi][i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
         }
-        const float send = (cl & 1) ? b2[0] : b2[1];
-        const float keep = (cl & 1) ? b2[1] : b2[0];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+          const float send = (cl & 2) ? b4[gi][i] : b4[gi][i + 2];
+          const float keep = (cl & 2) ? b4[gi][i + 2] : b4[gi][i];
+          b2[gi][i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+      }
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) {
+        const float send = (cl & 1) ? b2[gi][0] : b2[gi][1];
+        const float keep = (cl & 1) ? b2[gi][1] : b2[gi][0];
         const float total = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        const long long gr = row0 + pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
         if (gr < rows && hb + cl < H) out[gr * H + hb + cl] = total + sBe[hb + cl];
       }
     }
