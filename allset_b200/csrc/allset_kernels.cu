@@ -2120,7 +2120,8 @@ int allset_pma_tail_fwd(const void* x, int x_dtype, const float* ln0_gamma, cons
   if (x == nullptr || out == nullptr || w1 == nullptr || w2 == nullptr || ln0_gamma == nullptr || ln1_gamma == nullptr)
     return fail(ALLSET_EINVAL, "pma_tail_fwd: null pointer");
   const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)ln0_gamma;
-  if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "pma_tail_fwd: x, out, w1, w2, ln0_gamma must be 16-byte aligned");
+  if (bits % 16 != 0 || (uintptr_t)x % 32 != 0)
+    return fail(ALLSET_EUNSUPPORTED, "pma_tail_fwd: out, w1, w2, ln0_gamma must be 16-byte and x 32-byte aligned");
   mlp5::Params p{x, out, ln0_gamma, ln0_beta, w1, b1, nullptr, nullptr, w2, b2, ln0_eps, 1e-5f, 1,
                  0, (long long)rows, status, 1, relu_final, ln1_gamma, ln1_beta, ln1_eps, nullptr, nullptr, nullptr, 0,
                  (long long)d * elem_bytes(out_dtype)};

@@ -183,6 +183,12 @@ __device__ __forceinline__ void st_shared16(uint32_t addr, uint32_t a, uint32_t 
 __device__ __forceinline__ void st_shared8(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
+// 32 bytes per thread in one request (LDG.256, sm_100): a full sector even when the lanes of a warp are rows apart
+__device__ __forceinline__ void ld_nc_32(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
 __device__ __forceinline__ uint4 ld_shared16(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -726,14 +732,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
 #pragma unroll 1
         for (int c = 0; c < D; c += 32) {
           float v[32], xf[32];
+          // a thread re-reads ITS row: 32-byte loads (LDG.256), so every request is one whole sector although the 32 rows
+          // of a warp instruction are D * sizeof(TIn) bytes apart
           constexpr int XC = RowChunk<TIn>::N;
 #pragma unroll
-          for (int j = 0; j < 32 / XC; ++j) {
-            const uint4 q = (gr < p.rows) ? ld_nc_16(xrow + (size_t)(c + j * XC) * sizeof(TIn)) : make_uint4(0, 0, 0, 0);
+          for (int j = 0; j < 32 / (2 * XC); ++j) {
+            uint4 qa = make_uint4(0, 0, 0, 0), qb = make_uint4(0, 0, 0, 0);
+            if (gr < p.rows) ld_nc_32(xrow + (size_t)(c + j * 2 * XC) * sizeof(TIn), qa, qb);
             float t[XC];
-            RowChunk<TIn>::unpack(q, t);
+            RowChunk<TIn>::unpack(qa, t);
 #pragma unroll
-            for (int e = 0; e < XC; ++e) xf[j * XC + e] = t[e];
+            for (int e = 0; e < XC; ++e) xf[j * 2 * XC + e] = t[e];
+            RowChunk<TIn>::unpack(qb, t);
+#pragma unroll
+            for (int e = 0; e < XC; ++e) xf[j * 2 * XC + XC + e] = t[e];
           }
           tmem_ld32(tmem_acc2 + lane_off + c, v);
 #pragma unroll
