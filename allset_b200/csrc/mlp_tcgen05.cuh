@@ -55,6 +55,7 @@ struct Params {
   const float* b_eff;    // [H] f32 or NULL
   float* score;          // [rows, H] f32
   int heads;
+  int direct;            // 1: epilogue 2 stores 32-byte pieces of a thread's own row (STG.256) instead of staging
   long long out_pitch;   // bytes between output rows (>= D * sizeof(TOut), multiple of 16); lets lin_V write packed records
 };
 
@@ -188,6 +189,12 @@ __device__ __forceinline__ void ld_nc_32(const void* p, uint4& a, uint4& b) {
   asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                : "l"(p));
+}
+__device__ __forceinline__ void st_global32(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                            uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+               "r"(f), "r"(g), "r"(h)
+               : "memory");
 }
 __device__ __forceinline__ uint4 ld_shared16(uint32_t addr) {
   uint4 v;
@@ -797,7 +804,27 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
               }
             }
           }
-          if constexpr (sizeof(TOut) == 2) {
+          if (p.direct) {
+            // thread-per-row stores in whole 32-byte sectors: no staging round trip through shared memory
+            const long long gr = row0 + r;
+            if (gr < p.rows) {
+              unsigned char* dst = ob + (size_t)gr * (size_t)p.out_pitch + (size_t)(pass * CPP + c) * sizeof(TOut);
+              if constexpr (sizeof(TOut) == 2) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                  st_global32(dst + 32 * q, pack_bf16(v[16 * q], v[16 * q + 1]), pack_bf16(v[16 * q + 2], v[16 * q + 3]),
+                              pack_bf16(v[16 * q + 4], v[16 * q + 5]), pack_bf16(v[16 * q + 6], v[16 * q + 7]),
+                              pack_bf16(v[16 * q + 8], v[16 * q + 9]), pack_bf16(v[16 * q + 10], v[16 * q + 11]),
+                              pack_bf16(v[16 * q + 12], v[16 * q + 13]), pack_bf16(v[16 * q + 14], v[16 * q + 15]));
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  st_global32(dst + 32 * q, __float_as_uint(v[8 * q]), __float_as_uint(v[8 * q + 1]),
+                              __float_as_uint(v[8 * q + 2]), __float_as_uint(v[8 * q + 3]), __float_as_uint(v[8 * q + 4]),
+                              __float_as_uint(v[8 * q + 5]), __float_as_uint(v[8 * q + 6]), __float_as_uint(v[8 * q + 7]));
+              }
+            }
+          } else if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               const int c16 = (c >> 3) + q4;
@@ -822,6 +849,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
           if (issuer && has_next) gemm1(k + 1);
         }
         __syncwarp();
+        if (p.direct) continue;                  // nothing staged: the hidden tile is untouched, no barrier needed
         const int wrow = (warp & 3) * 32;
 #pragma unroll
         for (int idx = lane; idx < 32 * CHUNKS_PER_ROW; idx += 32) {
