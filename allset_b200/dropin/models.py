@@ -1,5 +1,6 @@
 """Drop-in `models` module: `SetGNN` is the B200-native one (same ctor / forward / state_dict as reference
-src/models.py:295-484); the ten baseline models are forwarded from the reference unchanged."""
+src/models.py:295-484); `UniGCNII` / `UniGCNIIConv` (reference src/models.py:909-995) run on the same segmented-reduce kernels; the other
+baseline models are forwarded from the reference unchanged."""
 import os as _os
 import sys as _sys
 
@@ -8,3 +9,4 @@ from allset_b200.dropin._forward import load_reference as _load, public_names as
 
 globals().update(_names(_load('models')))
 from allset_b200.models import SetGNN  # noqa: E402,F401
+from allset_b200.uni import UniGCNII, UniGCNIIConv  # noqa: E402,F401  (same kernels)

@@ -19,6 +19,7 @@ from layers import *
 from models import *
 import allset_b200
 assert SetGNN is allset_b200.SetGNN and HalfNLHconv is allset_b200.HalfNLHconv and PMA is allset_b200.PMA
+assert UniGCNII is allset_b200.UniGCNII and UniGCNIIConv is allset_b200.UniGCNIIConv
 for name in ('HyperGCN', 'CEGCN', 'CEGAT', 'HCHA', 'HNHN', 'HGNN', 'MLP_model', 'UniGCNII', 'HypergraphConv', 'HNHNConv'):
     assert name in globals(), name
 assert HCHA.__module__.startswith('_allset_reference_')
