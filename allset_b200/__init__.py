@@ -7,6 +7,7 @@ Public surface (mirrors the reference's module API, reference src/layers.py + sr
     UniGCNII, UniGCNIIConv                  the reference's UniGCNII baseline on the same kernels (V->E mean, E->V sum)
     GraphedForward                          CUDA-graph replay of a SetGNN forward (launch-bound real datasets)
     preprocessing, sharding, synthetic      incidence preprocessing, multi-GPU partition + fused exchange, generators
+    ingest                                  star expansion of a hyperedge dictionary + flat memory-mapped dataset cache
 The device code lives in liballset_b200.so (C ABI: include/allset_b200.h), built by `python -m allset_b200.build`.
 There is no CPU fallback anywhere in this package.
 """
