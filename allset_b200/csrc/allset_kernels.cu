@@ -719,6 +719,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+constexpr int kPmaOnlinePiece = 8;   // pieces up to this many rows take the single-pass online-softmax path
+
 // PMA over the same TMA ring: every staged item is a value row (row_bytes) plus the H fp32 scores of that source row
 // (a second bulk copy onto the same mbarrier).  The online softmax runs per lane-chunk in the log2 domain
 // (a2 = leaky_relu(score) * log2(e); p = 2^(a2 - m2)), state (m2, l, acc) is flushed at segment boundaries:
@@ -875,6 +877,32 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
       const uint32_t prow = rows + (uint32_t)r * ROWB, psc = scs + (uint32_t)r * SB;
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
+        if (plen <= kPmaOnlinePiece) {
+          // short piece (the E->V direction: ~5 rows per piece): ONE pass with an online max -- per row two ex2 and a
+          // rescale of the carried state, but none of the two-pass loop / remainder control overhead that made the
+          // kernel issue-bound on short segments (ncu: 4.2 G warp instructions = 70 per incidence, 82 % issue-active)
+          float m = m2[c], lc = l[c];
+#pragma unroll 1
+          for (int k = 0; k < plen; ++k) {
+            uint32_t r0[4];
+            load_chunk(prow + k * ROWB, c, r0);
+            const float a = load_a2(psc + k * SB, c);
+            const float mn = fmaxf(m, a);
+            const float cf = ex2_approx(m - mn);             // 2^-inf = 0 for the first row of a segment
+            const float p0 = ex2_approx(a - mn);
+            m = mn;
+            lc = fmaf(lc, cf, p0);
+#pragma unroll
+            for (int i = 0; i < EPC; i += 2) {
+              if (EPC >= 2) fmul2(acc[c * EPC + i], acc[c * EPC + i + 1], cf);
+              else acc[c * EPC + i] *= cf;
+            }
+            fma_chunk(c, r0, p0);
+          }
+          m2[c] = m;
+          l[c] = lc;
+          continue;
+        }
         // pass 1: piece max
         float pm = -INFINITY;
         int k = 0;
