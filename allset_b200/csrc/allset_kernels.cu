@@ -829,6 +829,7 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
   };
 
   const uint64_t pol_rows = l2_policy_evict_first(), pol_side = l2_policy_evict_last();
+  const bool dense = (v_pitch == (long long)ROWB) && (s_pitch == (long long)SB);
   int ipos = kb, pf_idx = 0;
   auto prefetch = [&]() {
     pf_idx = 0;
@@ -841,10 +842,15 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)n * (ROWB + SB));
     __syncwarp();
 #endif
-    stage_rows<ROWB, true>(ring + (uint32_t)st * (RPS * ROWB), reinterpret_cast<const unsigned char*>(v), pf_idx, n, bar, lane, pol_rows,
-                           (size_t)v_pitch);
-    stage_side(sring + (uint32_t)st * RPS * SB, reinterpret_cast<const unsigned char*>(score), pf_idx, n, SB, bar, lane,
-               s_pitch == v_pitch ? pol_rows : pol_side, (size_t)s_pitch);
+    if (dense) {      // the usual case keeps the compile-time row pitch (a shift instead of a 64-bit multiply per chunk)
+      stage_rows<ROWB, true>(ring + (uint32_t)st * (RPS * ROWB), reinterpret_cast<const unsigned char*>(v), pf_idx, n, bar, lane, pol_rows);
+      stage_side(sring + (uint32_t)st * RPS * SB, reinterpret_cast<const unsigned char*>(score), pf_idx, n, SB, bar, lane, pol_side, SB);
+    } else {
+      stage_rows<ROWB, true>(ring + (uint32_t)st * (RPS * ROWB), reinterpret_cast<const unsigned char*>(v), pf_idx, n, bar, lane, pol_rows,
+                             (size_t)v_pitch);
+      stage_side(sring + (uint32_t)st * RPS * SB, reinterpret_cast<const unsigned char*>(score), pf_idx, n, SB, bar, lane,
+                 s_pitch == v_pitch ? pol_rows : pol_side, (size_t)s_pitch);
+    }
 #if ALLSET_STREAM_COPY == 0
     cp_async_arrive(bar);
 #endif
