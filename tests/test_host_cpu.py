@@ -47,6 +47,44 @@ def test_ctypes_signatures_cover_the_header(built_lib):
     assert _lib.lib().allset_version() == _lib.ABI_VERSION
 
 
+def _header_prototypes():
+    """name -> list of parameter declarations, parsed from the header (comments stripped)."""
+    text = open(os.path.join(ROOT, 'include', 'allset_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'\b(allset_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S):
+        params = [q.strip() for q in m.group(2).split(',')]
+        protos[m.group(1)] = [] if params in ([''], ['void']) else params
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Arity and the pointer / integer / float kind of every parameter: a ctypes binding that drifts from the header
+    (an argument added on one side only) corrupts the call silently."""
+    from allset_b200 import _lib
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, params in protos.items():
+        argtypes = _lib.SIGNATURES[name][1]
+        assert len(argtypes) == len(params), '%s: header has %d parameters, ctypes %d' % (name, len(params), len(argtypes))
+        for decl, ct in zip(params, argtypes):
+            if '*' in decl:
+                assert ct in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ct, 'contents') or ct.__name__.startswith('LP_'), \
+                    '%s: %r bound as %s' % (name, decl, ct)
+            elif re.search(r'\bfloat\b', decl):
+                assert ct is ctypes.c_float, '%s: %r bound as %s' % (name, decl, ct)
+            elif re.search(r'\bint64_t\b', decl):
+                assert ct is ctypes.c_int64, '%s: %r bound as %s' % (name, decl, ct)
+            elif re.search(r'\bint32_t\b', decl):
+                assert ct is ctypes.c_int32, '%s: %r bound as %s' % (name, decl, ct)
+            elif re.search(r'\bsize_t\b', decl):
+                assert ct is ctypes.c_size_t, '%s: %r bound as %s' % (name, decl, ct)
+            elif re.search(r'\bint\b', decl):
+                assert ct is ctypes.c_int, '%s: %r bound as %s' % (name, decl, ct)
+            else:
+                raise AssertionError('%s: unrecognised parameter %r' % (name, decl))
+
+
 def test_library_is_sm100a_only(built_lib):
     import shutil
     import subprocess
