@@ -10,6 +10,13 @@ src/convert_datasets_to_pygDataset.py:163-175, src/load_other_datasets.py:121-19
                                           re-parses pickles into dense Python lists (`node_list += list(cur_he)`) on
                                           every first load and stores a pickled PyG `Data` afterwards
 
+    load_le_dataset(dir, name)            == load_LE_dataset (load_other_datasets.py:32-119): `<name>.content` (id, features..., label
+                                             per line, nodes first then hyperedges) + `<name>.edges` (node id, hyperedge id)
+    load_cornell_dataset(dir, name)       == load_cornell_dataset (load_other_datasets.py:293-386): one hyperedge per line,
+                                             one label per line; features = one-hot(label) + N(0, noise) (the reference
+                                             draws the noise from numpy's global RNG, so features match in distribution,
+                                             labels / incidence exactly)
+
 Host-side code (numpy / torch CPU); the arrays it yields are what `allset_b200.preprocessing` consumes on the GPU.
 """
 from __future__ import annotations
@@ -43,6 +50,59 @@ def star_expansion(hyperedges: Union[Mapping[object, Sequence[int]], Iterable[Se
     key = np.unique(row0 * total + row1)                        # sort by (row 0, row 1) and drop duplicates
     ei = np.stack([key // total, key % total])
     return torch.from_numpy(ei), len(lists)
+
+
+def _coalesced_star(nodes: np.ndarray, edges: np.ndarray, total: int) -> torch.Tensor:
+    """[V|E ; E|V] sorted by (row 0, row 1) with duplicates dropped == torch_sparse.coalesce(edge_index, None, total, total)."""
+    row0 = np.concatenate([nodes, edges]).astype(np.int64)
+    row1 = np.concatenate([edges, nodes]).astype(np.int64)
+    key = np.unique(row0 * total + row1)
+    return torch.from_numpy(np.stack([key // total, key % total]))
+
+
+def load_le_dataset(path: str, dataset: str):
+    """`<path>/<dataset>/<dataset>.content` + `.edges` -> namespace(x [n_x, F] f32, edge_index, y [n_x] i64, n_x,
+    num_hyperedges), equal to the reference's load_LE_dataset (ids are remapped to their row position in .content; the
+    reference does it with a Python dict + map over every incidence, here with one argsort + searchsorted)."""
+    content = np.loadtxt(os.path.join(path, dataset, dataset + '.content'), dtype=np.float64, ndmin=2)
+    ids = content[:, 0].astype(np.int64)
+    labels = content[:, -1].astype(np.int64)
+    feats = content[:, 1:-1].astype(np.float32)
+    raw = np.loadtxt(os.path.join(path, dataset, dataset + '.edges'), dtype=np.int64, ndmin=2)
+    order = np.argsort(ids, kind='stable')
+    pos = np.searchsorted(ids[order], raw.reshape(-1))
+    if np.any(pos >= ids.size) or np.any(ids[order][np.minimum(pos, ids.size - 1)] != raw.reshape(-1)):
+        raise ValueError('%s.edges refers to ids that %s.content does not list' % (dataset, dataset))
+    mapped = order[pos].reshape(raw.shape)
+    nodes, edges = mapped[:, 0], mapped[:, 1]
+    if nodes.max() != edges.min() - 1 or np.unique(mapped).size != mapped.max() + 1:
+        raise ValueError('node / hyperedge ids must be consecutive with nodes first (reference asserts the same)')
+    n_x = int(nodes.max()) + 1
+    n_he = int(edges.max()) - n_x + 1
+    return SimpleNamespace(x=torch.from_numpy(feats[:n_x].copy()), y=torch.from_numpy(labels[:n_x].copy()),
+                           edge_index=_coalesced_star(nodes, edges, n_x + n_he), n_x=n_x, num_hyperedges=n_he)
+
+
+def load_cornell_dataset(path: str, dataset: str, feature_noise: float = 0.1, feature_dim: Optional[int] = None,
+                         generator: Optional[np.random.Generator] = None):
+    """`node-labels-<dataset>.txt` + `hyperedges-<dataset>.txt` -> namespace(x, edge_index, y, n_x, num_hyperedges) as
+    the reference's load_cornell_dataset: node ids shifted to start at 0, hyperedge ids n_x, n_x+1, ... in line order."""
+    labels = np.loadtxt(os.path.join(path, dataset, 'node-labels-%s.txt' % dataset), dtype=np.int64, ndmin=1)
+    n_x = labels.size
+    n_cls = int(labels.max())
+    feats = np.zeros((n_x, n_cls if feature_dim is None else max(feature_dim, n_cls)), dtype=np.float64)
+    feats[np.arange(n_x), labels - 1] = 1
+    rng = generator if generator is not None else np.random.default_rng()
+    feats = rng.normal(feats, feature_noise, feats.shape)
+    with open(os.path.join(path, dataset, 'hyperedges-%s.txt' % dataset)) as f:
+        lines = [ln for ln in f.read().split('\n') if ln]
+    sizes = np.fromiter((ln.count(',') + 1 for ln in lines), dtype=np.int64, count=len(lines))
+    nodes = np.array(','.join(lines).split(','), dtype=np.int64)
+    nodes = nodes - nodes.min()
+    edges = np.repeat(np.arange(n_x, n_x + len(lines), dtype=np.int64), sizes)
+    total = int(max(nodes.max(), edges.max())) + 1
+    return SimpleNamespace(x=torch.from_numpy(feats.astype(np.float32)), y=torch.from_numpy(labels.copy()),
+                           edge_index=_coalesced_star(nodes, edges, total), n_x=n_x, num_hyperedges=len(lines))
 
 
 def _to_numpy(t: torch.Tensor):

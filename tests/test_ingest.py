@@ -64,3 +64,47 @@ def test_cache_to_device_feeds_preprocessing(tmp_path):
     assert d.edge_index.is_cuda
     ei, norm, tot = P.preprocess(d.edge_index, d.n_x, d.num_hyperedges)
     assert tot == c['totedges'] and ei.shape == c['with_loops'].shape
+
+
+# --- the two text formats, against the reference's own loaders (dev container only: needs the raw zip + shims) ---------
+def _extract(tmp_path, members):
+    with zipfile.ZipFile(RAW_ZIP) as z:
+        for src, dst in members:
+            os.makedirs(os.path.dirname(str(tmp_path / dst)), exist_ok=True)
+            with open(str(tmp_path / dst), 'wb') as f:
+                f.write(z.read('AllSet_all_raw_data/' + src))
+
+
+def _reference_loaders():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+    import ref_harness
+    return ref_harness.load().loaders, ref_harness._quiet
+
+
+@pytest.mark.skipif(not os.path.isfile(RAW_ZIP), reason='reference raw data not present')
+def test_le_loader_equals_reference(tmp_path):
+    _extract(tmp_path, [('zoo/zoo.content', 'zoo/zoo.content'), ('zoo/zoo.edges', 'zoo/zoo.edges')])
+    loaders, quiet = _reference_loaders()
+    with quiet():
+        ref = loaders.load_LE_dataset(path=str(tmp_path), dataset='zoo')
+    mine = ingest.load_le_dataset(str(tmp_path), 'zoo')
+    assert mine.n_x == int(ref.n_x) and mine.num_hyperedges == int(ref.num_hyperedges)
+    assert torch.equal(mine.edge_index, ref.edge_index) and torch.equal(mine.y, ref.y)
+    torch.testing.assert_close(mine.x, ref.x, rtol=0, atol=0)
+
+
+@pytest.mark.skipif(not os.path.isfile(RAW_ZIP), reason='reference raw data not present')
+def test_cornell_loader_equals_reference(tmp_path):
+    name = 'house-committees'
+    _extract(tmp_path, [('%s/node-labels-%s.txt' % (name, name), '%s/node-labels-%s.txt' % (name, name)),
+                        ('%s/hyperedges-%s.txt' % (name, name), '%s/hyperedges-%s.txt' % (name, name))])
+    loaders, quiet = _reference_loaders()
+    with quiet():
+        ref = loaders.load_cornell_dataset(path=str(tmp_path), dataset=name, feature_noise=0.0)
+    mine = ingest.load_cornell_dataset(str(tmp_path), name, feature_noise=0.0)
+    assert mine.n_x == int(ref.n_x) and mine.num_hyperedges == int(ref.num_hyperedges)
+    assert torch.equal(mine.edge_index, ref.edge_index) and torch.equal(mine.y, ref.y)
+    torch.testing.assert_close(mine.x, ref.x, rtol=0, atol=0)            # noise 0: one-hot of the label on both sides
+    noisy = ingest.load_cornell_dataset(str(tmp_path), name, feature_noise=0.5, feature_dim=10)
+    assert noisy.x.shape == (mine.n_x, 10) and 0.3 < float((noisy.x - torch.nn.functional.pad(mine.x, (0, 10 - mine.x.shape[1]))).std()) < 0.7
