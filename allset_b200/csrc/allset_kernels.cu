@@ -364,11 +364,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#if defined(ALLSET_STREAM_COPY) && ALLSET_STREAM_COPY == 1
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+#endif
 #ifndef ALLSET_L2_HINTS
 #define ALLSET_L2_HINTS 1
 #endif
@@ -1016,15 +1018,12 @@ __device__ __forceinline__ void pma_accumulate(const T* __restrict__ v, const fl
         raw[k] = CH::zero();
         a[k] = -INFINITY;
         if (u + k < n && active) {
-          a[k] = __ldg(score + (size_t)idx * (size_t)H + h);
+          a[k] = leaky(__ldg(score + (size_t)idx * (size_t)H + h), slope);   // padding slots stay -inf for any slope
           raw[k] = CH::load(v + (size_t)idx * (size_t)d + feat);
         }
       }
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        a[k] = leaky(a[k], slope);   // leaky(-inf) stays -inf (slope > 0)
-        bm = fmaxf(bm, a[k]);
-      }
+      for (int k = 0; k < U; ++k) bm = fmaxf(bm, a[k]);
       const float m_new = fmaxf(m, bm);
       const float c = (m == -INFINITY) ? 0.f : expf(m - m_new);
       l *= c;
@@ -1799,23 +1798,16 @@ int launch_stream(const StreamPlan& p, const T* x, const int* rowptr, const int*
   if (peers.n > 0) {
     if (WEIGHTED) return fail(ALLSET_EUNSUPPORTED, "segreduce_fwd_bcast: per-incidence weights are not supported");
     auto kern = segreduce_stream_kernel<T, LB, false, true>;
-    static size_t configured = 0;                               // per instantiation
-    if (configured < p.smem) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-      if (e != cudaSuccess) return fail(ALLSET_ECUDA, "segreduce_stream: smem opt-in: %s", cudaGetErrorString(e));
-      configured = p.smem;
-    }
+    // the opt-in is per DEVICE and this process may drive several: set it on every launch (a host-side table write)
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return fail(ALLSET_ECUDA, "segreduce_stream: smem opt-in: %s", cudaGetErrorString(e));
     kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(x, rowptr, col, w, sscale, n_tgt, d, mean, p.seg_per_warp,
                                                       p.stages, out, peers);
     return ALLSET_OK;
   }
   auto kern = segreduce_stream_kernel<T, LB, WEIGHTED, false>;
-  static size_t configured = 0;                                 // per instantiation
-  if (configured < p.smem) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-    if (e != cudaSuccess) return fail(ALLSET_ECUDA, "segreduce_stream: smem opt-in: %s", cudaGetErrorString(e));
-    configured = p.smem;
-  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e != cudaSuccess) return fail(ALLSET_ECUDA, "segreduce_stream: smem opt-in: %s", cudaGetErrorString(e));
   kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(x, rowptr, col, w, sscale, n_tgt, d, mean, p.seg_per_warp,
                                                     p.stages, out, peers);
   return ALLSET_OK;
@@ -1863,14 +1855,9 @@ template <typename T, int LB>
 int launch_pma_stream(const StreamPlan& p, const T* v, const float* score, const float* seed, const int* rowptr,
                       const int* col, long long n_tgt, int H, int C, float slope, T* out, float* stats,
                       const PeerOuts& peers, cudaStream_t st, long long v_pitch, long long s_pitch) {
-  static size_t configured[2] = {0, 0};
-  const int b = peers.n > 0 ? 1 : 0;
-  auto kern = b ? pma_stream_kernel<T, LB, true> : pma_stream_kernel<T, LB, false>;
-  if (configured[b] < p.smem) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-    if (e != cudaSuccess) return fail(ALLSET_ECUDA, "pma_stream: smem opt-in: %s", cudaGetErrorString(e));
-    configured[b] = p.smem;
-  }
+  auto kern = peers.n > 0 ? pma_stream_kernel<T, LB, true> : pma_stream_kernel<T, LB, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);   // per device
+  if (e != cudaSuccess) return fail(ALLSET_ECUDA, "pma_stream: smem opt-in: %s", cudaGetErrorString(e));
   kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(v, score, seed, rowptr, col, n_tgt, H, C, slope, p.seg_per_warp,
                                                     p.stages, out, stats, peers,
                                                     v_pitch > 0 ? v_pitch : (long long)LB * 32,
@@ -2225,7 +2212,8 @@ static int pma_fwd_impl(const void* v, const float* score, const float* seed, in
                   s_pitch % 16 != 0))
     return fail(ALLSET_EINVAL, "pma_fwd_strided: pitches must cover a row / a score record and be multiples of 16");
   if (H <= 0 || C <= 0 || n_tgt < 0 || n_long < 0) return fail(ALLSET_EINVAL, "pma_fwd: bad size");
-  if (!(slope > 0.f)) return fail(ALLSET_EINVAL, "pma_fwd: negative_slope must be > 0");
+  if (!(slope == slope) || slope > 3.0e38f || slope < -3.0e38f)   // the reference's PMA takes any finite slope, 0 included
+    return fail(ALLSET_EINVAL, "pma_fwd: negative_slope must be finite");
   if (n_tgt >= INT32_MAX) return fail(ALLSET_ERANGE, "pma_fwd: rows do not fit int32");
   if (n_tgt == 0) return ALLSET_OK;
   if (seed == nullptr || rowptr == nullptr || out == nullptr || (n_long > 0 && long_ids == nullptr))

@@ -75,7 +75,7 @@ class Incidence(object):
 
     def __init__(self, by_tgt: Csr, by_src: Csr):
         self.by_tgt, self.by_src = by_tgt, by_src
-        self._ones_cache = {}
+        self._resized = {}
 
     @property
     def n_src(self) -> int:
@@ -124,19 +124,45 @@ class Incidence(object):
         by_tgt = self.by_src if n_tgt is None else self.by_src.head(n_tgt)
         return Incidence(by_tgt, self.by_tgt)
 
-    def weights_all_one(self, norm: torch.Tensor) -> bool:
-        """True when the per-incidence weights are all exactly 1 (the reference default `data.norm =
-        ones_like(edge_index[0])`, src/preprocessing.py:453-454) so the multiply can be skipped.  Cached per
-        (storage, version); costs one sync the first time a given tensor is seen."""
-        key = (norm.data_ptr(), norm._version, norm.numel(), norm.dtype)
-        hit = self._ones_cache.get(key)
+    def with_n_src(self, n_src: int) -> 'Incidence':
+        """The same incidence list over a source table of `n_src` rows (>= max(src)+1).  SetGNN needs it when trailing
+        nodes belong to no hyperedge: the E->V output then has max(node)+1 < N rows (torch_scatter's implicit size,
+        SURVEY Appendix A) and feeds the next layer's V->E, which the reference -- a plain gather -- accepts."""
+        if n_src == self.n_src:
+            return self
+        hit = self._resized.get(n_src)
         if hit is None:
-            hit = bool((norm == 1).all().item()) if norm.numel() > 0 else True
-            if len(self._ones_cache) > 8:
-                self._ones_cache.clear()
-            self._ones_cache[key] = hit
+            if n_src > self.n_src:
+                raise ValueError('x has %d rows but the incidence list was built for %d source rows' % (n_src, self.n_src))
+            s = self.by_src
+            if n_src < self.n_src and int(s.rowptr[n_src]) != s.nnz:
+                raise IndexError('incidence list refers to source rows beyond the %d rows of x' % n_src)
+            t = Csr.__new__(Csr)
+            t.__dict__.update(self.by_tgt.__dict__)
+            t.n_src = int(n_src)
+            hit = self._resized[n_src] = Incidence(t, s.head(n_src))
         return hit
 
+    def weights_all_one(self, norm: torch.Tensor) -> bool:
+        """True when the per-incidence weights are all exactly 1 so the multiply can be skipped.  Only INTEGER weights
+        take the shortcut -- the reference default `data.norm = ones_like(edge_index[0])` is int64
+        (src/preprocessing.py:453-454); float weights (deg_half_sym, `Importance * norm`) always go through the weighted
+        kernel.  The verdict is cached ON the tensor object with its `_version` (one sync the first time): a cache keyed
+        on the storage address would be fooled by the allocator handing the same address to a later temporary."""
+        if norm.is_floating_point() or norm.is_complex():
+            return False
+        tagged = getattr(norm, _ONES_ATTR, None)
+        if tagged is not None and tagged[0] == norm._version:
+            return tagged[1]
+        hit = bool((norm == 1).all().item()) if norm.numel() > 0 else True
+        try:
+            setattr(norm, _ONES_ATTR, (norm._version, hit))
+        except Exception:  # noqa  (tensor subclasses without a __dict__)
+            pass
+        return hit
+
+
+_ONES_ATTR = '_allset_all_one'
 
 # ------------------------------------------------------------------------------------------------------------
 # lookup for layers called with a plain `edge_index` tensor

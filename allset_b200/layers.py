@@ -102,6 +102,8 @@ class MLP(nn.Module):
     def _tc_ok(self, x) -> bool:
         if self.tc_dtype != torch.bfloat16 or torch.is_grad_enabled() or len(self.lins) != 2:
             return False
+        if self.training and self.dropout > 0:       # the fused kernel has no dropout between the Linears (MC dropout,
+            return False                             # no-grad forwards in train mode): take the path that applies it
         if not (x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16)):
             return False
         d = x.shape[1]
@@ -134,7 +136,7 @@ class MLP(nn.Module):
 
 def _resolve(edge_index, n_src: int) -> Incidence:
     if isinstance(edge_index, Incidence):
-        return edge_index
+        return edge_index.with_n_src(n_src)
     if not isinstance(edge_index, Tensor):
         raise TypeError('edge_index must be a [2, nnz] tensor or an allset_b200.Incidence')
     if not edge_index.is_cuda:

@@ -96,6 +96,16 @@ def choose_ranges(rowptr: torch.Tensor, parts: int, row_weight: int = 0, toleran
     return balanced_ranges(rowptr, parts, row_weight)
 
 
+def range_shapes(rowptr: torch.Tensor, ranges: Sequence[Tuple[int, int]]) -> List[Tuple[int, int]]:
+    """(rows, longest segment) of every range of a CSR -- one host sync, at partition time."""
+    n = int(rowptr.numel()) - 1
+    if n <= 0:
+        return [(0, 0) for _ in ranges]
+    lens = (rowptr[1:] - rowptr[:-1])
+    longest = torch.stack([lens[lo:hi].max() if hi > lo else lens.new_zeros(()) for lo, hi in ranges]).tolist()
+    return [(hi - lo, int(m)) for (lo, hi), m in zip(ranges, longest)]
+
+
 class ReplicatedRows(object):
     """A [rows, d] feature buffer replicated on every rank of the group, allocated in SYMMETRIC memory
     (torch.distributed._symmetric_memory) so that each rank holds peer-mapped pointers to all replicas: the fused
@@ -159,6 +169,12 @@ class ShardedIncidence(object):
         self.v_ranges = choose_ranges(s.rowptr, world, row_weight)
         self.e_lo, self.e_hi = self.e_ranges[rank]
         self.v_lo, self.v_hi = self.v_ranges[rank]
+        # (rows, longest segment) of EVERY rank's range, per direction: whether a direction takes the fused-exchange
+        # kernel must be the same answer on all ranks (a rank that fell back to NCCL while its peers wait on the
+        # symmetric-memory barrier would hang), so it is decided from these tables, never from the local slice alone.
+        # Every rank holds the full rowptr, so no collective is needed to agree.
+        self.e_shapes = range_shapes(t.rowptr, self.e_ranges)
+        self.v_shapes = range_shapes(s.rowptr, self.v_ranges)
         if world == 1:
             self.e_csr, self.v_csr = t, s
         else:
@@ -167,43 +183,45 @@ class ShardedIncidence(object):
             rp, col, p0 = slice_csr(s.rowptr, s.col, self.v_lo, self.v_hi)
             self.v_csr = Csr(rp, col, s.perm[p0:p0 + col.numel()], self.v_hi - self.v_lo, self.n_e)
 
+    def fused_ok(self, direction: str, x_src, out_full) -> bool:
+        """Whether EVERY rank's range of `direction` ('e': V->E, 'v': E->V) is taken by the fused-exchange stream
+        kernel for rows shaped like x_src.  Pure function of (graph, world, dtype, width): identical on all ranks."""
+        from . import _lib
+        if self.world == 1 or not isinstance(out_full, ReplicatedRows):
+            return False
+        shapes = self.e_shapes if direction == 'e' else self.v_shapes
+        return all(_lib.fused_exchange_eligible(x_src.dtype, x_src.shape[1], rows, longest) for rows, longest in shapes)
+
     # -- AllDeepSets ------------------------------------------------------------------------------------------
-    def _reduce(self, csr, x_src, out_full, lo, hi, mean):
+    def _reduce(self, direction, csr, x_src, out_full, lo, hi, mean):
         """Reduce this rank's target range into rows [lo, hi) of the replicated buffer.  `out_full` is a plain tensor
         (exchange = a later all-gather) or a ReplicatedRows (exchange fused into the kernel's epilogue).  Returns True
-        when the exchange has already been issued by the kernel."""
+        when the exchange has already been issued by the kernel -- the same value on every rank (`fused_ok`); a fused
+        launch the library then rejects raises instead of silently diverging from the peers."""
         from . import _lib
-        if isinstance(out_full, ReplicatedRows) and self.world > 1 and \
-                (csr.long_ids is None or _lib.stream_takes_long_segments(x_src, csr.n_tgt, csr.max_len)):
-            try:
-                _lib.segreduce_fwd_bcast(x_src, csr.rowptr, csr.col, csr.n_tgt, mean, out_full.tensor[lo:hi],
-                                         out_full.peer_ptrs(lo))
-                return True
-            except _lib.Unsupported:
-                pass
+        if self.fused_ok(direction, x_src, out_full):
+            _lib.segreduce_fwd_bcast(x_src, csr.rowptr, csr.col, csr.n_tgt, mean, out_full.tensor[lo:hi],
+                                     out_full.peer_ptrs(lo))
+            return True
         t = out_full.tensor if isinstance(out_full, ReplicatedRows) else out_full
         _lib.segreduce_fwd(x_src, csr.rowptr, csr.col, csr.n_tgt, mean, long_ids=csr.long_ids,
                            long_threshold=csr.long_threshold, out=t[lo:hi], max_segment_len=csr.max_len)
         return False
 
     def v2e_reduce(self, x_v, x_e_full, mean: bool = False):
-        return self._reduce(self.e_csr, _plain(x_v), x_e_full, self.e_lo, self.e_hi, mean)
+        return self._reduce('e', self.e_csr, _plain(x_v), x_e_full, self.e_lo, self.e_hi, mean)
 
     def e2v_reduce(self, x_e, x_v_full, mean: bool = False):
-        return self._reduce(self.v_csr, _plain(x_e), x_v_full, self.v_lo, self.v_hi, mean)
+        return self._reduce('v', self.v_csr, _plain(x_e), x_v_full, self.v_lo, self.v_hi, mean)
 
     # -- AllSetTransformer ------------------------------------------------------------------------------------
-    def _pma(self, csr, v, score, seed, heads, out_full, lo, hi, slope):
+    def _pma(self, direction, csr, v, score, seed, heads, out_full, lo, hi, slope):
         from . import _lib
         C = v.shape[1] // heads
-        if isinstance(out_full, ReplicatedRows) and self.world > 1 and \
-                (csr.long_ids is None or _lib.stream_takes_long_segments(v, csr.n_tgt, csr.max_len)):
-            try:
-                _lib.pma_fwd_bcast(v, score, seed, heads, C, slope, csr.rowptr, csr.col, csr.n_tgt,
-                                   out_full.tensor[lo:hi], out_full.peer_ptrs(lo))
-                return True
-            except _lib.Unsupported:
-                pass
+        if heads % 4 == 0 and self.fused_ok(direction, v, out_full):
+            _lib.pma_fwd_bcast(v, score, seed, heads, C, slope, csr.rowptr, csr.col, csr.n_tgt,
+                               out_full.tensor[lo:hi], out_full.peer_ptrs(lo))
+            return True
         t = out_full.tensor if isinstance(out_full, ReplicatedRows) else out_full
         _lib.pma_fwd(v, score, seed, heads, C, slope, csr.rowptr, csr.col, csr.n_tgt, want_stats=False,
                      long_ids=csr.long_ids, long_threshold=csr.long_threshold, out=t[lo:hi],
@@ -211,10 +229,10 @@ class ShardedIncidence(object):
         return False
 
     def v2e_pma(self, v_v, score_v, seed, heads, out_e_full, slope: float = 0.2):
-        return self._pma(self.e_csr, _plain(v_v), score_v, seed, heads, out_e_full, self.e_lo, self.e_hi, slope)
+        return self._pma('e', self.e_csr, _plain(v_v), score_v, seed, heads, out_e_full, self.e_lo, self.e_hi, slope)
 
     def e2v_pma(self, v_e, score_e, seed, heads, out_v_full, slope: float = 0.2):
-        return self._pma(self.v_csr, _plain(v_e), score_e, seed, heads, out_v_full, self.v_lo, self.v_hi, slope)
+        return self._pma('v', self.v_csr, _plain(v_e), score_e, seed, heads, out_v_full, self.v_lo, self.v_hi, slope)
 
     # -- exchanges --------------------------------------------------------------------------------------------
     def gather_e(self, x_e_full, fused: bool = False):

@@ -10,13 +10,17 @@ by the E->V segmented reduce over every vertex (AllDeepSets, aggregate='add' as 
 d=128, bf16 rows / fp32 accumulate.  Workload = BASELINE.json configs[3]'s graph (synthetic |V|=10M, |E|=2M,
 hyperedge size 1+Poisson(29), nnz~60M, seed 1234) -- the 10M-vertex / 2M-hyperedge synthetic the north_star target
 is quoted on; it fits one B200.  With N > 1 the SAME graph is hyperedge-sharded (V->E) / vertex-sharded (E->V) over
-N ranks with an all-gather of X_e and of the updated X_v inside every step (strong scaling).
+N ranks (strong scaling).  The exchange of X_e between the two directions is inside every step.  The updated X_v is
+left vertex-sharded by default (last layer: the next operator is row-parallel); `--replicate-xv` adds north_star's
+per-layer replication of X_v to every step, and BOTH modes are timed in every multi-GPU run (`other_mode`).
 
 JSON line (rank 0): value = |E| * K / t (device-timed, inputs resident in HBM, max over ranks); e2e = same metric
 through the public API with the vertex features starting in pinned HOST memory and the result read back to the host
 every step; roofline = the segmented-reduce kernel's algorithmic bytes / its CUDA-event duration against
-MEASURED_PEAKS.json; cpu_baseline = the reference's CPU op sequence (oracle port: index_select -> norm*x_j ->
-scatter_add_, fp32) on a bounded sample of the same graph distribution on this box's host cores.
+MEASURED_PEAKS.json (`traffic` is the DRAM byte count of the committed ncu capture of the same launch, read from
+profiles/traffic.json -- static, labelled as such); cpu_baseline = the reference's CPU op sequence (oracle port:
+index_select -> norm*x_j -> scatter_add_, fp32) on a 1/10-scale graph of the same distribution on this box's host
+cores, with the full half-layer pair (f_enc -> aggregate -> f_dec, twice) timed beside it.
 
 --impl reference times that CPU path alone (the reference has no GPU kernel of its own).
 Only the cpu_baseline / --impl reference legs import oracle/.
@@ -52,7 +56,7 @@ def parse_args():
     ap.add_argument('--heads', type=int, default=8)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
     ap.add_argument('--seed', type=int, default=1234)
-    ap.add_argument('--cpu-scale', type=int, default=20, help='CPU legs run on a 1/scale graph of the same distribution')
+    ap.add_argument('--cpu-scale', type=int, default=10, help='CPU legs run on a 1/scale graph of the same distribution')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-pma', action='store_true')
@@ -171,6 +175,41 @@ def cpu_time_pairs(a, steps, warmup, budget_s=None):
             break
     dt = time.perf_counter() - t0
     return m * done / dt, cores, desc, dt / done * 1e3, done
+
+
+def cpu_time_half_layers(a, steps=2, budget_s=15.0):
+    """The full AllDeepSets half-layer pair of the reference on the same sample graph: relu(f_enc) -> aggregate ->
+    relu(f_dec), V->E then E->V (oracle.half_nlh_conv = reference src/layers.py:623-636), random-init weights, eval."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import allset_oracle as O
+    n, m, node, he, x, norm, _ = cpu_sample_graph(a)
+    g = torch.Generator().manual_seed(a.seed + 7)
+    d = a.d
+    params = {}
+    for conv in ('V2EConvs.0.', 'E2VConvs.0.'):
+        for f in ('f_enc.', 'f_dec.'):
+            for i in range(2):
+                params[conv + f + 'lins.%d.weight' % i] = torch.randn(d, d, generator=g) / d ** 0.5
+                params[conv + f + 'lins.%d.bias' % i] = torch.zeros(d)
+                params[conv + f + 'normalizations.%d.weight' % i] = torch.ones(d)
+                params[conv + f + 'normalizations.%d.bias' % i] = torch.zeros(d)
+
+    def pair():
+        with torch.no_grad():
+            xe = O.half_nlh_conv(params, 'V2EConvs.0.', x, node, he, norm, 'sum', attention=False)
+            return O.half_nlh_conv(params, 'E2VConvs.0.', xe, he, node, norm, 'sum', attention=False)
+
+    pair()
+    done, t0 = 0, time.perf_counter()
+    for _ in range(steps):
+        pair()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
+    return {'value': m / dt, 'unit': UNIT, 'ms_per_pair_on_sample': dt * 1e3, 'steps': done,
+            'what': 'reference half layers (LN->Linear->ReLU->LN->Linear, relu, aggregate, same again) x2, fp32, eval'}
 
 
 def run_reference(a):
@@ -524,7 +563,7 @@ def run_b200(a):
             tr = json.load(open(traffic_path))
             if tr.get('workload') == workload_name(a):
                 roofline['traffic'] = tr.get('dram_bytes_per_launch')
-                roofline['traffic_source'] = tr.get('source')
+                roofline['traffic_source'] = 'static: ' + str(tr.get('source')) + ' (not re-measured in this run)'
         except Exception:
             pass
 
@@ -534,6 +573,10 @@ def run_b200(a):
         v, cores, desc, ms, done = cpu_time_pairs(a, steps=8, warmup=1, budget_s=20.0)
         cpu_baseline = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc,
                         'ms_per_step_on_sample': ms, 'steps': done}
+        try:
+            cpu_baseline['half_layer_pair'] = cpu_time_half_layers(a)
+        except Exception as exc:  # noqa  (reported, never fatal for the GPU line)
+            cpu_baseline['half_layer_pair'] = {'error': repr(exc)}
 
     if rank == 0:
         line = {

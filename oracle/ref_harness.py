@@ -5,8 +5,8 @@
   1. puts `oracle/shims/` (published-semantics stand-ins, see its README) and `/root/reference/src` on sys.path,
   2. restores `np.int` (removed in numpy >= 1.24; used at load_other_datasets.py:166),
   3. imports the reference's `layers`, `models`, `preprocessing`, `load_other_datasets` modules as they are.
-Used by `oracle/make_golden.py` (fixture generation) and by `tests/test_oracle_vs_reference.py` (skipped when the
-reference tree is absent).  Nothing here is reachable from `allset_b200/`.
+Used by the `oracle/make_golden*.py` fixture generators and by `tests/test_ingest.py` (skipped when the reference tree
+is absent).  Nothing here is reachable from `allset_b200/`.
 """
 from __future__ import annotations
 

@@ -200,7 +200,6 @@ def test_segment_reduce_widths(d, dtype):
     x = torch.randn(300, d, generator=g).to(dtype)
     w = torch.rand(4000, generator=g) + 0.5
     xr = x.float()
-    tol = FP32 if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2 * (1500 ** 0.5))
     for reduce, weight in (('sum', None), ('mean', None), ('add', w), ('mean', w)):
         out = ab().segment_reduce(x.to(dev()), inc, None if weight is None else weight.to(dev()), reduce)
         ref = O.aggregate_sum_mean(xr, src, tgt, weight, reduce)
@@ -210,7 +209,6 @@ def test_segment_reduce_widths(d, dtype):
         else:
             # output is the bf16 rounding of an fp32 accumulation of exactly-represented inputs
             torch.testing.assert_close(out.float().cpu(), ref, rtol=1e-2, atol=1e-2)
-    assert tol
 
 
 def test_segment_reduce_fp32_short_segments_match_sequential_sum_exactly():
