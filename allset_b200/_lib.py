@@ -160,6 +160,7 @@ def long_segments(rowptr: torch.Tensor, n_tgt: int, threshold: int) -> Optional[
 # d=256): reducing 4096-row segments inside one warp's stream is 18-36 % slower than bucketing them for the CTA
 # kernels (5.0-5.8 ms vs 4.3 ms), so only segments up to ~1.5 average warp chunks stay inline.
 STREAM_MAX_SEGMENT = 2048
+LONG_SEGMENT_BUCKET = 1024       # = graph.LONG_SEGMENT_THRESHOLD: longer segments are bucketed for the CTA kernels
 
 
 def stream_takes_long_segments(t: torch.Tensor, n_tgt: int, max_len: int) -> bool:
@@ -167,6 +168,18 @@ def stream_takes_long_segments(t: torch.Tensor, n_tgt: int, max_len: int) -> boo
     if max_len > STREAM_MAX_SEGMENT or t.dim() != 2:
         return False
     return bool(lib().allset_stream_eligible(_dtype_code(t), t.shape[1], n_tgt))
+
+
+def fused_exchange_eligible(dtype: torch.dtype, d: int, n_tgt: int, longest_segment: int) -> bool:
+    """Whether a rank whose range has `n_tgt` target rows (longest segment `longest_segment`) takes the
+    fused-exchange stream kernel for [*, d] rows of `dtype`.  A pure function of its arguments: every rank evaluates it
+    for EVERY rank's range and fuses only if all do (allset_b200.sharding.ShardedIncidence.fused_ok)."""
+    code = F32 if dtype == torch.float32 else BF16 if dtype == torch.bfloat16 else None
+    if code is None or n_tgt <= 0:
+        return False
+    if longest_segment > LONG_SEGMENT_BUCKET and longest_segment > STREAM_MAX_SEGMENT:
+        return False
+    return bool(lib().allset_stream_eligible(code, d, n_tgt))
 
 
 def segreduce_fwd(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, mean: bool,
