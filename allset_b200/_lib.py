@@ -42,6 +42,11 @@ SIGNATURES = {
     'allset_bias_act_norm': (_c.c_int, [_p, _p, _c.c_int, _p, _p, _p, _f32, _i64, _i32, _p, _p, _p]),
     'allset_bias_act_norm_bwd_blocks': (_i32, [_i64]),
     'allset_bias_act_norm_bwd': (_c.c_int, [_p, _p, _p, _c.c_int, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
+    'allset_rowop_supported': (_c.c_int, [_i32]),
+    'allset_rowop_fwd': (_c.c_int, [_p, _c.c_int, _p, _c.c_int, _p, _p, _p, _f32, _c.c_int, _f32, _c.c_uint64, _i64, _i32,
+                                    _p, _c.c_int, _p, _p]),
+    'allset_rowop_bwd': (_c.c_int, [_p, _c.c_int, _p, _c.c_int, _p, _c.c_int, _p, _p, _p, _p, _c.c_int, _f32, _c.c_uint64,
+                                    _i64, _i32, _p, _p, _p, _p]),
     'allset_mlp2_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _c.c_int, _i64, _i32,
                                    _p, _c.c_int, _i64, _p, _p]),
     'allset_pma_fwd_strided': (_c.c_int, [_p, _i64, _p, _i64, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64, _p, _p, _p]),
@@ -242,6 +247,70 @@ def bias_act_norm(x: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bo
                                               _ptr(beta), float(eps), rows, d, _ptr(out), _ptr(stats), _stream()),
                    'allset_bias_act_norm')
     return (out, stats) if want_stats else out
+
+
+ROWOP_WIDTHS = (64, 128, 256, 512, 1024)
+
+
+def rowop_fwd(x: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+              residual: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
+              beta: Optional[torch.Tensor] = None, eps: float = 1e-5, relu_out: bool = False, drop_p: float = 0.0,
+              seed: int = 0, out_dtype: Optional[torch.dtype] = None, want_stats: bool = False,
+              out: Optional[torch.Tensor] = None):
+    """out = dropout_p(relu_out(LayerNorm(residual + relu(x + bias)))), every stage optional, ONE pass; x / residual
+    fp32 or bf16 (same dtype), out fp32 or bf16, parameters and statistics fp32 (allset_rowop_fwd)."""
+    _need(x, 'x')
+    _need(bias, 'bias', torch.float32, optional=True)
+    _need(residual, 'residual', x.dtype, optional=True)
+    _need(gamma, 'gamma', torch.float32, optional=True)
+    _need(beta, 'beta', torch.float32, optional=True)
+    if x.dim() != 2:
+        raise ValueError('x must be [rows, d]')
+    rows, d = x.shape
+    if (bias is not None and bias.numel() != d) or (gamma is not None and gamma.numel() != d) or \
+            (beta is not None and beta.numel() != d) or (residual is not None and residual.shape != x.shape):
+        raise ValueError('rowop: shape mismatch')
+    out_dtype = out_dtype or x.dtype
+    if out is None:
+        out = torch.empty((rows, d), dtype=out_dtype, device=x.device)
+    else:
+        _need(out, 'out', out_dtype)
+        if tuple(out.shape) != (rows, d):
+            raise ValueError('out must be [rows, d]')
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if (want_stats and gamma is not None) else None
+    if rows > 0:
+        with torch.cuda.device(x.device):
+            _check(lib().allset_rowop_fwd(_ptr(x), _dtype_code(x), _ptr(bias), 1 if relu else 0, _ptr(residual),
+                                          _ptr(gamma), _ptr(beta), float(eps), 1 if relu_out else 0, float(drop_p),
+                                          int(seed) & 0xFFFFFFFFFFFFFFFF, rows, d, _ptr(out), _dtype_code(out),
+                                          _ptr(stats), _stream()), 'allset_rowop_fwd')
+    return (out, stats) if want_stats else out
+
+
+def rowop_bwd(dy: torch.Tensor, x: torch.Tensor, bias: Optional[torch.Tensor], relu: bool,
+              residual: Optional[torch.Tensor], gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
+              stats: Optional[torch.Tensor], relu_out: bool, drop_p: float, seed: int, want_dres: bool):
+    """-> (dx, dres | None, dgamma, dbeta, dbias): dx / dres in dy's dtype; the column sums (fp32) come from per-CTA
+    partials summed here (deterministic)."""
+    _need(dy, 'dy')
+    _need(x, 'x')
+    rows, d = x.shape
+    if tuple(dy.shape) != (rows, d):
+        raise ValueError('dy must match x')
+    dx = torch.empty((rows, d), dtype=dy.dtype, device=x.device)
+    dres = torch.empty_like(dx) if want_dres else None
+    if rows == 0:
+        z = torch.zeros(d, device=x.device)
+        return dx, dres, z, z.clone(), z.clone()
+    blocks = lib().allset_bias_act_norm_bwd_blocks(rows)
+    partial = torch.empty((blocks, 3, d), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().allset_rowop_bwd(_ptr(dy), _dtype_code(dy), _ptr(x), _dtype_code(x), _ptr(bias), 1 if relu else 0,
+                                      _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(stats), 1 if relu_out else 0,
+                                      float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, rows, d, _ptr(dx), _ptr(dres),
+                                      _ptr(partial), _stream()), 'allset_rowop_bwd')
+    sums = partial.sum(dim=0)
+    return dx, dres, sums[0], sums[1], sums[2]
 
 
 BIAS_ACT_NORM_BWD_WIDTHS = (128, 256, 512, 1024)

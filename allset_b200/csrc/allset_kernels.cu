@@ -33,6 +33,7 @@
 #include <cstring>
 
 #include "allset_b200.h"
+#include "rowop.cuh"
 
 namespace {
 
@@ -2111,6 +2112,71 @@ int allset_bias_act_norm_bwd(const float* dy, const float* x, const float* bias,
   else
     bias_act_norm_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, x, bias, relu, residual, gamma, stats, rows, dx, dres, partial);
   return check_launch("bias_act_norm_bwd");
+}
+
+// ---- rowop: mixed-precision row glue with dropout, forward + backward (rowop.cuh) --------------------------------
+namespace {
+bool rowop_width_ok(int32_t d) { return d == 64 || d == 128 || d == 256 || d == 512 || d == 1024; }
+void rowop_dropout(float p, unsigned* thr16, float* keep_scale) {
+  long t = lroundf(p * 65536.f);
+  if (t < 0) t = 0;
+  if (t > 65535) t = 65535;
+  *thr16 = (unsigned)t;
+  *keep_scale = 65536.f / (float)(65536 - t);        // 1 / (1 - p) for the p that is actually applied
+}
+}  // namespace
+
+int allset_rowop_supported(int32_t d) { return rowop_width_ok(d) ? 1 : 0; }
+
+int allset_rowop_fwd(const void* x, int x_dtype, const float* bias, int relu, const void* residual, const float* gamma,
+                     const float* beta, float eps, int relu_out, float drop_p, uint64_t seed, int64_t rows, int32_t d,
+                     void* out, int out_dtype, float* stats, void* stream) {
+  if (rows < 0 || d <= 0) return fail(ALLSET_EINVAL, "rowop_fwd: bad size");
+  if (bad_dtype(x_dtype) || bad_dtype(out_dtype)) return fail(ALLSET_EINVAL, "rowop_fwd: dtype must be 0 (f32) or 1 (bf16)");
+  if (!(drop_p >= 0.f) || drop_p >= 1.f) return fail(ALLSET_EINVAL, "rowop_fwd: dropout p must be in [0, 1)");
+  if (rows == 0) return ALLSET_OK;
+  if (x == nullptr || out == nullptr) return fail(ALLSET_EINVAL, "rowop_fwd: null pointer");
+  if (beta != nullptr && gamma == nullptr) return fail(ALLSET_EINVAL, "rowop_fwd: beta without gamma");
+  const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)gamma |
+                         (uintptr_t)beta;
+  if (!rowop_width_ok(d) || bits % 16 != 0 || (uintptr_t)stats % 8 != 0)
+    return fail(ALLSET_EUNSUPPORTED, "rowop_fwd: needs d in {64,128,256,512,1024} and 16-byte aligned rows");
+  rowop::FwdArgs a{x, bias, relu, residual, gamma, beta, eps, 1.f, 0u, seed, rows, out, stats, relu_out};
+  if (drop_p > 0.f) rowop_dropout(drop_p, &a.thr16, &a.keep_scale);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  using bf16 = __nv_bfloat16;
+  if (x_dtype == ALLSET_F32 && out_dtype == ALLSET_F32) rowop::launch_fwd<float, float>(a, d, st);
+  else if (x_dtype == ALLSET_F32) rowop::launch_fwd<float, bf16>(a, d, st);
+  else if (out_dtype == ALLSET_F32) rowop::launch_fwd<bf16, float>(a, d, st);
+  else rowop::launch_fwd<bf16, bf16>(a, d, st);
+  return check_launch("rowop_fwd");
+}
+
+int allset_rowop_bwd(const void* dy, int g_dtype, const void* x, int x_dtype, const float* bias, int relu,
+                     const void* residual, const float* gamma, const float* beta, const float* stats, int relu_out,
+                     float drop_p, uint64_t seed, int64_t rows, int32_t d, void* dx, void* dres, float* partial,
+                     void* stream) {
+  if (rows < 0 || d <= 0) return fail(ALLSET_EINVAL, "rowop_bwd: bad size");
+  if (bad_dtype(x_dtype) || bad_dtype(g_dtype)) return fail(ALLSET_EINVAL, "rowop_bwd: dtype must be 0 (f32) or 1 (bf16)");
+  if (!(drop_p >= 0.f) || drop_p >= 1.f) return fail(ALLSET_EINVAL, "rowop_bwd: dropout p must be in [0, 1)");
+  if (rows == 0) return ALLSET_OK;
+  if (dy == nullptr || x == nullptr || dx == nullptr || partial == nullptr)
+    return fail(ALLSET_EINVAL, "rowop_bwd: null pointer");
+  if (gamma != nullptr && stats == nullptr) return fail(ALLSET_EINVAL, "rowop_bwd: stats required with gamma");
+  const uintptr_t bits = (uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)bias | (uintptr_t)residual |
+                         (uintptr_t)gamma | (uintptr_t)dres | (uintptr_t)partial;
+  if (!rowop_width_ok(d) || bits % 16 != 0 || (uintptr_t)stats % 8 != 0)
+    return fail(ALLSET_EUNSUPPORTED, "rowop_bwd: needs d in {64,128,256,512,1024} and 16-byte aligned rows");
+  rowop::BwdArgs a{dy, x, bias, relu, residual, gamma, stats, 1.f, 0u, seed, rows, dx, dres, partial, beta, relu_out};
+  if (drop_p > 0.f) rowop_dropout(drop_p, &a.thr16, &a.keep_scale);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)allset_bias_act_norm_bwd_blocks(rows);
+  using bf16 = __nv_bfloat16;
+  if (g_dtype == ALLSET_F32 && x_dtype == ALLSET_F32) rowop::launch_bwd<float, float>(a, d, blocks, st);
+  else if (g_dtype == ALLSET_F32) rowop::launch_bwd<float, bf16>(a, d, blocks, st);
+  else if (x_dtype == ALLSET_F32) rowop::launch_bwd<bf16, float>(a, d, blocks, st);
+  else rowop::launch_bwd<bf16, bf16>(a, d, blocks, st);
+  return check_launch("rowop_bwd");
 }
 
 int allset_mlp2_fwd(const void* x, int x_dtype, const float* ln0_gamma, const float* ln0_beta, float ln0_eps,

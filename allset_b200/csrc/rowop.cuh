@@ -1,0 +1,326 @@
+// rowop.cuh -- row-wise dense glue with mixed-precision I/O, dropout and a fused backward (included by
+// allset_kernels.cu inside its anonymous namespace).
+//
+//   z = residual + act(x + bias);   y = LayerNorm_{gamma,beta}(z);   out = dropout_p(act2(y))    (each stage optional)
+//
+// This is what sits between the Linears of the reference's MLP (reference src/layers.py:571-579: Linear -> ReLU ->
+// norm -> dropout) and around PMA's rFF (src/layers.py:153-157), as ONE pass over the rows forward and ONE pass
+// backward, with bf16 or fp32 rows on either side (fp32 statistics and parameters).  The training path of the bf16 mode
+// is "bf16 tensor-core GEMM -> rowop -> GEMM -> rowop" forward and the mirrored chain backward; ATen spends a bias kernel,
+// a ReLU kernel, a LayerNorm kernel (1.67 ms per [1M,128] rows measured) and a dropout kernel per stage, each with an
+// autograd-saved copy.
+//
+// Layout: one warp per row, the row in registers.  d = 32 * NPL, NPL in {2,4,8,16,32}; a lane owns NCH chunks of
+// CE = min(NPL, 4) consecutive elements, chunk c of lane l = columns (c*32 + l)*CE ..+CE, so every warp access is one
+// contiguous 32*CE*sizeof(T)-byte piece.
+//
+// Dropout is counter-based: element (row, col) is kept iff a 16-bit slice of mix64(seed, row * d/4 + col/4) >= p*65536,
+// so the backward pass regenerates the mask instead of reading one (torch's dropout saves a bool mask: +1 byte per
+// element each way).  Statistically equivalent to F.dropout, not the same stream of random numbers.
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace rowop {
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx) {
+  uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+template <typename T, int CE>
+struct Vec;                                     // CE consecutive elements of type T <-> CE floats
+
+template <int CE>
+struct Vec<float, CE> {
+  __device__ static __forceinline__ void load(const float* p, float (&f)[CE]) {
+    if (CE == 4) { const float4 v = __ldcs(reinterpret_cast<const float4*>(p)); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+    else { const float2 v = __ldcs(reinterpret_cast<const float2*>(p)); f[0] = v.x; f[1] = v.y; }
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&f)[CE]) {
+    if (CE == 4) *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    else *reinterpret_cast<float2*>(p) = make_float2(f[0], f[1]);
+  }
+};
+
+template <int CE>
+struct Vec<bf16, CE> {
+  __device__ static __forceinline__ void load(const bf16* p, float (&f)[CE]) {
+    if (CE == 4) {
+      const uint2 v = __ldcs(reinterpret_cast<const uint2*>(p));
+      f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+      f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    } else {
+      const unsigned v = __ldcs(reinterpret_cast<const unsigned*>(p));
+      f[0] = __uint_as_float(v << 16); f[1] = __uint_as_float(v & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ void store(bf16* p, const float (&f)[CE]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
+    if (CE == 4) {
+      const __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
+      *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b));
+    } else {
+      *reinterpret_cast<unsigned*>(p) = *reinterpret_cast<const unsigned*>(&a);
+    }
+  }
+};
+
+template <int CE>
+__device__ __forceinline__ void load_param(const float* p, float (&f)[CE]) {
+  if (CE == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+  else { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); f[0] = v.x; f[1] = v.y; }
+}
+
+// keep-mask bits of the CE elements of one chunk (bit k set = keep element k)
+template <int CE>
+__device__ __forceinline__ unsigned keep_bits(uint64_t seed, long long row, int d, int col, unsigned thr16) {
+  // one 64-bit hash per 4 consecutive columns; CE == 2 chunks use the low or high half of it
+  const uint64_t h = mix64(seed, (uint64_t)row * (uint64_t)(d >> 2) + (uint64_t)(col >> 2));
+  unsigned bits = 0;
+#pragma unroll
+  for (int k = 0; k < CE; ++k) {
+    const int q = (CE == 4) ? k : ((col & 2) + k);
+    bits |= (((unsigned)(h >> (16 * q)) & 0xffffu) >= thr16 ? 1u : 0u) << k;
+  }
+  return bits;
+}
+
+struct FwdArgs {
+  const void* x; const float* bias; int relu; const void* residual; const float* gamma; const float* beta; float eps;
+  float keep_scale; unsigned thr16; uint64_t seed; long long rows; void* out; float* stats; int relu_out;
+};
+
+template <typename TIn, typename TOut, int NPL>
+__global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
+  constexpr int D = 32 * NPL;
+  constexpr int CE = NPL < 4 ? NPL : 4;
+  constexpr int NCH = NPL / CE;
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= a.rows) return;
+  const TIn* xr = static_cast<const TIn*>(a.x) + row * D;
+  float v[NCH][CE];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) Vec<TIn, CE>::load(xr + (c * 32 + lane) * CE, v[c]);
+  if (a.bias != nullptr) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float b[CE];
+      load_param<CE>(a.bias + (c * 32 + lane) * CE, b);
+#pragma unroll
+      for (int k = 0; k < CE; ++k) v[c][k] += b[k];
+    }
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int k = 0; k < CE; ++k) v[c][k] = fmaxf(v[c][k], 0.f);
+  }
+  if (a.residual != nullptr) {
+    const TIn* rr = static_cast<const TIn*>(a.residual) + row * D;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float r[CE];
+      Vec<TIn, CE>::load(rr + (c * 32 + lane) * CE, r);
+#pragma unroll
+      for (int k = 0; k < CE; ++k) v[c][k] += r[k];
+    }
+  }
+  if (a.gamma != nullptr) {
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int k = 0; k < CE; ++k) sum += v[c][k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int k = 0; k < CE; ++k) { const float t = v[c][k] - mean; sq += t * t; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.f / D) + a.eps);
+    if (a.stats != nullptr && lane == 0) *reinterpret_cast<float2*>(a.stats + row * 2) = make_float2(mean, rstd);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float g[CE], b[CE];
+      load_param<CE>(a.gamma + (c * 32 + lane) * CE, g);
+      if (a.beta != nullptr) load_param<CE>(a.beta + (c * 32 + lane) * CE, b);
+#pragma unroll
+      for (int k = 0; k < CE; ++k) v[c][k] = (v[c][k] - mean) * rstd * g[k] + (a.beta != nullptr ? b[k] : 0.f);
+    }
+  }
+  if (a.relu_out) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int k = 0; k < CE; ++k) v[c][k] = fmaxf(v[c][k], 0.f);
+  }
+  if (a.thr16 != 0u) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const unsigned keep = keep_bits<CE>(a.seed, row, D, (c * 32 + lane) * CE, a.thr16);
+#pragma unroll
+      for (int k = 0; k < CE; ++k) v[c][k] = ((keep >> k) & 1u) ? v[c][k] * a.keep_scale : 0.f;
+    }
+  }
+  TOut* orow = static_cast<TOut*>(a.out) + row * D;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) Vec<TOut, CE>::store(orow + (c * 32 + lane) * CE, v[c]);
+}
+
+struct BwdArgs {
+  const void* dy; const void* x; const float* bias; int relu; const void* residual; const float* gamma;
+  const float* stats; float keep_scale; unsigned thr16; uint64_t seed; long long rows; void* dx; void* dres;
+  float* partial; const float* beta; int relu_out;
+};
+
+// Backward.  A warp walks rows with a grid stride so that every lane owns fixed columns: d(gamma), d(beta), d(bias)
+// accumulate in registers over all rows of the warp, are combined per CTA through shared memory and written as ONE
+// partial row per CTA (partial[cta][3][D]; the host sums over CTAs: deterministic, no atomics).
+//   g0 = dy * keep / (1-p) * [y > 0 if act2];  zh = (z - mean) * rstd;  y = zh * gamma + beta;  g = g0 * gamma
+//   dz = rstd * (g - mean_d(g) - zh * mean_d(g * zh))        (dz = g0 without LayerNorm)
+//   d(residual) = dz;   d(x) = dz * [x + bias > 0]  (relu)  else dz
+template <typename TG, typename TX, int NPL>
+__global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
+  constexpr int D = 32 * NPL;
+  constexpr int CE = NPL < 4 ? NPL : 4;
+  constexpr int NCH = NPL / CE;
+  __shared__ float red[8][3][32 * CE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nwarps = (long long)gridDim.x * 8;
+  float bsv[NCH][CE], gmv[NCH][CE], btv[NCH][CE], dgam[NCH][CE], dbet[NCH][CE], dbia[NCH][CE];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+    for (int k = 0; k < CE; ++k) { bsv[c][k] = 0.f; gmv[c][k] = 1.f; btv[c][k] = 0.f; dgam[c][k] = dbet[c][k] = dbia[c][k] = 0.f; }
+    if (a.bias != nullptr) load_param<CE>(a.bias + (c * 32 + lane) * CE, bsv[c]);
+    if (a.gamma != nullptr) load_param<CE>(a.gamma + (c * 32 + lane) * CE, gmv[c]);
+    if (a.relu_out && a.beta != nullptr) load_param<CE>(a.beta + (c * 32 + lane) * CE, btv[c]);
+  }
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < a.rows; row += nwarps) {
+    const TX* xr = static_cast<const TX*>(a.x) + row * D;
+    const TG* dyr = static_cast<const TG*>(a.dy) + row * D;
+    float mean = 0.f, rstd = 1.f;
+    if (a.gamma != nullptr) {
+      const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats + row * 2));
+      mean = st.x; rstd = st.y;
+    }
+    float pre[NCH][CE], g[NCH][CE], zh[NCH][CE];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * CE;
+      float z[CE], g0[CE];
+      Vec<TX, CE>::load(xr + col, pre[c]);
+      Vec<TG, CE>::load(dyr + col, g0);
+#pragma unroll
+      for (int k = 0; k < CE; ++k) {
+        pre[c][k] += bsv[c][k];
+        z[k] = a.relu ? fmaxf(pre[c][k], 0.f) : pre[c][k];
+      }
+      if (a.residual != nullptr) {
+        float r[CE];
+        Vec<TX, CE>::load(static_cast<const TX*>(a.residual) + row * D + col, r);
+#pragma unroll
+        for (int k = 0; k < CE; ++k) z[k] += r[k];
+      }
+      if (a.thr16 != 0u) {
+        const unsigned keep = keep_bits<CE>(a.seed, row, D, col, a.thr16);
+#pragma unroll
+        for (int k = 0; k < CE; ++k) g0[k] = ((keep >> k) & 1u) ? g0[k] * a.keep_scale : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < CE; ++k) {
+        zh[c][k] = (z[k] - mean) * rstd;
+        if (a.relu_out && !(zh[c][k] * gmv[c][k] + btv[c][k] > 0.f)) g0[k] = 0.f;
+        g[c][k] = g0[k] * gmv[c][k];
+        if (a.gamma != nullptr) {
+          dgam[c][k] += g0[k] * zh[c][k];
+          dbet[c][k] += g0[k];
+          s1 += g[c][k];
+          s2 += g[c][k] * zh[c][k];
+        }
+      }
+    }
+    if (a.gamma != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      s1 *= (1.f / D);
+      s2 *= (1.f / D);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * CE;
+      float dz[CE], dp[CE];
+#pragma unroll
+      for (int k = 0; k < CE; ++k) {
+        dz[k] = a.gamma != nullptr ? rstd * (g[c][k] - s1 - zh[c][k] * s2) : g[c][k];
+        dp[k] = (a.relu && !(pre[c][k] > 0.f)) ? 0.f : dz[k];
+        dbia[c][k] += dp[k];
+      }
+      if (a.dres != nullptr) Vec<TG, CE>::store(static_cast<TG*>(a.dres) + row * D + col, dz);
+      Vec<TG, CE>::store(static_cast<TG*>(a.dx) + row * D + col, dp);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+    for (int k = 0; k < CE; ++k) {
+      red[warp][0][lane * CE + k] = dgam[c][k];
+      red[warp][1][lane * CE + k] = dbet[c][k];
+      red[warp][2][lane * CE + k] = dbia[c][k];
+    }
+    __syncthreads();
+    if (warp < 3) {                                 // warp q sums quantity q over the 8 warps
+#pragma unroll
+      for (int k = 0; k < CE; ++k) {
+        float s = red[0][warp][lane * CE + k];
+#pragma unroll
+        for (int w2 = 1; w2 < 8; ++w2) s += red[w2][warp][lane * CE + k];
+        a.partial[((size_t)blockIdx.x * 3 + warp) * D + (c * 32 + lane) * CE + k] = s;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename TIn, typename TOut>
+bool launch_fwd(const FwdArgs& a, int d, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((a.rows * 32 + 255) / 256);
+  switch (d) {
+    case 64: fwd_kernel<TIn, TOut, 2><<<blocks, 256, 0, st>>>(a); return true;
+    case 128: fwd_kernel<TIn, TOut, 4><<<blocks, 256, 0, st>>>(a); return true;
+    case 256: fwd_kernel<TIn, TOut, 8><<<blocks, 256, 0, st>>>(a); return true;
+    case 512: fwd_kernel<TIn, TOut, 16><<<blocks, 256, 0, st>>>(a); return true;
+    case 1024: fwd_kernel<TIn, TOut, 32><<<blocks, 256, 0, st>>>(a); return true;
+    default: return false;
+  }
+}
+
+template <typename TG, typename TX>
+bool launch_bwd(const BwdArgs& a, int d, unsigned blocks, cudaStream_t st) {
+  switch (d) {
+    case 64: bwd_kernel<TG, TX, 2><<<blocks, 256, 0, st>>>(a); return true;
+    case 128: bwd_kernel<TG, TX, 4><<<blocks, 256, 0, st>>>(a); return true;
+    case 256: bwd_kernel<TG, TX, 8><<<blocks, 256, 0, st>>>(a); return true;
+    case 512: bwd_kernel<TG, TX, 16><<<blocks, 256, 0, st>>>(a); return true;
+    case 1024: bwd_kernel<TG, TX, 32><<<blocks, 256, 0, st>>>(a); return true;
+    default: return false;
+  }
+}
+
+}  // namespace rowop

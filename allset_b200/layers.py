@@ -66,37 +66,61 @@ class MLP(nn.Module):
             if not isinstance(norm, nn.Identity):
                 norm.reset_parameters()
 
-    def forward(self, x, final_relu: bool = False, out_dtype: Optional[torch.dtype] = None):
-        """`final_relu` (extension, default off = reference behaviour) applies the ReLU that every caller on the path
-        wraps around the MLP (`F.relu(self.f_enc(x))`, reference src/layers.py:631,634) inside the last fused pass.
-        `out_dtype` (extension) is honoured by the tcgen05 path only; other paths return x.dtype."""
+    def forward(self, x, final_relu: bool = False, out_dtype: Optional[torch.dtype] = None, final_dropout: float = 0.0):
+        """Extensions (defaults = reference behaviour): `final_relu` applies the ReLU every caller on the path wraps
+        around the MLP (`F.relu(self.f_enc(x))`, reference src/layers.py:631,634) and `final_dropout` the dropout that
+        follows it (:632, training only), both inside the last fused pass; `out_dtype` is honoured by the fused paths."""
         if self._tc_ok(x):
             l0, l1 = self.normalizations
-            return _lib.mlp2_fwd(x.contiguous(), self.lins[0].weight, self.lins[0].bias, self.lins[1].weight,
-                                 self.lins[1].bias, self._ln_tuple(l0), self._ln_tuple(l1), final_relu,
-                                 out_dtype or torch.float32)
+            y = _lib.mlp2_fwd(x.contiguous(), self.lins[0].weight, self.lins[0].bias, self.lins[1].weight,
+                              self.lins[1].bias, self._ln_tuple(l0), self._ln_tuple(l1), final_relu,
+                              out_dtype or torch.float32)
+            return F.dropout(y, p=final_dropout, training=True) if (final_dropout > 0 and self.training) else y
+        if self._chain_ok(x):
+            return self._forward_chain(x, final_relu, out_dtype, final_dropout)
         if x.dtype != self.lins[0].weight.dtype:
             x = x.to(self.lins[0].weight.dtype)
-        if self._fused_ok(x):
-            y, bias = self.forward_fused_open(x)
-            return ops.bias_act_norm(y, bias, relu=final_relu)
         x = self.normalizations[0](x)
         for i, lin in enumerate(self.lins[:-1]):
             x = F.relu(lin(x), inplace=True)
             x = self.normalizations[i + 1](x)
             x = F.dropout(x, p=self.dropout, training=self.training)
         x = self.lins[-1](x)
-        return F.relu(x) if final_relu else x
+        if final_relu:
+            x = F.relu(x)
+        return F.dropout(x, p=final_dropout, training=self.training) if final_dropout > 0 else x
 
-    # -- fast path: cuBLAS GEMMs WITHOUT bias + ONE fused pass (bias, ReLU, LayerNorm) between them, forward and
-    #    backward (allset_bias_act_norm[_bwd]); dropout stays a separate ATen op ---------------------------------------
-    def _fused_ok(self, x) -> bool:
+    # -- chain path (training AND inference, fp32 or bf16 mode): bias-free GEMMs with ONE fused rowop pass between them
+    #    (bias, ReLU, LayerNorm, dropout -- forward and backward are each one kernel, allset_rowop_fwd / _bwd).  In bf16
+    #    mode the GEMMs take bf16 operands on the tensor cores and the activations between them are bf16; parameters,
+    #    LayerNorm statistics, gradients of the parameters and the rows handed to the next half layer stay fp32. ------
+    def compute_dtype(self) -> torch.dtype:
+        return torch.bfloat16 if self.tc_dtype == torch.bfloat16 else torch.float32
+
+    def _chain_ok(self, x) -> bool:
+        if not (x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16)):
+            return False
+        if x.shape[0] < ops.FUSED_DENSE_MIN_ROWS or self.lins[0].weight.dtype != torch.float32:
+            return False
         if not all(isinstance(n, (nn.LayerNorm, nn.Identity)) for n in self.normalizations):
             return False
-        widths = [lin.out_features for lin in self.lins]
-        if isinstance(self.normalizations[0], nn.LayerNorm):
-            widths.append(self.lins[0].in_features)
-        return all(ops.fused_dense_ok(x, w) for w in widths)
+        return all(lin.out_features in _lib.ROWOP_WIDTHS for lin in self.lins[:-1])
+
+    def _forward_chain(self, x, final_relu, out_dtype, final_dropout):
+        cd = self.compute_dtype()
+        io = x.dtype if out_dtype is None else out_dtype
+        p = self.dropout if self.training else 0.0
+        pf = final_dropout if self.training else 0.0
+        n0 = self.normalizations[0]
+        if isinstance(n0, nn.LayerNorm):
+            h = ops.rowop(x, gamma=n0.weight, beta=n0.bias, eps=n0.eps, out_dtype=cd)
+        else:
+            h = x if x.dtype == cd else x.to(cd)
+        for i, lin in enumerate(self.lins[:-1]):
+            n = self.normalizations[i + 1]
+            h = ops.rowop(ops.linear_nb(h, lin.weight), lin.bias, relu=True, drop_p=p, out_dtype=cd, **self._ln(n))
+        last = self.lins[-1]
+        return ops.rowop(ops.linear_nb(h, last.weight), last.bias, relu=final_relu, drop_p=pf, out_dtype=io)
 
     # -- tensor-core path: the whole two-layer MLP in one tcgen05 kernel (eval mode, bf16 operands) ---------------------
     def _tc_ok(self, x) -> bool:
@@ -122,16 +146,6 @@ class MLP(nn.Module):
         if isinstance(norm, nn.LayerNorm):
             return dict(gamma=norm.weight, beta=norm.bias, eps=norm.eps)
         return {}
-
-    def forward_fused_open(self, x):
-        """Everything up to the last Linear's GEMM: returns (y = h @ W_last^T WITHOUT bias, bias_last) so that the
-        caller can fold the bias, an activation, a residual and a LayerNorm into one pass (ops.bias_act_norm)."""
-        if isinstance(self.normalizations[0], nn.LayerNorm):
-            x = ops.bias_act_norm(x, **self._ln(self.normalizations[0]))
-        for i, lin in enumerate(self.lins[:-1]):
-            x = ops.bias_act_norm(F.linear(x, lin.weight), lin.bias, relu=True, **self._ln(self.normalizations[i + 1]))
-            x = F.dropout(x, p=self.dropout, training=self.training)
-        return F.linear(x, self.lins[-1].weight), self.lins[-1].bias
 
 
 def _resolve(edge_index, n_src: int) -> Incidence:
@@ -182,9 +196,11 @@ class PMA(nn.Module):
         self.ln1.reset_parameters()
         nn.init.xavier_uniform_(self.att_r)
 
-    def forward(self, x, edge_index, size=None, return_attention_weights=None, relu_out: bool = False):
-        """`relu_out` (extension, default off = reference behaviour): also apply the ReLU SetGNN.forward wraps around
-        every half layer (reference src/models.py:475,478), inside the fused tail kernel where there is one."""
+    def forward(self, x, edge_index, size=None, return_attention_weights=None, relu_out: bool = False,
+                out_dropout: float = 0.0):
+        """Extensions (defaults = reference behaviour): `relu_out` also applies the ReLU SetGNN.forward wraps around every
+        half layer (reference src/models.py:475,478) and `out_dropout` the dropout that follows it (:476,479, training
+        only), inside the last fused pass where there is one."""
         assert x.dim() == 2, 'Static graphs not supported in `GATConv`.'
         H, C = self.heads, self.hidden
         inc = _resolve(edge_index, x.size(0))
@@ -194,12 +210,14 @@ class PMA(nn.Module):
         seed = self.att_r.view(H, C)
         w_eff = (self.lin_K.weight.view(H, C, -1) * seed.unsqueeze(-1)).sum(dim=1)         # [H, in]
         b_eff = (self.lin_K.bias.view(H, C) * seed).sum(dim=1)                             # [H]
-        fused = self.rFF._fused_ok(x) and ops.fused_dense_ok(x, self.heads * self.hidden)
         want_alpha = isinstance(return_attention_weights, bool)
+        pdrop = out_dropout if self.training else 0.0
         out = None
         tc_v = self._tc_v_ok(x)
         tc_score = tc_v and H * H * C <= 1024               # w_eff must fit the kernel's 4 KB side buffer
-        score = None if tc_score else F.linear(x, w_eff, b_eff)                            # [n_src, H]
+        chain = self._chain_ok(x)
+        xf = x if x.dtype == w_eff.dtype else x.to(w_eff.dtype)
+        score = None if tc_score else F.linear(xf, w_eff, b_eff)                           # [n_src, H] fp32
         if tc_v:
             # bf16 mode: V = lin_V(x) as ONE tcgen05 kernel that writes the bf16 rows the aggregation gathers; the same
             # launch computes the fp32 scores in its producer warps (no second pass over x)
@@ -228,15 +246,18 @@ class PMA(nn.Module):
                     v = v.contiguous()
             else:
                 v, score = lin_v()
+        elif chain:
+            # training / fp32 mode at scale: bias-free GEMM (bf16 operands in bf16 mode) + one rowop pass that adds the
+            # bias and writes the rows in the storage dtype the aggregation gathers
+            cd = self.rFF.compute_dtype()
+            xb = x if x.dtype == cd else x.to(cd)
+            v = ops.rowop(ops.linear_nb(xb, self.lin_V.weight), self.lin_V.bias, out_dtype=self.agg_dtype or cd)
         else:
-            if fused:
-                x_V = ops.bias_act_norm(F.linear(x, self.lin_V.weight), self.lin_V.bias)
-            else:
-                x_V = self.lin_V(x)
+            x_V = self.lin_V(xf)
             v = x_V if self.agg_dtype is None else x_V.to(self.agg_dtype)
         if out is None:
             out, alpha = ops.pma_aggregate(v, score, self.att_r, inc, H, self.negative_slope, return_alpha=want_alpha)
-        applied_relu = False
+        applied = False
         if self.rFF._tc_ok(out):
             # bf16 mode: ln0 -> rFF -> ln1(residual + relu(.)) [-> the caller's ReLU] as ONE tcgen05 kernel reading the
             # aggregated rows in their storage dtype
@@ -244,21 +265,37 @@ class PMA(nn.Module):
             out = _lib.pma_tail_fwd(out.contiguous(), (self.ln0.weight, self.ln0.bias, self.ln0.eps), l0.weight, l0.bias,
                                     l1.weight, l1.bias, (self.ln1.weight, self.ln1.bias, self.ln1.eps),
                                     relu_final=relu_out, out_dtype=score.dtype)
-            applied_relu = relu_out
-        elif fused:
-            out = out.to(score.dtype)                                    # [n_tgt, H*C], seed already added
-            out = ops.bias_act_norm(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps)
-            y, bias = self.rFF.forward_fused_open(out)
-            out = ops.bias_act_norm(y, bias, relu=True, residual=out, gamma=self.ln1.weight, beta=self.ln1.bias,
-                                    eps=self.ln1.eps)                    # ln1(out + relu(rFF(out))), one pass
+            if pdrop > 0:
+                out = F.dropout(out, p=pdrop, training=True)
+            applied = True
+        elif chain and self.rFF._chain_ok(out):
+            cd = self.rFF.compute_dtype()
+            y = ops.rowop(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps, out_dtype=cd)   # ln0 (:155)
+            a = y
+            for lin in self.rFF.lins[:-1]:                                   # rFF: no norms, no dropout (:76-80)
+                a = ops.rowop(ops.linear_nb(a, lin.weight), lin.bias, relu=True, out_dtype=cd)
+            last = self.rFF.lins[-1]
+            out = ops.rowop(ops.linear_nb(a, last.weight), last.bias, relu=True, residual=y, gamma=self.ln1.weight,
+                            beta=self.ln1.bias, eps=self.ln1.eps, relu_out=relu_out, drop_p=pdrop,
+                            out_dtype=score.dtype)                           # ln1(y + relu(rFF(y))) [relu, dropout], one pass
+            applied = True
         else:
             out = self.ln0(out.to(score.dtype))
             out = self.ln1(out + F.relu(self.rFF(out)))
-        if relu_out and not applied_relu:
-            out = F.relu(out)
+        if not applied:
+            if relu_out:
+                out = F.relu(out)
+            if pdrop > 0:
+                out = F.dropout(out, p=pdrop, training=True)
         if want_alpha:
             return out, (edge_index, alpha)
         return out
+
+    def _chain_ok(self, x) -> bool:
+        d = self.heads * self.hidden
+        return (x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16)
+                and x.shape[0] >= ops.FUSED_DENSE_MIN_ROWS and d in _lib.ROWOP_WIDTHS
+                and self.lin_V.weight.dtype == torch.float32)
 
     # Packed [values | scores] records for the gather (allset_pma_fwd_strided) are OFF by default: measured on the
     # 10 M-vertex graph they are slower (4.03 vs 3.85 ms V->E) -- HBM fills L2 in 64-byte units, so a 288-byte record
@@ -327,19 +364,20 @@ class HalfNLHconv(nn.Module):
                 if isinstance(f, MLP):
                     f.tc_dtype = dtype if dtype == torch.bfloat16 else None
 
-    def forward(self, x, edge_index, norm, aggr='add', relu_out: bool = False):
-        """`relu_out` (extension): fold SetGNN.forward's `F.relu(conv(.))` (reference src/models.py:475,478) into the
-        layer -- the identity for a non-attention layer, which already ends in relu(f_dec(.))."""
+    def forward(self, x, edge_index, norm, aggr='add', relu_out: bool = False, out_dropout: float = 0.0):
+        """Extensions: `relu_out` folds SetGNN.forward's `F.relu(conv(.))` (reference src/models.py:475,478) into the layer
+        -- the identity for a non-attention layer, which already ends in relu(f_dec(.)) -- and `out_dropout` the dropout
+        SetGNN applies to the result (:476,479; training only)."""
         if self.attention:
-            return self.prop(x, edge_index, relu_out=relu_out)       # norm and aggr are ignored, as in the reference
+            return self.prop(x, edge_index, relu_out=relu_out, out_dropout=out_dropout)   # norm, aggr ignored (reference)
         if aggr is None:
             raise ValueError('aggr was not passed!')
         io_dtype = x.dtype
         if isinstance(self.f_enc, MLP):
-            x = self.f_enc(x, final_relu=True, out_dtype=self.agg_dtype)    # tcgen05 path writes the storage dtype
+            # relu(f_enc(x)) and the dropout behind it (:631-632) end in the storage dtype the aggregation gathers
+            x = self.f_enc(x, final_relu=True, out_dtype=self.agg_dtype, final_dropout=self.dropout)
         else:
-            x = F.relu(self.f_enc(x))
-        x = F.dropout(x, p=self.dropout, training=self.training)
+            x = F.dropout(F.relu(self.f_enc(x)), p=self.dropout, training=self.training)
         inc = _resolve(edge_index, x.size(0))
         weight = None
         if norm is not None and not (not norm.requires_grad and inc.weights_all_one(norm)):
@@ -347,9 +385,11 @@ class HalfNLHconv(nn.Module):
         xs = x if self.agg_dtype is None else x.to(self.agg_dtype)
         x = ops.segment_reduce(xs, inc, weight, aggr)
         if isinstance(self.f_dec, MLP):
-            if not self.f_dec._tc_ok(x):             # the tcgen05 path reads the storage dtype directly
+            if not (self.f_dec._tc_ok(x) or self.f_dec._chain_ok(x)):     # the fused paths read the storage dtype directly
                 x = x.to(io_dtype)
-            x = self.f_dec(x, final_relu=True, out_dtype=io_dtype)
+            x = self.f_dec(x, final_relu=True, out_dtype=io_dtype, final_dropout=out_dropout)
         else:
             x = F.relu(self.f_dec(x.to(io_dtype)))
+            if out_dropout > 0:
+                x = F.dropout(x, p=out_dropout, training=self.training)
         return x

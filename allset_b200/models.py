@@ -110,15 +110,11 @@ class SetGNN(nn.Module):
         return v2e, e2v
 
     def _half(self, conv, x, inc, norm):
-        """`F.relu(conv(x, ...))` of reference src/models.py:475,478.  A non-attention half layer already ends in
-        relu(f_dec(.)) (src/layers.py:634): the outer ReLU is the identity (value and gradient) and a full pass over
-        [rows, d], so it is skipped.  A PMA half layer ends in a LayerNorm: the ReLU is applied here, except in bf16
-        eval mode where it is folded into the fused tail kernel (a forward hook on the layer then sees post-ReLU rows)."""
-        if not conv.attention:
-            return conv(x, inc, norm, self.aggr)
-        if conv.agg_dtype == torch.bfloat16 and not torch.is_grad_enabled():
-            return conv(x, inc, norm, self.aggr, relu_out=True)
-        return F.relu(conv(x, inc, norm, self.aggr))
+        """`F.dropout(F.relu(conv(x, ...)))` of reference src/models.py:475-476,478-479 with the ReLU and the dropout
+        folded into the layer's last fused pass.  A non-attention half layer already ends in relu(f_dec(.))
+        (src/layers.py:634): the outer ReLU is the identity (value and gradient).  A PMA half layer ends in a LayerNorm:
+        the ReLU is applied by its tail kernel (a forward hook on the layer then sees post-ReLU, post-dropout rows)."""
+        return conv(x, inc, norm, self.aggr, relu_out=True, out_dropout=self.dropout)
 
     def forward(self, data):
         """data.x [N, F]; data.edge_index [2, nnz] int64 (row 0 node id, row 1 hyperedge id, any base);
@@ -146,9 +142,7 @@ class SetGNN(nn.Module):
         else:
             x = F.dropout(x, p=0.2, training=self.training)     # input dropout, hard-coded in the reference
             for i, _ in enumerate(self.V2EConvs):
-                x = self._half(self.V2EConvs[i], x, v2e, norm)                    # = F.relu(conv(.)), :475
-                x = F.dropout(x, p=self.dropout, training=self.training)
-                x = self._half(self.E2VConvs[i], x, e2v, norm)                    # :478
-                x = F.dropout(x, p=self.dropout, training=self.training)
+                x = self._half(self.V2EConvs[i], x, v2e, norm)                    # = dropout(relu(conv(.))), :475-476
+                x = self._half(self.E2VConvs[i], x, e2v, norm)                    # :478-479
             x = self.classifier(x)
         return x

@@ -184,3 +184,116 @@ def fused_dense_ok(x: torch.Tensor, width: int) -> bool:
     if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.shape[0] < FUSED_DENSE_MIN_ROWS:
         return False
     return (not torch.is_grad_enabled()) or width in _lib.BIAS_ACT_NORM_BWD_WIDTHS
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Training-path dense glue: rowop (fused forward AND backward, bf16 / fp32 rows, dropout) + bias-free Linear on the
+# tensor cores.  An MLP in bf16 mode is   rowop(LN) -> linear_nb -> rowop(bias, ReLU, LN, dropout) -> linear_nb ->
+# rowop(bias, ReLU, dropout)   forward and the mirrored chain backward, with bf16 activations in between.
+# ----------------------------------------------------------------------------------------------------------------------
+def _new_seed() -> int:
+    """Dropout seed drawn from torch's CPU generator: follows torch.manual_seed, no device sync."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+class _RowOp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, residual, gamma, beta, relu, eps, relu_out, drop_p, out_dtype):
+        x = x.contiguous()
+        res = None if residual is None else residual.contiguous()
+        seed = _new_seed() if drop_p > 0 else 0
+        out, stats = _lib.rowop_fwd(x, bias, relu, res, gamma, beta, eps, relu_out, drop_p, seed, out_dtype,
+                                    want_stats=True)
+        ctx.cfg = (relu, relu_out, drop_p, seed)
+        ctx.has = (bias is not None, residual is not None, gamma is not None, beta is not None)
+        ctx.save_for_backward(x, bias, res, gamma, beta, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, bias, res, gamma, beta, stats = ctx.saved_tensors
+        relu, relu_out, drop_p, seed = ctx.cfg
+        has_bias, has_res, has_gamma, has_beta = ctx.has
+        dx, dres, dgamma, dbeta, dbias = _lib.rowop_bwd(dy.contiguous(), x, bias, relu, res, gamma, beta, stats, relu_out,
+                                                        drop_p, seed, want_dres=has_res and ctx.needs_input_grad[2])
+        if dx.dtype != x.dtype:
+            dx = dx.to(x.dtype)
+        if dres is not None and dres.dtype != res.dtype:
+            dres = dres.to(res.dtype)
+        return (dx if ctx.needs_input_grad[0] else None,
+                dbias if has_bias and ctx.needs_input_grad[1] else None,
+                dres if has_res and ctx.needs_input_grad[2] else None,
+                dgamma if has_gamma and ctx.needs_input_grad[3] else None,
+                dbeta if has_beta and ctx.needs_input_grad[4] else None,
+                None, None, None, None, None)
+
+
+def rowop_ok(x: torch.Tensor) -> bool:
+    """[rows, d] rows the rowop kernels take: CUDA, fp32 / bf16, d in {64,128,256,512,1024}."""
+    return (x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16)
+            and x.shape[1] in _lib.ROWOP_WIDTHS)
+
+
+def rowop(x: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+          residual: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
+          beta: Optional[torch.Tensor] = None, eps: float = 1e-5, relu_out: bool = False, drop_p: float = 0.0,
+          out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Differentiable  dropout_p(relu_out(LayerNorm(residual + relu(x + bias))))  in one pass (reference
+    src/layers.py:571-579 between two Linears; :153-157 around PMA's rFF).  Widths the kernels do not take are composed
+    from ATen ops ON THE SAME DEVICE (odd widths such as a dataset's raw feature count or the class count)."""
+    if residual is not None and residual.dtype != x.dtype:
+        residual = residual.to(x.dtype)
+    if not rowop_ok(x):
+        y = x.float()
+        if bias is not None:
+            y = y + bias
+        if relu:
+            y = torch.relu(y)
+        if residual is not None:
+            y = y + residual.float()
+        if gamma is not None:
+            y = torch.nn.functional.layer_norm(y, (y.shape[-1],), gamma, beta, eps)
+        if relu_out:
+            y = torch.relu(y)
+        if drop_p > 0:
+            y = torch.nn.functional.dropout(y, drop_p, True)
+        return y.to(out_dtype or x.dtype)
+    if not torch.is_grad_enabled():
+        seed = _new_seed() if drop_p > 0 else 0
+        return _lib.rowop_fwd(x.contiguous(), bias, relu, None if residual is None else residual.contiguous(), gamma, beta,
+                              eps, relu_out, drop_p, seed, out_dtype)
+    return _RowOp.apply(x, bias, residual, gamma, beta, relu, eps, relu_out, drop_p, out_dtype)
+
+
+class _LinearNB(torch.autograd.Function):
+    """y = x @ W^T without bias, operands in `x.dtype` (bf16: tensor-core GEMM with fp32 accumulation; fp32: SGEMM), W
+    kept as the fp32 master parameter; dW is accumulated and returned in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        wc = w if w.dtype == x.dtype else w.to(x.dtype)
+        ctx.save_for_backward(x, wc)
+        ctx.w_dtype = w.dtype
+        return torch.mm(x, wc.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wc = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.mm(dy, wc) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if dy.dtype == torch.float32:
+                dw = torch.mm(dy.t(), x)
+            else:
+                dw = torch.mm(dy.t(), x, out_dtype=torch.float32)
+            if dw.dtype != ctx.w_dtype:
+                dw = dw.to(ctx.w_dtype)
+        return dx, dw
+
+
+def linear_nb(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """x [rows, in] (bf16 | fp32) @ w[out, in]^T -> [rows, out] in x.dtype; the bias is left to the rowop that follows."""
+    if not torch.is_grad_enabled():
+        return torch.mm(x, (w if w.dtype == x.dtype else w.to(x.dtype)).t())
+    return _LinearNB.apply(x, w)

@@ -180,6 +180,26 @@ int allset_bias_act_norm_bwd(const float* dy, const float* x, const float* bias,
                              const float* residual, const float* gamma, const float* stats,
                              int64_t rows, int32_t d, float* dx, float* dres, float* partial, void* stream);
 
+/* --- rowop: the same glue with mixed-precision rows, dropout and a backward for every width it takes -------------
+ *   z = residual + relu(x + bias);  y = LayerNorm(z);  out = dropout_p(relu_out(y))     (every stage optional)
+ * = what sits between the Linears of MLP.forward in TRAINING (src/layers.py:571-579: Linear -> ReLU -> norm -> dropout)
+ * and around PMA's rFF (src/layers.py:153-157), one pass forward and one pass backward, so that the Linears themselves
+ * can run as bf16 tensor-core GEMMs with bf16 activations in between.
+ *   x, residual [rows, d] x_dtype;  out [rows, d] out_dtype;  bias, gamma, beta [d] f32;  stats [rows, 2] f32 or NULL
+ *   d in {64, 128, 256, 512, 1024} (allset_rowop_supported), rows 16-byte aligned; ALLSET_EUNSUPPORTED otherwise.
+ *   drop_p in [0, 1): element (r, c) is kept iff a 16-bit slice of a counter hash of (seed, r, c) >= p * 65536 and
+ *   scaled by 1 / (1 - p) -- F.dropout's distribution, regenerated (not stored) by the backward pass from the same seed.
+ * Backward: dy [rows, d] g_dtype -> dx (and dres, or NULL) in g_dtype; partial [blocks, 3, d] f32 = per-CTA column sums
+ * of (d gamma, d beta, d bias), blocks = allset_bias_act_norm_bwd_blocks(rows), summed over dim 0 by the caller. */
+int allset_rowop_supported(int32_t d);
+int allset_rowop_fwd(const void* x, int x_dtype, const float* bias, int relu, const void* residual,
+                     const float* gamma, const float* beta, float eps, int relu_out, float drop_p, uint64_t seed,
+                     int64_t rows, int32_t d, void* out, int out_dtype, float* stats, void* stream);
+int allset_rowop_bwd(const void* dy, int g_dtype, const void* x, int x_dtype, const float* bias, int relu,
+                     const void* residual, const float* gamma, const float* beta, const float* stats, int relu_out,
+                     float drop_p, uint64_t seed, int64_t rows, int32_t d, void* dx, void* dres, float* partial,
+                     void* stream);
+
 /* Gradient w.r.t. the per-incidence weights (SetGNN.LearnMask, src/models.py:451-452):
  * grad_w[k] = tgt_scale[t] * <x[col[k], :], grad_out[t, :]>  for k in segment t (CSR order).
  * tgt_scale [n_tgt] fp32 or NULL (mean: 1/max(count,1)). */

@@ -17,5 +17,6 @@ timeout 600 python scripts/run_train.py --impl reference -- $CORA --runs 5 --cud
 timeout 600 python scripts/run_train.py --impl reference -- $CITE --runs 5 --cuda 0 2>$OUT/train_ref_gpu_citeseer.err | grep '^{' | tee $OUT/train_ref_gpu_citeseer.json
 echo "== training-step profile at config-3 size"
 timeout 600 python scripts/prof_train.py > $OUT/prof_train.txt 2>&1 ; tail -5 $OUT/prof_train.txt
+echo "== model bench" ; timeout 600 python scripts/model_bench.py 2>&1 | grep "^{" | tee $OUT/model_bench.jsonl
 echo "== bench" ; timeout 600 python bench.py --steps 30 --warmup 5 2>$OUT/bench.err | tee $OUT/bench.json ; tail -3 $OUT/bench.err
 ls -la $OUT

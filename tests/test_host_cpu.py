@@ -73,6 +73,8 @@ def test_ctypes_signatures_match_the_header_prototypes():
                     '%s: %r bound as %s' % (name, decl, ct)
             elif re.search(r'\bfloat\b', decl):
                 assert ct is ctypes.c_float, '%s: %r bound as %s' % (name, decl, ct)
+            elif re.search(r'\buint64_t\b', decl):
+                assert ct is ctypes.c_uint64, '%s: %r bound as %s' % (name, decl, ct)
             elif re.search(r'\bint64_t\b', decl):
                 assert ct is ctypes.c_int64, '%s: %r bound as %s' % (name, decl, ct)
             elif re.search(r'\bint32_t\b', decl):
