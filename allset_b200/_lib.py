@@ -16,7 +16,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('ALLSET_B200_LIB') or os.path.join(_HERE, 'liballset_b200.so')   # override: kernel tuning builds
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 F32, BF16 = 0, 1
 SUM, MEAN = 0, 1
@@ -31,14 +31,17 @@ SIGNATURES = {
     'allset_version': (_c.c_int, []),
     'allset_last_error': (_c.c_char_p, []),
     'allset_stream_eligible': (_c.c_int, [_c.c_int, _i32, _i64]),
+    'allset_pma_stream_eligible': (_c.c_int, [_c.c_int, _i32, _i32, _i64]),
+    'allset_stream_workspace_bytes': (_sz, [_i32]),
     'allset_csr_workspace_bytes': (_sz, [_i64, _i64]),
     'allset_csr_from_coo': (_c.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     'allset_long_segments_workspace_bytes': (_sz, [_i64]),
     'allset_long_segments': (_c.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
     'allset_segreduce_fwd': (_c.c_int, [_p, _c.c_int, _i64, _i32, _p, _p, _p, _p, _i64, _c.c_int,
-                                        _p, _i32, _i32, _p, _p]),
+                                        _p, _i32, _i32, _p, _p, _sz, _p]),
     'allset_segreduce_fwd_bcast': (_c.c_int, [_p, _c.c_int, _i64, _i32, _p, _p, _p, _p, _i64, _c.c_int,
-                                              _p, _c.POINTER(_c.c_void_p), _i32, _p]),
+                                              _p, _c.POINTER(_c.c_void_p), _i32, _p, _p, _sz, _p]),
+    'allset_push_rows': (_c.c_int, [_p, _i64, _i64, _c.POINTER(_c.c_void_p), _i32, _p, _p]),
     'allset_bias_act_norm': (_c.c_int, [_p, _p, _c.c_int, _p, _p, _p, _f32, _i64, _i32, _p, _p, _p]),
     'allset_bias_act_norm_bwd_blocks': (_i32, [_i64]),
     'allset_bias_act_norm_bwd': (_c.c_int, [_p, _p, _p, _c.c_int, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
@@ -49,15 +52,16 @@ SIGNATURES = {
                                     _i64, _i32, _p, _p, _p, _p]),
     'allset_mlp2_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _c.c_int, _i64, _i32,
                                    _p, _c.c_int, _i64, _p, _p]),
-    'allset_pma_fwd_strided': (_c.c_int, [_p, _i64, _p, _i64, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64, _p, _p, _p]),
+    'allset_pma_fwd_strided': (_c.c_int, [_p, _i64, _p, _i64, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64, _p, _p, _p, _sz,
+                                          _p]),
     'allset_pma_tail_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _f32, _c.c_int, _i64, _i32,
                                        _p, _c.c_int, _p, _p]),
     'allset_linear_score_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _p, _p, _i32, _i64, _i32, _p, _c.c_int, _i64, _p, _p, _p]),
     'allset_segreduce_bwd_w': (_c.c_int, [_p, _p, _c.c_int, _i32, _p, _p, _p, _i64, _p, _p]),
     'allset_pma_fwd': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
-                                  _p, _i32, _i32, _p, _p, _p]),
+                                  _p, _i32, _i32, _p, _p, _p, _sz, _p]),
     'allset_pma_fwd_bcast': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
-                                        _p, _p, _c.POINTER(_c.c_void_p), _i32, _p]),
+                                        _p, _p, _c.POINTER(_c.c_void_p), _i32, _p, _p, _sz, _p]),
     'allset_pma_alpha': (_c.c_int, [_p, _p, _i32, _f32, _p, _p, _i64, _p, _p]),
     'allset_rowdot_heads': (_c.c_int, [_p, _p, _p, _c.c_int, _i64, _i32, _i32, _p, _p]),
     'allset_pma_bwd': (_c.c_int, [_p, _p, _p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
@@ -161,36 +165,46 @@ def long_segments(rowptr: torch.Tensor, n_tgt: int, threshold: int) -> Optional[
 # ----------------------------------------------------------------------------------------------------------
 # AllDeepSets
 # ----------------------------------------------------------------------------------------------------------
-# Longest segment a single warp's stream is allowed to own.  Measured on a power-law graph (sizes ~ s^-2 up to 4096,
-# d=256): reducing 4096-row segments inside one warp's stream is 18-36 % slower than bucketing them for the CTA
-# kernels (5.0-5.8 ms vs 4.3 ms), so only segments up to ~1.5 average warp chunks stay inline.
-STREAM_MAX_SEGMENT = 2048
-LONG_SEGMENT_BUCKET = 1024       # = graph.LONG_SEGMENT_THRESHOLD: longer segments are bucketed for the CTA kernels
+# Workspace of the stream kernels (allset_stream_workspace_bytes): partial results + ready flags of the pieces of long
+# segments that are cut at warp-chunk boundaries.  Zero-initialised once, left zeroed by every launch; one per
+# (device, stream) because concurrent launches must not share it.
+_stream_ws = {}
 
 
-def stream_takes_long_segments(t: torch.Tensor, n_tgt: int, max_len: int) -> bool:
-    """True when the stream kernels handle this shape and the longest segment is short enough to stay inline."""
-    if max_len > STREAM_MAX_SEGMENT or t.dim() != 2:
-        return False
-    return bool(lib().allset_stream_eligible(_dtype_code(t), t.shape[1], n_tgt))
+def stream_workspace(device: torch.device, d: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    need = lib().allset_stream_workspace_bytes(int(d))
+    ws = _stream_ws.get(key)
+    if ws is None or ws.numel() < need:
+        with torch.cuda.device(device):
+            ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        _stream_ws[key] = ws
+    return ws
 
 
-def fused_exchange_eligible(dtype: torch.dtype, d: int, n_tgt: int, longest_segment: int) -> bool:
-    """Whether a rank whose range has `n_tgt` target rows (longest segment `longest_segment`) takes the
-    fused-exchange stream kernel for [*, d] rows of `dtype`.  A pure function of its arguments: every rank evaluates it
-    for EVERY rank's range and fuses only if all do (allset_b200.sharding.ShardedIncidence.fused_ok)."""
+def stream_eligible(dtype: torch.dtype, d: int, n_tgt: int, heads: int = 0) -> bool:
+    """Whether [*, d] rows of `dtype` reduced into n_tgt segments take the stream kernels (heads > 0: the PMA one).  With
+    their workspace those kernels handle segments of any length, so no long-segment bucketing is needed then."""
     code = F32 if dtype == torch.float32 else BF16 if dtype == torch.bfloat16 else None
-    if code is None or n_tgt <= 0:
+    if code is None or n_tgt <= 0 or d <= 0:
         return False
-    if longest_segment > LONG_SEGMENT_BUCKET and longest_segment > STREAM_MAX_SEGMENT:
-        return False
+    if heads > 0:
+        return d % heads == 0 and bool(lib().allset_pma_stream_eligible(code, heads, d // heads, n_tgt))
     return bool(lib().allset_stream_eligible(code, d, n_tgt))
+
+
+def fused_exchange_eligible(dtype: torch.dtype, d: int, n_tgt: int, heads: int = 0) -> bool:
+    """Whether a rank whose range has `n_tgt` target rows takes the fused-exchange stream kernel for [*, d] rows of
+    `dtype`.  A pure function of its arguments: every rank evaluates it for EVERY rank's range and fuses only if all do
+    (allset_b200.sharding.ShardedIncidence.fused_ok)."""
+    return stream_eligible(dtype, d, n_tgt, heads)
 
 
 def segreduce_fwd(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, mean: bool,
                   w: Optional[torch.Tensor] = None, src_scale: Optional[torch.Tensor] = None,
                   long_ids: Optional[torch.Tensor] = None, long_threshold: int = 0,
-                  out: Optional[torch.Tensor] = None, max_segment_len: int = 0) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, max_segment_len: int = 0, allow_stream: bool = True
+                  ) -> torch.Tensor:
     _need(x, 'x')
     _need(rowptr, 'rowptr', torch.int32)
     _need(col, 'col', torch.int32)
@@ -213,13 +227,16 @@ def segreduce_fwd(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tg
             raise ValueError('out must be [n_tgt, d]')
     if d == 0 or n_tgt == 0:
         return out
-    if long_ids is not None and max_segment_len and stream_takes_long_segments(x, n_tgt, max_segment_len):
-        long_ids = None
+    ws = None
+    if allow_stream and stream_eligible(x.dtype, d, n_tgt):
+        ws, long_ids = stream_workspace(x.device, d), None          # the stream kernel cuts long segments itself
+
     n_long = 0 if long_ids is None else long_ids.numel()
     with torch.cuda.device(x.device):
         _check(lib().allset_segreduce_fwd(_ptr(x), _dtype_code(x), n_src, d, _ptr(rowptr), _ptr(col), _ptr(w),
                                           _ptr(src_scale), n_tgt, MEAN if mean else SUM, _ptr(long_ids), n_long,
-                                          long_threshold, _ptr(out), _stream()), 'allset_segreduce_fwd')
+                                          long_threshold, _ptr(out), _ptr(ws), 0 if ws is None else ws.numel(), _stream()),
+               'allset_segreduce_fwd')
     return out
 
 
@@ -469,25 +486,32 @@ def _peer_array(peer_ptrs):
 
 def segreduce_fwd_bcast(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, mean: bool,
                         out: torch.Tensor, peer_ptrs, w: Optional[torch.Tensor] = None,
-                        src_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """segreduce_fwd whose epilogue also stores every reduced row into the same row of each peer replica.
+                        src_scale: Optional[torch.Tensor] = None, peer_mask: Optional[torch.Tensor] = None
+                        ) -> torch.Tensor:
+    """segreduce_fwd whose epilogue also sends every reduced row to the same row of each peer replica.
     `out` = this rank's row range inside its own replica; `peer_ptrs` = addresses (ints, peer-mapped device pointers)
-    of that same row range in the other ranks' replicas.  Raises Unsupported for shapes the stream kernel rejects."""
+    of that same row range in the other ranks' replicas; `peer_mask` [n_tgt] uint8 (bit j = peer j needs the row) or
+    None = all.  Raises Unsupported for shapes the stream kernel rejects."""
     _need(x, 'x')
     _need(rowptr, 'rowptr', torch.int32)
     _need(col, 'col', torch.int32)
     _need(out, 'out', x.dtype)
     _need(w, 'w', torch.float32, optional=True)
     _need(src_scale, 'src_scale', torch.float32, optional=True)
+    _need(peer_mask, 'peer_mask', torch.uint8, optional=True)
     n_src, d = x.shape
     if tuple(out.shape) != (n_tgt, d):
         raise ValueError('out must be [n_tgt, d]')
+    if peer_mask is not None and peer_mask.numel() != n_tgt:
+        raise ValueError('peer_mask must have one byte per target row')
     if n_tgt == 0:
         return out
+    ws = stream_workspace(x.device, d)
     with torch.cuda.device(x.device):
         code = lib().allset_segreduce_fwd_bcast(_ptr(x), _dtype_code(x), n_src, d, _ptr(rowptr), _ptr(col), _ptr(w),
                                                 _ptr(src_scale), n_tgt, MEAN if mean else SUM, _ptr(out),
-                                                _peer_array(peer_ptrs), len(peer_ptrs), _stream())
+                                                _peer_array(peer_ptrs), len(peer_ptrs), _ptr(peer_mask), _ptr(ws),
+                                                ws.numel(), _stream())
     if code == EUNSUPPORTED:
         raise Unsupported(lib().allset_last_error().decode())
     _check(code, 'allset_segreduce_fwd_bcast')
@@ -496,24 +520,44 @@ def segreduce_fwd_bcast(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor
 
 def pma_fwd_bcast(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: int, C: int, slope: float,
                   rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, out: torch.Tensor, peer_ptrs,
-                  stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  stats: Optional[torch.Tensor] = None, peer_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need(v, 'v')
     _need(score, 'score', torch.float32)
     _need(seed, 'seed', torch.float32)
     _need(out, 'out', v.dtype)
     _need(stats, 'stats', torch.float32, optional=True)
+    _need(peer_mask, 'peer_mask', torch.uint8, optional=True)
     if tuple(out.shape) != (n_tgt, H * C):
         raise ValueError('out must be [n_tgt, H*C]')
     if n_tgt == 0:
         return out
+    ws = stream_workspace(v.device, H * C)
     with torch.cuda.device(v.device):
         code = lib().allset_pma_fwd_bcast(_ptr(v), _ptr(score), _ptr(seed), _dtype_code(v), H, C, float(slope),
                                           _ptr(rowptr), _ptr(col), n_tgt, _ptr(out), _ptr(stats),
-                                          _peer_array(peer_ptrs), len(peer_ptrs), _stream())
+                                          _peer_array(peer_ptrs), len(peer_ptrs), _ptr(peer_mask), _ptr(ws), ws.numel(),
+                                          _stream())
     if code == EUNSUPPORTED:
         raise Unsupported(lib().allset_last_error().decode())
     _check(code, 'allset_pma_fwd_bcast')
     return out
+
+
+def push_rows(rows: torch.Tensor, peer_ptrs, peer_mask: Optional[torch.Tensor] = None) -> None:
+    """Send `rows` (this rank's [n, d] row range, a view into its own replica) to the same rows of the peer replicas
+    (`peer_ptrs`: peer-mapped addresses of that range); `peer_mask` [n] uint8 selects the peers per row."""
+    _need(rows, 'rows')
+    _need(peer_mask, 'peer_mask', torch.uint8, optional=True)
+    if rows.dim() != 2:
+        raise ValueError('rows must be [n, d]')
+    n, d = rows.shape
+    if peer_mask is not None and peer_mask.numel() != n:
+        raise ValueError('peer_mask must have one byte per row')
+    if n == 0 or len(peer_ptrs) == 0:
+        return
+    with torch.cuda.device(rows.device):
+        _check(lib().allset_push_rows(_ptr(rows), n, d * rows.element_size(), _peer_array(peer_ptrs), len(peer_ptrs),
+                                      _ptr(peer_mask), _stream()), 'allset_push_rows')
 
 
 def packed_pma_records(n_src: int, d: int, H: int, dtype: torch.dtype, device) -> tuple:
@@ -541,10 +585,11 @@ def pma_fwd_strided(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H:
     stats = torch.empty((n_tgt, H, 2), dtype=torch.float32, device=v.device) if want_stats else None
     if n_tgt == 0:
         return out, stats
+    ws = stream_workspace(v.device, H * C)
     with torch.cuda.device(v.device):
         code = lib().allset_pma_fwd_strided(_ptr(v), v.stride(0) * v.element_size(), _ptr(score), score.stride(0) * 4,
                                             _ptr(seed), _dtype_code(v), H, C, float(slope), _ptr(rowptr), _ptr(col),
-                                            n_tgt, _ptr(out), _ptr(stats), _stream())
+                                            n_tgt, _ptr(out), _ptr(stats), _ptr(ws), ws.numel(), _stream())
     if code == EUNSUPPORTED:
         raise Unsupported(lib().allset_last_error().decode())
     _check(code, 'allset_pma_fwd_strided')
@@ -571,7 +616,7 @@ def segreduce_bwd_w(x: torch.Tensor, grad_out: torch.Tensor, rowptr: torch.Tenso
 def pma_fwd(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: int, C: int, slope: float,
             rowptr: torch.Tensor, col: torch.Tensor, n_tgt: int, want_stats: bool = True,
             long_ids: Optional[torch.Tensor] = None, long_threshold: int = 0, out: Optional[torch.Tensor] = None,
-            max_segment_len: int = 0):
+            max_segment_len: int = 0, allow_stream: bool = True):
     """v [n_src, H*C], score [n_src, H] f32, seed [H*C] f32 -> (out [n_tgt, H*C], stats [n_tgt, H, 2] | None)."""
     _need(v, 'v')
     _need(score, 'score', torch.float32)
@@ -590,13 +635,15 @@ def pma_fwd(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, H: int, C:
     stats = torch.empty((n_tgt, H, 2), dtype=torch.float32, device=v.device) if want_stats else None
     if n_tgt == 0:
         return out, stats
-    if long_ids is not None and max_segment_len and H % 4 == 0 and stream_takes_long_segments(v, n_tgt, max_segment_len):
-        long_ids = None
+    ws = None
+    if allow_stream and stream_eligible(v.dtype, H * C, n_tgt, heads=H):
+        ws, long_ids = stream_workspace(v.device, H * C), None       # the stream kernel cuts long segments itself
+
     n_long = 0 if long_ids is None else long_ids.numel()
     with torch.cuda.device(v.device):
         _check(lib().allset_pma_fwd(_ptr(v), _ptr(score), _ptr(seed), _dtype_code(v), H, C, float(slope), _ptr(rowptr),
                                     _ptr(col), n_tgt, _ptr(long_ids), n_long, long_threshold, _ptr(out), _ptr(stats),
-                                    _stream()), 'allset_pma_fwd')
+                                    _ptr(ws), 0 if ws is None else ws.numel(), _stream()), 'allset_pma_fwd')
     return out, stats
 
 

@@ -480,6 +480,69 @@ __device__ __forceinline__ long long chunk_boundary(const int* __restrict__ rowp
   return hi;
 }
 
+// Long segments.  A chunk boundary that falls inside a segment of at least kSplitMinLen incidences CUTS it (when both
+// pieces keep kSplitMinPiece incidences), so that a 4096-row hyperedge of a power-law graph is reduced by as many warps
+// as its share of the work instead of serialising one warp (measured before: 5.0-5.8 ms with 4096-row segments inside
+// one warp's stream vs 4.3 ms for bucketed CTA kernels).  Pieces are combined without atomics, in stream order:
+//   * a chunk has at most ONE non-final piece, at its end: its partial state goes to workspace slot [chunk] and a flag
+//     is released (1 = first piece of the segment, 2 = continuing piece);
+//   * a chunk has at most one FINAL piece, at its start: the warp parks that state in its own `head` slot, finishes the
+//     rest of its stream, then walks back over the flags of the preceding chunks (decoupled look-back: they run on the
+//     same or earlier CTAs), adds their partials in ascending order, writes the row and clears the flags it consumed.
+// The workspace (allset_stream_workspace_bytes, zero-initialised once by the caller) is therefore left zeroed.
+constexpr int kSplitMinLen = 256;
+constexpr int kSplitMinPiece = 32;
+constexpr long long kStreamMaxChunks = 148LL * kStreamWarps * 8;
+
+struct Cut {
+  long long seg;   // first segment that STARTS at or after the cut (inside == 0) / the segment being cut (inside == 1)
+  int k;           // stream position of the cut
+  int inside;
+};
+
+__device__ __forceinline__ Cut chunk_cut(const int* __restrict__ rowptr, long long n_tgt, long long total,
+                                         long long chunk, long long n_chunks, int lane, bool split) {
+  Cut c;
+  c.seg = chunk_boundary(rowptr, n_tgt, total, chunk, n_chunks, lane);
+  c.k = __ldg(rowptr + c.seg);
+  c.inside = 0;
+  if (split && chunk > 0 && chunk < n_chunks && c.seg > 0) {
+    const long long target = total * chunk / n_chunks;
+    const long long s = c.seg - 1;
+    const int beg = __ldg(rowptr + s);
+    const long long o = target - ((long long)beg + s);      // 0 < o <= len + 1: where the target falls inside segment s
+    const long long len = (long long)c.k - beg;
+    if (len >= kSplitMinLen && o >= kSplitMinPiece && len - o >= kSplitMinPiece) {
+      c.seg = s;
+      c.k = beg + (int)o;
+      c.inside = 1;
+    }
+  }
+  return c;
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct StreamWs {           // views into the caller's workspace
+  int* flags;               // [kStreamMaxChunks]
+  float* tail;              // [kStreamMaxChunks][stride]: published non-final pieces
+  float* head;              // [kStreamMaxChunks][stride]: a warp's own parked final piece
+};
+__device__ __forceinline__ StreamWs stream_ws(void* ws, int stride) {
+  StreamWs v;
+  v.flags = reinterpret_cast<int*>(ws);
+  v.tail = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + kStreamMaxChunks * 4);
+  v.head = v.tail + kStreamMaxChunks * (long long)stride;
+  return v;
+}
+
 // One lane's share of a staged row: LB bytes (LB = row_bytes / 32).  LB >= 16 is read as LB/16 16-byte chunks,
 // chunk c of lane l at byte (c*32 + l)*16, so every LDS.128 of the warp covers 512 contiguous bytes.
 template <typename T, int LB>
@@ -549,11 +612,38 @@ struct LaneRow {
       }
     }
   }
+  // the same row image into shared memory (`p` = shared-space byte address): staging for bulk stores
+  __device__ static __forceinline__ void store_shared(uint32_t p, int lane, const float (&acc)[NA]) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const uint32_t a = p + offset(lane, c);
+      uint32_t o[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int q = 0; q < CB / 4; ++q) {
+        if (ES == 2) {
+          __nv_bfloat162 v = __floats2bfloat162_rn(acc[c * EPC + 2 * q], acc[c * EPC + 2 * q + 1]);
+          o[q] = *reinterpret_cast<uint32_t*>(&v);
+        } else {
+          o[q] = __float_as_uint(acc[c * EPC + q]);
+        }
+      }
+      if (CB == 16) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+      else if (CB == 8) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(o[0]), "r"(o[1]) : "memory");
+      else asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(o[0]) : "memory");
+    }
+  }
 };
 
 // Fused exchange: besides `out`, every reduced row is also stored into the same row of up to 7 peer replicas
-// (peer-mapped device pointers: NVLink P2P stores, fire-and-forget), so the all-gather that would follow the kernel
-// rides on its epilogue.  delta[j] = byte distance from `out` row 0 to the same row in peer j's buffer.
+// (peer-mapped device pointers over NVLink, or ONE multicast address the NVSwitch replicates), so the all-gather that
+// would follow the kernel rides on its epilogue.  delta[j] = byte distance from `out` row 0 to the same row in peer j's
+// buffer.  `mask` (optional, one byte per target row) selects the peers that need the row: bit j = peer j -- a vertex
+// row is needed only by the ranks whose hyperedge range touches the vertex.
+//   PUSH == 1: the reducing warp stores the row to every selected peer itself (st.global, fire-and-forget until the
+//              NVLink queue back-pressures the warp);
+//   PUSH == 2: the row is parked in a 2-slot shared-memory staging buffer and ONE lane hands it to the TMA
+//              (cp.async.bulk shared -> global, one bulk store per selected peer), so the warp goes back to gathering
+//              while the copies drain; a slot is reused after cp.async.bulk.wait_group.read.
 struct PeerOuts {
   long long delta[7];
   int n;
@@ -561,21 +651,47 @@ struct PeerOuts {
 
 // static indexing only (a dynamically indexed by-value struct would be copied to local memory)
 template <typename T, typename LR, int NA>
-__device__ __forceinline__ void store_to_peers(T* ob, const PeerOuts& peers, int lane, const float (&acc)[NA]) {
+__device__ __forceinline__ void store_to_peers(T* row, const PeerOuts& peers, unsigned mask, int lane,
+                                               const float (&acc)[NA]) {
 #pragma unroll
   for (int j = 0; j < 7; ++j)
-    if (j < peers.n) LR::store(reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ob) + peers.delta[j]), lane, acc);
+    if (j < peers.n && ((mask >> j) & 1u))
+      LR::store(reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(row) + peers.delta[j]), lane, acc);
 }
 
-template <typename T, int LB, bool WEIGHTED, bool BCAST>
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+template <typename T, typename LR, int NA, int ROWB>
+__device__ __forceinline__ void bulk_to_peers(T* row, const PeerOuts& peers, unsigned mask, int lane, uint32_t stage,
+                                              int& nslot, const float (&acc)[NA]) {
+  const uint32_t slot = stage + (uint32_t)(nslot & 1) * ROWB;
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the copies that read this slot are done
+  __syncwarp();
+  LR::store_shared(slot, lane, acc);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (j < peers.n && ((mask >> j) & 1u)) bulk_s2g(reinterpret_cast<unsigned char*>(row) + peers.delta[j], slot, ROWB);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  ++nslot;
+}
+
+template <typename T, int LB, bool WEIGHTED, int PUSH>
 __global__ void __launch_bounds__(kStreamWarps * 32, 1)
 segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                         const float* __restrict__ w, const float* __restrict__ sscale, long long n_tgt, int d,
-                        int mean, int seg_per_warp, int stages, T* __restrict__ out, PeerOuts peers) {
+                        int mean, int seg_per_warp, int stages, T* __restrict__ out, PeerOuts peers,
+                        const unsigned char* __restrict__ peer_mask, void* ws) {
   using LR = LaneRow<T, LB>;
   constexpr int NA = LR::NA;
   constexpr int ROWB = LB * 32;
   constexpr int RPS = (kStreamStageBytes / ROWB) < 32 ? (kStreamStageBytes / ROWB) : 32;   // rows per stage
+  constexpr int PS = NA * 32;                                                            // floats per parked piece
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // seg_per_warp only sizes the grid (host); the actual block of segments is cost-balanced
@@ -583,43 +699,65 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
   const long long chunk = (long long)blockIdx.x * kStreamWarps + warp;
   if (chunk >= n_chunks) return;                      // warp-uniform; nothing below synchronises across warps
   const long long total_cost = (long long)__ldg(rowptr + n_tgt) + n_tgt;
-  const long long s_first = chunk_boundary(rowptr, n_tgt, total_cost, chunk, n_chunks, lane);
-  const int nseg = (int)(chunk_boundary(rowptr, n_tgt, total_cost, chunk + 1, n_chunks, lane) - s_first);
-  if (nseg <= 0) return;
+  const bool split = ws != nullptr && n_chunks <= kStreamMaxChunks;
+  const Cut c0 = chunk_cut(rowptr, n_tgt, total_cost, chunk, n_chunks, lane, split);
+  const Cut c1 = chunk_cut(rowptr, n_tgt, total_cost, chunk + 1, n_chunks, lane, split);
+  const long long s_first = c0.seg;
+  const int nseg = (int)(c1.seg - s_first);            // segments that END inside this chunk
+  const int kb = c0.k, ke = c1.k;
+  if (nseg <= 0 && ke <= kb) return;
   const uint32_t ring = smem_u32(smem) + (uint32_t)warp * (uint32_t)stages * (RPS * ROWB);
   const uint32_t bars = smem_u32(smem) + (uint32_t)kStreamWarps * (uint32_t)stages * (RPS * ROWB) +
                         (uint32_t)warp * (uint32_t)stages * 8u;
   float* wbuf = reinterpret_cast<float*>(smem + (size_t)kStreamWarps * stages * (RPS * ROWB) +
                                          (size_t)kStreamWarps * stages * 8) + (size_t)warp * stages * RPS;
+  // staging rows of the bulk-store exchange: behind the ring, the barriers and the (optional) weight buffer
+  const uint32_t stage_out = smem_u32(smem) + (uint32_t)kStreamWarps * (uint32_t)stages * (RPS * ROWB + 8 + (WEIGHTED ? RPS * 4 : 0)) +
+                             16u + (uint32_t)warp * 2u * ROWB;
+  int nslot = 0;
   if (lane < stages) mbar_init(bars + lane * 8, kStreamBarCount);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
 
   const int* __restrict__ rp = rowptr + s_first;
-  const int kb = __ldg(rp), ke = __ldg(rp + nseg);
-  // segment cursor: end of the current segment and (prefetched, warp-uniform load) of the next one
+  const StreamWs wsv = stream_ws(ws, PS);
   float acc[NA];
 #pragma unroll
   for (int i = 0; i < NA; ++i) acc[i] = 0.f;
-  T* __restrict__ ob = out + (size_t)s_first * (size_t)d;
-  int seg = 0, cur_beg = kb, cur_end = __ldg(rp + 1), nxt_end = __ldg(rp + min(2, nseg)), pos = kb;
+  // segment cursor: end of the current segment and (prefetched, warp-uniform load) of the next one; the tail piece of a
+  // cut segment (seg == nseg) never ends inside the stream
+  int seg = 0, cur_beg = kb, pos = kb;
+  int cur_end = nseg > 0 ? __ldg(rp + 1) : INT32_MAX, nxt_end = __ldg(rp + min(2, max(nseg, 0)));
 
-  auto flush = [&]() {
+  // a finished row: scale (mean), store, exchange
+  auto emit = [&](long long s_idx, float cnt, float (&val)[NA]) {
     if (mean) {
-      const float cnt = (float)max(cur_end - cur_beg, 1);
       const float rc = __frcp_rn(cnt);
 #pragma unroll
-      for (int i = 0; i < NA; ++i) acc[i] = div_count(acc[i], cnt, rc);
+      for (int i = 0; i < NA; ++i) val[i] = div_count(val[i], cnt, rc);
     }
-    LR::store(ob, lane, acc);
-    if (BCAST) store_to_peers<T, LR, NA>(ob, peers, lane, acc);
-    ob += d;
+    T* row = out + (size_t)s_idx * (size_t)d;
+    LR::store(row, lane, val);
+    if (PUSH != 0) {
+      const unsigned m = peer_mask != nullptr ? (unsigned)__ldg(peer_mask + s_idx) : 0xffu;
+      if (PUSH == 1) store_to_peers<T, LR, NA>(row, peers, m, lane, val);
+      else bulk_to_peers<T, LR, NA, ROWB>(row, peers, m, lane, stage_out, nslot, val);
+    }
+  };
+  auto flush = [&]() {
+    if (seg == 0 && c0.inside) {
+      // final piece of a segment that began in an earlier chunk: park it, combine after the stream (see below)
+#pragma unroll
+      for (int i = 0; i < NA; ++i) wsv.head[chunk * PS + i * 32 + lane] = acc[i];
+    } else {
+      emit(s_first + seg, (float)max(cur_end - cur_beg, 1), acc);
+    }
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.f;
     ++seg;
     cur_beg = cur_end;
     cur_end = seg < nseg ? nxt_end : INT32_MAX;
-    nxt_end = __ldg(rp + min(seg + 2, nseg));
+    nxt_end = __ldg(rp + min(seg + 2, max(nseg, 0)));
   };
 
   // ---- producer side ---------------------------------------------------------------------------------------
@@ -666,9 +804,9 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
     if (WEIGHTED) __syncwarp();
     const uint32_t rows = ring + (uint32_t)st * (RPS * ROWB);
     const float* wrow = wbuf + st * RPS;
-    if (!BCAST && n == RPS) {
+    if (PUSH == 0 && n == RPS) {
       // full stage: fully unrolled, one compare per row against the (stage-relative) end of the current segment
-      // (the fused-exchange variant keeps a single flush site: its epilogue stores to up to 8 replicas)
+      // (the fused-exchange variants keep a single flush site: their epilogue stores to up to 8 replicas)
       int rel = cur_end - cbase;
 #pragma unroll
       for (int r = 0; r < RPS; ++r) {
@@ -701,6 +839,72 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
     }
   }
   while (seg < nseg) flush();
+
+  // ---- pieces of cut segments ------------------------------------------------------------------------------
+  if (c1.inside) {
+    // non-final piece at the end of the stream: publish it for the warp that owns the end of the segment
+#pragma unroll
+    for (int i = 0; i < NA; ++i) wsv.tail[chunk * PS + i * 32 + lane] = acc[i];
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_gpu(wsv.flags + chunk, (c0.inside && nseg == 0) ? 2 : 1);
+  }
+  if (c0.inside && nseg > 0) {
+    long long q0 = chunk - 1;
+    while (true) {                                // walk back to the chunk holding the first piece
+      int f;
+      do { f = ld_acquire_gpu(wsv.flags + q0); } while (f == 0);
+      if (f == 1) break;
+      --q0;
+    }
+    float tot[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) tot[i] = 0.f;
+    for (long long q = q0; q < chunk; ++q) {
+#pragma unroll
+      for (int i = 0; i < NA; ++i) tot[i] = __fadd_rn(tot[i], __ldcg(wsv.tail + q * PS + i * 32 + lane));
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) tot[i] = __fadd_rn(tot[i], wsv.head[chunk * PS + i * 32 + lane]);
+    __syncwarp();
+    if (lane == 0)
+      for (long long q = q0; q < chunk; ++q) wsv.flags[q] = 0;      // leave the workspace zeroed for the next launch
+    emit(s_first, (float)max(__ldg(rp + 1) - __ldg(rp), 1), tot);
+  }
+  if (PUSH == 2) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+}
+
+// The exchange by itself: rows [0, n_rows) of this rank's range (already in its own replica) -> the same rows of the
+// selected peers.  Used where the producer of the rows is not one of the fused-exchange kernels (a cuBLAS GEMM epilogue,
+// a rowop pass): one read of the rows, up to 7 NVLink stores per 16-byte chunk, 4 chunks in flight per thread.
+__global__ void __launch_bounds__(256)
+push_rows_kernel(const uint4* __restrict__ src, long long n_chunks, int chunks_per_row, PeerOuts peers,
+                 const unsigned char* __restrict__ mask) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; g0 < n_chunks; g0 += 4 * stride) {
+    uint4 v[4];
+    unsigned m[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long g = g0 + u * stride;
+      m[u] = 0u;
+      if (g < n_chunks) {
+        v[u] = __ldcs(src + g);
+        m[u] = mask != nullptr ? (unsigned)__ldg(mask + g / chunks_per_row) : 0xffu;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long g = g0 + u * stride;
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+        if (j < peers.n && ((m[u] >> j) & 1u))
+          *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(const_cast<uint4*>(src + g)) + peers.delta[j]) = v[u];
+    }
+  }
 }
 
 // d{0,1} = a * b{0,1} + d{0,1}: one FFMA2 (sm_100 packed fp32, both halves rounded like scalar FFMA)
@@ -728,16 +932,18 @@ constexpr int kPmaOnlinePiece = 8;   // pieces up to this many rows take the sin
 // (a second bulk copy onto the same mbarrier).  The online softmax runs per lane-chunk in the log2 domain
 // (a2 = leaky_relu(score) * log2(e); p = 2^(a2 - m2)), state (m2, l, acc) is flushed at segment boundaries:
 // out = acc / (l + 1e-16) + seed  (PyG softmax then scatter-add then += att_r, reference layers.py:168-194,153).
-template <typename T, int LB, bool BCAST>
+template <typename T, int LB, int PUSH>
 __global__ void __launch_bounds__(kStreamWarps * 32, 1)
 pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, const float* __restrict__ seed,
                   const int* __restrict__ rowptr, const int* __restrict__ col, long long n_tgt, int H, int C,
                   float slope, int seg_per_warp, int stages, T* __restrict__ out, float* __restrict__ stats,
-                  PeerOuts peers, long long v_pitch, long long s_pitch) {
+                  PeerOuts peers, long long v_pitch, long long s_pitch, const unsigned char* __restrict__ peer_mask,
+                  void* ws) {
   using LR = LaneRow<T, LB>;
   constexpr int ES = LR::ES, NA = LR::NA, CH = LR::CH, CB = LR::CB, EPC = LR::EPC;
   constexpr int ROWB = LB * 32;
   constexpr int RPS = (kStreamStageBytes / ROWB) < 32 ? (kStreamStageBytes / ROWB) : 32;
+  constexpr int PS = (NA + 2 * CH) * 32;                      // floats per parked piece: acc, then m2, then l
   constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -745,9 +951,13 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
   const long long chunk = (long long)blockIdx.x * kStreamWarps + warp;
   if (chunk >= n_chunks) return;
   const long long total_cost = (long long)__ldg(rowptr + n_tgt) + n_tgt;
-  const long long s_first = chunk_boundary(rowptr, n_tgt, total_cost, chunk, n_chunks, lane);
-  const int nseg = (int)(chunk_boundary(rowptr, n_tgt, total_cost, chunk + 1, n_chunks, lane) - s_first);
-  if (nseg <= 0) return;
+  const bool split = ws != nullptr && n_chunks <= kStreamMaxChunks;
+  const Cut c0 = chunk_cut(rowptr, n_tgt, total_cost, chunk, n_chunks, lane, split);
+  const Cut c1 = chunk_cut(rowptr, n_tgt, total_cost, chunk + 1, n_chunks, lane, split);
+  const long long s_first = c0.seg;
+  const int nseg = (int)(c1.seg - s_first);                   // segments that END inside this chunk
+  const int kb = c0.k, ke = c1.k;
+  if (nseg <= 0 && ke <= kb) return;
   const int d = H * C;
   const uint32_t SB = (uint32_t)H * 4u;                                       // score bytes per row
   const uint32_t ring = smem_u32(smem) + (uint32_t)warp * (uint32_t)stages * (RPS * ROWB);
@@ -755,12 +965,15 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
                          (uint32_t)warp * (uint32_t)stages * RPS * SB;
   const uint32_t bars = smem_u32(smem) + (uint32_t)kStreamWarps * (uint32_t)stages * RPS * (ROWB + SB) +
                         (uint32_t)warp * (uint32_t)stages * 8u;
+  const uint32_t stage_out = smem_u32(smem) + (uint32_t)kStreamWarps * (uint32_t)stages * (RPS * (ROWB + SB) + 8u) + 16u +
+                             (uint32_t)warp * 2u * ROWB;
+  int nslot = 0;
   if (lane < stages) mbar_init(bars + lane * 8, kStreamBarCount);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
 
   const int* __restrict__ rp = rowptr + s_first;
-  const int kb = __ldg(rp), ke = __ldg(rp + nseg);
+  const StreamWs wsv = stream_ws(ws, PS);
 
   int hc[CH];                                   // head of each of this lane's chunks
   float sd[NA];                                 // seed slice of this lane
@@ -776,34 +989,51 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
   for (int c = 0; c < CH; ++c) { m2[c] = -INFINITY; l[c] = 0.f; }
 #pragma unroll
   for (int i = 0; i < NA; ++i) acc[i] = 0.f;
-  T* __restrict__ ob = out + (size_t)s_first * (size_t)d;
-  float* __restrict__ sb_out = stats != nullptr ? stats + (size_t)s_first * H * 2 : nullptr;
-  int seg = 0, cur_end = __ldg(rp + 1), nxt_end = __ldg(rp + min(2, nseg)), pos = kb;
+  int seg = 0, pos = kb;
+  int cur_end = nseg > 0 ? __ldg(rp + 1) : INT32_MAX, nxt_end = __ldg(rp + min(2, max(nseg, 0)));
 
-  auto flush = [&]() {
+  // a finished segment: out = acc / (l + 1e-16) + seed, statistics, exchange
+  auto emit = [&](long long s_idx, const float (&mm)[CH], const float (&ll)[CH], const float (&aa)[NA]) {
     float o[NA];
+    float* sb_out = stats != nullptr ? stats + (size_t)s_idx * H * 2 : nullptr;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      const float denom = l[c] + 1e-16f;
+      const float denom = ll[c] + 1e-16f;
       const float inv = 1.0f / denom;
 #pragma unroll
-      for (int i = 0; i < EPC; ++i) o[c * EPC + i] = fmaf(acc[c * EPC + i], inv, sd[c * EPC + i]);
+      for (int i = 0; i < EPC; ++i) o[c * EPC + i] = fmaf(aa[c * EPC + i], inv, sd[c * EPC + i]);
       if (sb_out != nullptr && (LR::offset(lane, c) / ES) % C == 0) {
-        sb_out[hc[c] * 2 + 0] = m2[c] * kLn2;
+        sb_out[hc[c] * 2 + 0] = mm[c] * kLn2;
         sb_out[hc[c] * 2 + 1] = denom;
       }
-      m2[c] = -INFINITY;
-      l[c] = 0.f;
     }
-    LR::store(ob, lane, o);
-    if (BCAST) store_to_peers<T, LR, NA>(ob, peers, lane, o);
-    ob += d;
-    if (sb_out != nullptr) sb_out += 2 * H;
+    T* row = out + (size_t)s_idx * (size_t)d;
+    LR::store(row, lane, o);
+    if (PUSH != 0) {
+      const unsigned m = peer_mask != nullptr ? (unsigned)__ldg(peer_mask + s_idx) : 0xffu;
+      if (PUSH == 1) store_to_peers<T, LR, NA>(row, peers, m, lane, o);
+      else bulk_to_peers<T, LR, NA, ROWB>(row, peers, m, lane, stage_out, nslot, o);
+    }
+  };
+  auto park = [&](float* slot) {                 // (acc, m2, l) of a piece of a cut segment
+#pragma unroll
+    for (int i = 0; i < NA; ++i) slot[i * 32 + lane] = acc[i];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      slot[(NA + c) * 32 + lane] = m2[c];
+      slot[(NA + CH + c) * 32 + lane] = l[c];
+    }
+  };
+  auto flush = [&]() {
+    if (seg == 0 && c0.inside) park(wsv.head + chunk * PS);       // final piece of a cut segment: combined after the stream
+    else emit(s_first + seg, m2, l, acc);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { m2[c] = -INFINITY; l[c] = 0.f; }
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.f;
     ++seg;
     cur_end = seg < nseg ? nxt_end : INT32_MAX;
-    nxt_end = __ldg(rp + min(seg + 2, nseg));
+    nxt_end = __ldg(rp + min(seg + 2, max(nseg, 0)));
   };
 
   // acc += p * row chunk c (unpack to fp32, packed FFMA2)
@@ -967,6 +1197,52 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
     }
   }
   while (seg < nseg) flush();
+
+  // ---- pieces of cut segments (see chunk_cut) -------------------------------------------------------------
+  if (c1.inside) {
+    park(wsv.tail + chunk * PS);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_gpu(wsv.flags + chunk, (c0.inside && nseg == 0) ? 2 : 1);
+  }
+  if (c0.inside && nseg > 0) {
+    long long q0 = chunk - 1;
+    while (true) {
+      int f;
+      do { f = ld_acquire_gpu(wsv.flags + q0); } while (f == 0);
+      if (f == 1) break;
+      --q0;
+    }
+    float tm[CH], tl[CH], ta[NA];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { tm[c] = -INFINITY; tl[c] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) ta[i] = 0.f;
+    // online-softmax merge of the pieces in stream order; the warp's own parked piece comes last
+    for (long long q = q0; q <= chunk; ++q) {
+      const float* slot = q < chunk ? wsv.tail + q * PS : wsv.head + chunk * PS;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float pm = __ldcg(slot + (NA + c) * 32 + lane), pl = __ldcg(slot + (NA + CH + c) * 32 + lane);
+        const float mn = fmaxf(tm[c], pm);
+        const float ca = ex2_approx(tm[c] - mn), cb = ex2_approx(pm - mn);    // 2^-inf = 0; an empty piece has pm = -inf
+        const float fa = (tm[c] == -INFINITY) ? 0.f : ca, fb = (pm == -INFINITY) ? 0.f : cb;
+        tm[c] = mn;
+        tl[c] = tl[c] * fa + pl * fb;
+#pragma unroll
+        for (int i = 0; i < EPC; ++i)
+          ta[c * EPC + i] = ta[c * EPC + i] * fa + __ldcg(slot + (c * EPC + i) * 32 + lane) * fb;
+      }
+    }
+    __syncwarp();
+    if (lane == 0)
+      for (long long q = q0; q < chunk; ++q) wsv.flags[q] = 0;
+    emit(s_first, tm, tl, ta);
+  }
+  if (PUSH == 2) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
 }
 
 // grad_w[k] = tgt_scale[t] * <x[col[k]], grad_out[t]>; one warp per segment (LearnMask only).
@@ -1792,50 +2068,70 @@ StreamPlan plan_stream(int d, int elem_bytes, long long n_tgt, const void* x, co
   return p;
 }
 
+// how the fused exchange leaves the SM: 1 = stores by the reducing warp, 2 = TMA bulk stores from a staging slot
+int push_mode() {
+  const char* e = getenv("ALLSET_PUSH");          // read per launch (a host-side lookup): A/B runs and tests flip it
+  return (e != nullptr && (e[0] == 'd' || e[0] == '1')) ? 1 : 2;
+}
+
+struct StreamExtra {            // optional arguments of the stream kernels
+  const unsigned char* peer_mask;
+  void* ws;
+};
+
 template <typename T, int LB, bool WEIGHTED>
 int launch_stream(const StreamPlan& p, const T* x, const int* rowptr, const int* col, const float* w,
                   const float* sscale, long long n_tgt, int d, int mean, T* out, const PeerOuts& peers,
-                  cudaStream_t st) {
+                  const StreamExtra& ex, cudaStream_t st) {
+  // the shared-memory opt-in is per DEVICE and this process may drive several: set it on every launch
   if (peers.n > 0) {
     if (WEIGHTED) return fail(ALLSET_EUNSUPPORTED, "segreduce_fwd_bcast: per-incidence weights are not supported");
-    auto kern = segreduce_stream_kernel<T, LB, false, true>;
-    // the opt-in is per DEVICE and this process may drive several: set it on every launch (a host-side table write)
+    const size_t smem_bulk = p.smem + (size_t)kStreamWarps * 2 * LB * 32;
+    if (push_mode() == 2 && smem_bulk <= 227 * 1024) {
+      auto kern = segreduce_stream_kernel<T, LB, false, 2>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bulk);
+      if (e != cudaSuccess) return fail(ALLSET_ECUDA, "segreduce_stream: smem opt-in: %s", cudaGetErrorString(e));
+      kern<<<p.blocks, kStreamWarps * 32, smem_bulk, st>>>(x, rowptr, col, w, sscale, n_tgt, d, mean, p.seg_per_warp,
+                                                           p.stages, out, peers, ex.peer_mask, ex.ws);
+      return ALLSET_OK;
+    }
+    auto kern = segreduce_stream_kernel<T, LB, false, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return fail(ALLSET_ECUDA, "segreduce_stream: smem opt-in: %s", cudaGetErrorString(e));
     kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(x, rowptr, col, w, sscale, n_tgt, d, mean, p.seg_per_warp,
-                                                      p.stages, out, peers);
+                                                      p.stages, out, peers, ex.peer_mask, ex.ws);
     return ALLSET_OK;
   }
-  auto kern = segreduce_stream_kernel<T, LB, WEIGHTED, false>;
+  auto kern = segreduce_stream_kernel<T, LB, WEIGHTED, 0>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return fail(ALLSET_ECUDA, "segreduce_stream: smem opt-in: %s", cudaGetErrorString(e));
   kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(x, rowptr, col, w, sscale, n_tgt, d, mean, p.seg_per_warp,
-                                                    p.stages, out, peers);
+                                                    p.stages, out, peers, nullptr, ex.ws);
   return ALLSET_OK;
 }
 
 template <typename T, bool WEIGHTED>
 int stream_by_width(const StreamPlan& p, const T* x, const int* rowptr, const int* col, const float* w,
                     const float* sscale, long long n_tgt, int d, int mean, T* out, const PeerOuts& peers,
-                    cudaStream_t st) {
+                    const StreamExtra& ex, cudaStream_t st) {
   switch (p.lane_bytes) {
-    case 4: return launch_stream<T, 4, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, st);
-    case 8: return launch_stream<T, 8, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, st);
-    case 16: return launch_stream<T, 16, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, st);
-    default: return launch_stream<T, 32, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, st);
+    case 4: return launch_stream<T, 4, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, ex, st);
+    case 8: return launch_stream<T, 8, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, ex, st);
+    case 16: return launch_stream<T, 16, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, ex, st);
+    default: return launch_stream<T, 32, WEIGHTED>(p, x, rowptr, col, w, sscale, n_tgt, d, mean, out, peers, ex, st);
   }
 }
 
 template <typename T>
 int segreduce_stream_typed(const StreamPlan& p, const void* x, const int* rowptr, const int* col, const float* w,
                            const float* sscale, long long n_tgt, int d, int mean, void* out, const PeerOuts& peers,
-                           cudaStream_t st) {
+                           const StreamExtra& ex, cudaStream_t st) {
   const bool weighted = (w != nullptr) || (sscale != nullptr);
   if (weighted)
     return stream_by_width<T, true>(p, static_cast<const T*>(x), rowptr, col, w, sscale, n_tgt, d, mean,
-                                    static_cast<T*>(out), peers, st);
+                                    static_cast<T*>(out), peers, ex, st);
   return stream_by_width<T, false>(p, static_cast<const T*>(x), rowptr, col, w, sscale, n_tgt, d, mean,
-                                   static_cast<T*>(out), peers, st);
+                                   static_cast<T*>(out), peers, ex, st);
 }
 
 // peer_outs[j] = address, in peer j's replica, of the row that `out` row 0 is -> byte deltas relative to `out`
@@ -1855,28 +2151,31 @@ int make_peers(void* out, void* const* peer_outs, int n_peers, PeerOuts* po) {
 template <typename T, int LB>
 int launch_pma_stream(const StreamPlan& p, const T* v, const float* score, const float* seed, const int* rowptr,
                       const int* col, long long n_tgt, int H, int C, float slope, T* out, float* stats,
-                      const PeerOuts& peers, cudaStream_t st, long long v_pitch, long long s_pitch) {
-  auto kern = peers.n > 0 ? pma_stream_kernel<T, LB, true> : pma_stream_kernel<T, LB, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);   // per device
+                      const PeerOuts& peers, const StreamExtra& ex, cudaStream_t st, long long v_pitch, long long s_pitch) {
+  const size_t smem_bulk = p.smem + (size_t)kStreamWarps * 2 * LB * 32;
+  const int push = peers.n == 0 ? 0 : ((push_mode() == 2 && smem_bulk <= 227 * 1024) ? 2 : 1);
+  auto kern = push == 0 ? pma_stream_kernel<T, LB, 0> : (push == 1 ? pma_stream_kernel<T, LB, 1> : pma_stream_kernel<T, LB, 2>);
+  const size_t smem = push == 2 ? smem_bulk : p.smem;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
   if (e != cudaSuccess) return fail(ALLSET_ECUDA, "pma_stream: smem opt-in: %s", cudaGetErrorString(e));
-  kern<<<p.blocks, kStreamWarps * 32, p.smem, st>>>(v, score, seed, rowptr, col, n_tgt, H, C, slope, p.seg_per_warp,
-                                                    p.stages, out, stats, peers,
-                                                    v_pitch > 0 ? v_pitch : (long long)LB * 32,
-                                                    s_pitch > 0 ? s_pitch : (long long)H * 4);
+  kern<<<p.blocks, kStreamWarps * 32, smem, st>>>(v, score, seed, rowptr, col, n_tgt, H, C, slope, p.seg_per_warp,
+                                                  p.stages, out, stats, peers,
+                                                  v_pitch > 0 ? v_pitch : (long long)LB * 32,
+                                                  s_pitch > 0 ? s_pitch : (long long)H * 4, ex.peer_mask, ex.ws);
   return ALLSET_OK;
 }
 
 template <typename T>
 int pma_stream_typed(const StreamPlan& p, const void* v, const float* score, const float* seed, const int* rowptr,
                      const int* col, long long n_tgt, int H, int C, float slope, void* out, float* stats,
-                     const PeerOuts& peers, cudaStream_t st, long long v_pitch, long long s_pitch) {
+                     const PeerOuts& peers, const StreamExtra& ex, cudaStream_t st, long long v_pitch, long long s_pitch) {
   const T* vi = static_cast<const T*>(v);
   T* oi = static_cast<T*>(out);
   switch (p.lane_bytes) {
-    case 4: return launch_pma_stream<T, 4>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st, v_pitch, s_pitch);
-    case 8: return launch_pma_stream<T, 8>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st, v_pitch, s_pitch);
-    case 16: return launch_pma_stream<T, 16>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st, v_pitch, s_pitch);
-    default: return launch_pma_stream<T, 32>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, st, v_pitch, s_pitch);
+    case 4: return launch_pma_stream<T, 4>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, ex, st, v_pitch, s_pitch);
+    case 8: return launch_pma_stream<T, 8>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, ex, st, v_pitch, s_pitch);
+    case 16: return launch_pma_stream<T, 16>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, ex, st, v_pitch, s_pitch);
+    default: return launch_pma_stream<T, 32>(p, vi, score, seed, rowptr, col, n_tgt, H, C, slope, oi, stats, peers, ex, st, v_pitch, s_pitch);
   }
 }
 
@@ -1997,10 +2296,27 @@ int allset_long_segments(const int32_t* rowptr, int64_t n_tgt, int32_t threshold
   return check_launch("long_segments");
 }
 
+namespace {
+size_t stream_ws_bytes(int32_t d) {
+  return (size_t)kStreamMaxChunks * 4 + 2 * (size_t)kStreamMaxChunks * (size_t)(d + 128) * 4;
+}
+// the workspace that lets the stream kernels cut long segments; NULL = never cut (long segments then need the buckets)
+int check_ws(const char* what, void* ws, size_t ws_bytes, int32_t d) {
+  if (ws == nullptr) return ALLSET_OK;
+  if (((uintptr_t)ws % 16) != 0 || ws_bytes < stream_ws_bytes(d))
+    return fail(ALLSET_EWORKSPACE, "%s: workspace must be 16-byte aligned and >= allset_stream_workspace_bytes(%d) = %zu bytes",
+                what, (int)d, stream_ws_bytes(d));
+  return ALLSET_OK;
+}
+}  // namespace
+
+size_t allset_stream_workspace_bytes(int32_t d) { return d > 0 ? stream_ws_bytes(d) : 0; }
+
 static int segreduce_fwd_impl(const void* x, int dtype, int64_t n_src, int32_t d, const int32_t* rowptr,
                               const int32_t* col, const float* w, const float* src_scale, int64_t n_tgt, int op,
                               const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out,
-                              void* const* peer_outs, int32_t n_peers, void* stream) {
+                              void* const* peer_outs, int32_t n_peers, const uint8_t* peer_mask, void* ws,
+                              size_t ws_bytes, void* stream) {
   if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "segreduce_fwd: unknown dtype %d", dtype);
   if (op != ALLSET_SUM && op != ALLSET_MEAN) return fail(ALLSET_EINVAL, "segreduce_fwd: unknown op %d", op);
   if (d <= 0 || n_tgt < 0 || n_src < 0 || n_long < 0) return fail(ALLSET_EINVAL, "segreduce_fwd: bad size");
@@ -2012,16 +2328,18 @@ static int segreduce_fwd_impl(const void* x, int dtype, int64_t n_src, int32_t d
     // legal only for an incidence list without entries; rowptr is then all zero and nothing is read
     if (n_src != 0) return fail(ALLSET_EINVAL, "segreduce_fwd: null x/col with n_src > 0");
   }
+  if (int rc = check_ws("segreduce_fwd", ws, ws_bytes, d)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // The stream kernel handles every segment length itself (a long segment is just a long piece of one warp's
-  // stream), so it is used when no segment exceeds the caller's long-segment bucket.
+  // The stream kernel handles every segment length itself: with a workspace it cuts long segments at chunk boundaries
+  // (so the long-segment buckets are not needed), without one it takes graphs whose segments are all moderate.
   const StreamPlan sp = plan_stream(d, elem_bytes(dtype), n_tgt, x, out, w != nullptr || src_scale != nullptr);
   PeerOuts peers;
   if (int rc = make_peers(out, peer_outs, n_peers, &peers)) return rc;
-  if (sp.ok && n_long == 0 && x != nullptr && col != nullptr) {
+  if (sp.ok && (n_long == 0 || ws != nullptr) && x != nullptr && col != nullptr) {
+    const StreamExtra ex{peer_mask, ws};
     const int rc = dtype == ALLSET_F32
-        ? segreduce_stream_typed<float>(sp, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, out, peers, st)
-        : segreduce_stream_typed<__nv_bfloat16>(sp, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, out, peers, st);
+        ? segreduce_stream_typed<float>(sp, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, out, peers, ex, st)
+        : segreduce_stream_typed<__nv_bfloat16>(sp, x, rowptr, col, w, src_scale, n_tgt, d, op == ALLSET_MEAN, out, peers, ex, st);
     if (rc != ALLSET_OK) return rc;
     return check_launch("segreduce_fwd(stream)");
   }
@@ -2042,18 +2360,36 @@ static int segreduce_fwd_impl(const void* x, int dtype, int64_t n_src, int32_t d
 int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d, const int32_t* rowptr,
                          const int32_t* col, const float* w, const float* src_scale, int64_t n_tgt, int op,
                          const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out,
-                         void* stream) {
+                         void* ws, size_t ws_bytes, void* stream) {
   return segreduce_fwd_impl(x, dtype, n_src, d, rowptr, col, w, src_scale, n_tgt, op, long_ids, n_long,
-                            long_threshold, out, nullptr, 0, stream);
+                            long_threshold, out, nullptr, 0, nullptr, ws, ws_bytes, stream);
 }
 
 int allset_segreduce_fwd_bcast(const void* x, int dtype, int64_t n_src, int32_t d, const int32_t* rowptr,
                                const int32_t* col, const float* w, const float* src_scale, int64_t n_tgt, int op,
-                               void* out, void* const* peer_outs, int32_t n_peers, void* stream) {
+                               void* out, void* const* peer_outs, int32_t n_peers, const uint8_t* peer_mask,
+                               void* ws, size_t ws_bytes, void* stream) {
   return segreduce_fwd_impl(x, dtype, n_src, d, rowptr, col, w, src_scale, n_tgt, op, nullptr, 0, 0, out, peer_outs,
-                            n_peers, stream);
+                            n_peers, peer_mask, ws, ws_bytes, stream);
 }
 
+
+int allset_push_rows(const void* rows, int64_t n_rows, int64_t row_bytes, void* const* peer_rows, int32_t n_peers,
+                     const uint8_t* peer_mask, void* stream) {
+  if (n_rows < 0 || row_bytes <= 0) return fail(ALLSET_EINVAL, "push_rows: bad size");
+  if (n_rows == 0 || n_peers == 0) return ALLSET_OK;
+  if (rows == nullptr) return fail(ALLSET_EINVAL, "push_rows: null pointer");
+  if (row_bytes % 16 != 0 || ((uintptr_t)rows % 16) != 0)
+    return fail(ALLSET_EUNSUPPORTED, "push_rows: rows must be 16-byte aligned multiples of 16 bytes");
+  PeerOuts peers;
+  if (int rc = make_peers(const_cast<void*>(rows), peer_rows, n_peers, &peers)) return rc;
+  const long long n_chunks = (long long)n_rows * (row_bytes / 16);
+  long long blocks = (n_chunks + 256 * 4 - 1) / (256 * 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  push_rows_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(rows), n_chunks, (int)(row_bytes / 16), peers, peer_mask);
+  return check_launch("push_rows");
+}
 
 int allset_bias_act_norm(const float* x, const float* bias, int relu, const float* residual, const float* gamma,
                          const float* beta, float eps, int64_t rows, int32_t d, float* out, float* stats,
@@ -2267,11 +2603,32 @@ int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32
   return check_launch("segreduce_bwd_w");
 }
 
+namespace {
+// whether (dtype, H, C, n_tgt) takes the PMA stream kernel: the sum kernel's conditions plus H % 4 == 0 (scores travel
+// as 16-byte pieces), no lane chunk straddling two heads, and the score ring fitting shared memory
+bool pma_stream_shape_ok(int dtype, int32_t H, int32_t C, int64_t n_tgt, StreamPlan* out_plan) {
+  alignas(256) static char dummy[256];
+  StreamPlan sp = plan_stream(H * C, elem_bytes(dtype), n_tgt, dummy, dummy, false);
+  if (!sp.ok) return false;
+  const int chunk_elems = (sp.lane_bytes >= 16 ? 16 : sp.lane_bytes) / elem_bytes(dtype);
+  const size_t stage_rows = (size_t)kStreamWarps * sp.stages * sp.rows_per_stage;
+  sp.smem += stage_rows * (size_t)H * 4;
+  if (H % 4 != 0 || C % chunk_elems != 0 || sp.smem > 227 * 1024) return false;
+  if (out_plan != nullptr) *out_plan = sp;
+  return true;
+}
+}  // namespace
+
+int allset_pma_stream_eligible(int dtype, int32_t H, int32_t C, int64_t n_tgt) {
+  if (bad_dtype(dtype) || H <= 0 || C <= 0 || n_tgt <= 0) return 0;
+  return pma_stream_shape_ok(dtype, H, C, n_tgt, nullptr) ? 1 : 0;
+}
+
 static int pma_fwd_impl(const void* v, const float* score, const float* seed, int dtype, int32_t H, int32_t C,
                         float slope, const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
                         const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out, float* stats,
-                        void* const* peer_outs, int32_t n_peers, void* stream, int64_t v_pitch = 0,
-                        int64_t s_pitch = 0) {
+                        void* const* peer_outs, int32_t n_peers, const uint8_t* peer_mask, void* ws, size_t ws_bytes,
+                        void* stream, int64_t v_pitch = 0, int64_t s_pitch = 0) {
   if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "pma_fwd: unknown dtype %d", dtype);
   const bool strided = v_pitch != 0 || s_pitch != 0;       // rows / scores with a byte pitch: stream kernel only
   if (strided && (v_pitch < (int64_t)H * C * elem_bytes(dtype) || s_pitch < (int64_t)H * 4 || v_pitch % 16 != 0 ||
@@ -2286,24 +2643,20 @@ static int pma_fwd_impl(const void* v, const float* score, const float* seed, in
     return fail(ALLSET_EINVAL, "pma_fwd: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int d = H * C;
+  if (int rc = check_ws("pma_fwd", ws, ws_bytes, d)) return rc;
   {
-    // stream kernel: scores travel as one H*4-byte bulk copy per row (needs H % 4 == 0 and 16-byte alignment) and a
-    // lane's chunk must not straddle two heads
-    StreamPlan sp = plan_stream(d, elem_bytes(dtype), n_tgt, v, out, false);
-    if (sp.ok) {
-      const int chunk_elems = (sp.lane_bytes >= 16 ? 16 : sp.lane_bytes) / elem_bytes(dtype);
-      const size_t stage_rows = (size_t)kStreamWarps * sp.stages * sp.rows_per_stage;
-      sp.smem += stage_rows * (size_t)H * 4;
-      if (H % 4 != 0 || C % chunk_elems != 0 || ((uintptr_t)score % 16) != 0 || sp.smem > 227 * 1024 ||
-          n_long != 0 || v == nullptr || col == nullptr || score == nullptr)
-        sp.ok = false;
-    }
+    StreamPlan sp{};
+    sp.ok = pma_stream_shape_ok(dtype, H, C, n_tgt, &sp);
+    if (sp.ok && (((uintptr_t)v % 16) != 0 || ((uintptr_t)out % 16) != 0 || ((uintptr_t)score % 16) != 0 ||
+                  (n_long != 0 && ws == nullptr) || v == nullptr || col == nullptr || score == nullptr))
+      sp.ok = false;
     PeerOuts peers;
     if (int rc = make_peers(out, peer_outs, n_peers, &peers)) return rc;
     if (sp.ok) {
+      const StreamExtra ex{peer_mask, ws};
       const int rc = dtype == ALLSET_F32
-          ? pma_stream_typed<float>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, peers, st, v_pitch, s_pitch)
-          : pma_stream_typed<__nv_bfloat16>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, peers, st, v_pitch, s_pitch);
+          ? pma_stream_typed<float>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, peers, ex, st, v_pitch, s_pitch)
+          : pma_stream_typed<__nv_bfloat16>(sp, v, score, seed, rowptr, col, n_tgt, H, C, slope, out, stats, peers, ex, st, v_pitch, s_pitch);
       if (rc != ALLSET_OK) return rc;
       return check_launch("pma_fwd(stream)");
     }
@@ -2338,24 +2691,25 @@ static int pma_fwd_impl(const void* v, const float* score, const float* seed, in
 int allset_pma_fwd(const void* v, const float* score, const float* seed, int dtype, int32_t H, int32_t C,
                    float slope, const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
                    const int32_t* long_ids, int32_t n_long, int32_t long_threshold, void* out, float* stats,
-                   void* stream) {
+                   void* ws, size_t ws_bytes, void* stream) {
   return pma_fwd_impl(v, score, seed, dtype, H, C, slope, rowptr, col, n_tgt, long_ids, n_long, long_threshold, out,
-                      stats, nullptr, 0, stream);
+                      stats, nullptr, 0, nullptr, ws, ws_bytes, stream);
 }
 
 int allset_pma_fwd_strided(const void* v, int64_t v_pitch, const float* score, int64_t s_pitch, const float* seed,
                            int dtype, int32_t H, int32_t C, float slope, const int32_t* rowptr, const int32_t* col,
-                           int64_t n_tgt, void* out, float* stats, void* stream) {
+                           int64_t n_tgt, void* out, float* stats, void* ws, size_t ws_bytes, void* stream) {
   if (v_pitch <= 0 || s_pitch <= 0) return fail(ALLSET_EINVAL, "pma_fwd_strided: pitches must be positive");
-  return pma_fwd_impl(v, score, seed, dtype, H, C, slope, rowptr, col, n_tgt, nullptr, 0, 0, out, stats, nullptr, 0, stream,
-                      v_pitch, s_pitch);
+  return pma_fwd_impl(v, score, seed, dtype, H, C, slope, rowptr, col, n_tgt, nullptr, 0, 0, out, stats, nullptr, 0,
+                      nullptr, ws, ws_bytes, stream, v_pitch, s_pitch);
 }
 
 int allset_pma_fwd_bcast(const void* v, const float* score, const float* seed, int dtype, int32_t H, int32_t C,
                          float slope, const int32_t* rowptr, const int32_t* col, int64_t n_tgt, void* out,
-                         float* stats, void* const* peer_outs, int32_t n_peers, void* stream) {
+                         float* stats, void* const* peer_outs, int32_t n_peers, const uint8_t* peer_mask, void* ws,
+                         size_t ws_bytes, void* stream) {
   return pma_fwd_impl(v, score, seed, dtype, H, C, slope, rowptr, col, n_tgt, nullptr, 0, 0, out, stats, peer_outs,
-                      n_peers, stream);
+                      n_peers, peer_mask, ws, ws_bytes, stream);
 }
 
 int allset_pma_alpha(const float* score, const float* stats, int32_t H, float slope, const int32_t* rowptr,

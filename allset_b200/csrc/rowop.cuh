@@ -96,87 +96,132 @@ struct FwdArgs {
   float keep_scale; unsigned thr16; uint64_t seed; long long rows; void* out; float* stats; int relu_out;
 };
 
+// rows a warp holds at once: the loads of all of them are issued before the first use, so a warp has R row-sized
+// requests in flight (a 256-byte bf16 row per warp is far too little to cover HBM latency: measured 2.3 TB/s with R = 1)
+template <int NPL>
+struct RowsPerWarp { static constexpr int R = NPL <= 4 ? 4 : (NPL == 8 ? 2 : 1); };
+
 template <typename TIn, typename TOut, int NPL>
 __global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
   constexpr int D = 32 * NPL;
   constexpr int CE = NPL < 4 ? NPL : 4;
   constexpr int NCH = NPL / CE;
+  constexpr int R = RowsPerWarp<NPL>::R;
   const int lane = threadIdx.x & 31;
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= a.rows) return;
-  const TIn* xr = static_cast<const TIn*>(a.x) + row * D;
-  float v[NCH][CE];
+  const long long row0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R;
+  if (row0 >= a.rows) return;
+  const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+  float v[R][NCH][CE];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) Vec<TIn, CE>::load(xr + (c * 32 + lane) * CE, v[c]);
-  if (a.bias != nullptr) {
+  for (int r = 0; r < R; ++r) {
+    const TIn* xr = static_cast<const TIn*>(a.x) + (row0 + (r < nr ? r : 0)) * D;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) Vec<TIn, CE>::load(xr + (c * 32 + lane) * CE, v[r][c]);
+  }
+  if (a.residual != nullptr) {
+    float rs[R][NCH][CE];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const TIn* rr = static_cast<const TIn*>(a.residual) + (row0 + (r < nr ? r : 0)) * D;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) Vec<TIn, CE>::load(rr + (c * 32 + lane) * CE, rs[r][c]);
+    }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       float b[CE];
-      load_param<CE>(a.bias + (c * 32 + lane) * CE, b);
 #pragma unroll
-      for (int k = 0; k < CE; ++k) v[c][k] += b[k];
+      for (int k = 0; k < CE; ++k) b[k] = 0.f;
+      if (a.bias != nullptr) load_param<CE>(a.bias + (c * 32 + lane) * CE, b);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < CE; ++k) {
+          const float t = v[r][c][k] + b[k];
+          v[r][c][k] = (a.relu ? fmaxf(t, 0.f) : t) + rs[r][c][k];
+        }
     }
-  }
-  if (a.relu) {
-#pragma unroll
-    for (int c = 0; c < NCH; ++c)
-#pragma unroll
-      for (int k = 0; k < CE; ++k) v[c][k] = fmaxf(v[c][k], 0.f);
-  }
-  if (a.residual != nullptr) {
-    const TIn* rr = static_cast<const TIn*>(a.residual) + row * D;
+  } else if (a.bias != nullptr || a.relu) {
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      float r[CE];
-      Vec<TIn, CE>::load(rr + (c * 32 + lane) * CE, r);
+      float b[CE];
 #pragma unroll
-      for (int k = 0; k < CE; ++k) v[c][k] += r[k];
+      for (int k = 0; k < CE; ++k) b[k] = 0.f;
+      if (a.bias != nullptr) load_param<CE>(a.bias + (c * 32 + lane) * CE, b);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < CE; ++k) {
+          const float t = v[r][c][k] + b[k];
+          v[r][c][k] = a.relu ? fmaxf(t, 0.f) : t;
+        }
     }
   }
   if (a.gamma != nullptr) {
-    float sum = 0.f;
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+    for (int r = 0; r < R; ++r) {
+      float sum = 0.f;
 #pragma unroll
-      for (int k = 0; k < CE; ++k) sum += v[c][k];
+      for (int c = 0; c < NCH; ++c)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum * (1.f / D);
-    float sq = 0.f;
+        for (int k = 0; k < CE; ++k) sum += v[r][c][k];
+      mean[r] = sum;
+    }
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+    for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int k = 0; k < CE; ++k) { const float t = v[c][k] - mean; sq += t * t; }
+      for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);     // R independent chains
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq * (1.f / D) + a.eps);
-    if (a.stats != nullptr && lane == 0) *reinterpret_cast<float2*>(a.stats + row * 2) = make_float2(mean, rstd);
+    for (int r = 0; r < R; ++r) {
+      mean[r] *= (1.f / D);
+      float sq = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int k = 0; k < CE; ++k) { const float t = v[r][c][k] - mean[r]; sq += t * t; }
+      rstd[r] = sq;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      rstd[r] = rsqrtf(rstd[r] * (1.f / D) + a.eps);
+      if (a.stats != nullptr && lane == 0 && r < nr)
+        *reinterpret_cast<float2*>(a.stats + (row0 + r) * 2) = make_float2(mean[r], rstd[r]);
+    }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       float g[CE], b[CE];
       load_param<CE>(a.gamma + (c * 32 + lane) * CE, g);
+#pragma unroll
+      for (int k = 0; k < CE; ++k) b[k] = 0.f;
       if (a.beta != nullptr) load_param<CE>(a.beta + (c * 32 + lane) * CE, b);
 #pragma unroll
-      for (int k = 0; k < CE; ++k) v[c][k] = (v[c][k] - mean) * rstd * g[k] + (a.beta != nullptr ? b[k] : 0.f);
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < CE; ++k) v[r][c][k] = (v[r][c][k] - mean[r]) * rstd[r] * g[k] + b[k];
     }
   }
-  if (a.relu_out) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
-#pragma unroll
-      for (int k = 0; k < CE; ++k) v[c][k] = fmaxf(v[c][k], 0.f);
-  }
-  if (a.thr16 != 0u) {
+  for (int r = 0; r < R; ++r) {
+    if (r >= nr) break;
+    const long long row = row0 + r;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const unsigned keep = keep_bits<CE>(a.seed, row, D, (c * 32 + lane) * CE, a.thr16);
+      if (a.relu_out) {
 #pragma unroll
-      for (int k = 0; k < CE; ++k) v[c][k] = ((keep >> k) & 1u) ? v[c][k] * a.keep_scale : 0.f;
+        for (int k = 0; k < CE; ++k) v[r][c][k] = fmaxf(v[r][c][k], 0.f);
+      }
+      if (a.thr16 != 0u) {
+        const unsigned keep = keep_bits<CE>(a.seed, row, D, (c * 32 + lane) * CE, a.thr16);
+#pragma unroll
+        for (int k = 0; k < CE; ++k) v[r][c][k] = ((keep >> k) & 1u) ? v[r][c][k] * a.keep_scale : 0.f;
+      }
+      Vec<TOut, CE>::store(static_cast<TOut*>(a.out) + row * D + (c * 32 + lane) * CE, v[r][c]);
     }
   }
-  TOut* orow = static_cast<TOut*>(a.out) + row * D;
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) Vec<TOut, CE>::store(orow + (c * 32 + lane) * CE, v[c]);
 }
 
 struct BwdArgs {
@@ -208,72 +253,89 @@ __global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
     if (a.gamma != nullptr) load_param<CE>(a.gamma + (c * 32 + lane) * CE, gmv[c]);
     if (a.relu_out && a.beta != nullptr) load_param<CE>(a.beta + (c * 32 + lane) * CE, btv[c]);
   }
-  for (long long row = (long long)blockIdx.x * 8 + warp; row < a.rows; row += nwarps) {
-    const TX* xr = static_cast<const TX*>(a.x) + row * D;
-    const TG* dyr = static_cast<const TG*>(a.dy) + row * D;
-    float mean = 0.f, rstd = 1.f;
-    if (a.gamma != nullptr) {
-      const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats + row * 2));
-      mean = st.x; rstd = st.y;
+  constexpr int R = RowsPerWarp<NPL>::R;
+  for (long long row0 = ((long long)blockIdx.x * 8 + warp) * R; row0 < a.rows; row0 += nwarps * R) {
+    const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+    float pre[R][NCH][CE], g[R][NCH][CE], zh[R][NCH][CE];
+    float mean[R], rstd[R], s1[R], s2[R];
+    // all loads of the R rows first (independent requests in flight), then the arithmetic
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + (r < nr ? r : 0);
+      const TX* xr = static_cast<const TX*>(a.x) + row * D;
+      const TG* dyr = static_cast<const TG*>(a.dy) + row * D;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        Vec<TX, CE>::load(xr + (c * 32 + lane) * CE, pre[r][c]);
+        Vec<TG, CE>::load(dyr + (c * 32 + lane) * CE, g[r][c]);
+        if (a.residual != nullptr) Vec<TX, CE>::load(static_cast<const TX*>(a.residual) + row * D + (c * 32 + lane) * CE, zh[r][c]);
+      }
+      mean[r] = 0.f;
+      rstd[r] = 1.f;
+      if (a.gamma != nullptr) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats + row * 2));
+        mean[r] = st.x;
+        rstd[r] = st.y;
+      }
     }
-    float pre[NCH][CE], g[NCH][CE], zh[NCH][CE];
-    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = (c * 32 + lane) * CE;
-      float z[CE], g0[CE];
-      Vec<TX, CE>::load(xr + col, pre[c]);
-      Vec<TG, CE>::load(dyr + col, g0);
+    for (int r = 0; r < R; ++r) {
+      s1[r] = 0.f;
+      s2[r] = 0.f;
+      const bool live = r < nr;                       // rows beyond the end contribute nothing to the column sums
 #pragma unroll
-      for (int k = 0; k < CE; ++k) {
-        pre[c][k] += bsv[c][k];
-        z[k] = a.relu ? fmaxf(pre[c][k], 0.f) : pre[c][k];
-      }
-      if (a.residual != nullptr) {
-        float r[CE];
-        Vec<TX, CE>::load(static_cast<const TX*>(a.residual) + row * D + col, r);
+      for (int c = 0; c < NCH; ++c) {
+        const int col = (c * 32 + lane) * CE;
+        unsigned keep = 0xfu;
+        if (a.thr16 != 0u) keep = keep_bits<CE>(a.seed, row0 + r, D, col, a.thr16);
 #pragma unroll
-        for (int k = 0; k < CE; ++k) z[k] += r[k];
-      }
-      if (a.thr16 != 0u) {
-        const unsigned keep = keep_bits<CE>(a.seed, row, D, col, a.thr16);
-#pragma unroll
-        for (int k = 0; k < CE; ++k) g0[k] = ((keep >> k) & 1u) ? g0[k] * a.keep_scale : 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < CE; ++k) {
-        zh[c][k] = (z[k] - mean) * rstd;
-        if (a.relu_out && !(zh[c][k] * gmv[c][k] + btv[c][k] > 0.f)) g0[k] = 0.f;
-        g[c][k] = g0[k] * gmv[c][k];
-        if (a.gamma != nullptr) {
-          dgam[c][k] += g0[k] * zh[c][k];
-          dbet[c][k] += g0[k];
-          s1 += g[c][k];
-          s2 += g[c][k] * zh[c][k];
+        for (int k = 0; k < CE; ++k) {
+          pre[r][c][k] += bsv[c][k];
+          float z = a.relu ? fmaxf(pre[r][c][k], 0.f) : pre[r][c][k];
+          if (a.residual != nullptr) z += zh[r][c][k];
+          float g0 = live ? g[r][c][k] : 0.f;
+          if (a.thr16 != 0u) g0 = ((keep >> k) & 1u) ? g0 * a.keep_scale : 0.f;
+          const float h = (z - mean[r]) * rstd[r];
+          zh[r][c][k] = h;
+          if (a.relu_out && !(h * gmv[c][k] + btv[c][k] > 0.f)) g0 = 0.f;
+          const float gg = g0 * gmv[c][k];
+          g[r][c][k] = gg;
+          if (a.gamma != nullptr) {
+            dgam[c][k] += g0 * h;
+            dbet[c][k] += g0;
+            s1[r] += gg;
+            s2[r] += gg * h;
+          }
         }
       }
     }
     if (a.gamma != nullptr) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-      }
-      s1 *= (1.f / D);
-      s2 *= (1.f / D);
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {                 // 2R independent shuffle chains
+          s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
+          s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+        }
     }
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = (c * 32 + lane) * CE;
-      float dz[CE], dp[CE];
+    for (int r = 0; r < R; ++r) {
+      if (r >= nr) break;
+      const long long row = row0 + r;
+      const float m1 = s1[r] * (1.f / D), m2 = s2[r] * (1.f / D);
 #pragma unroll
-      for (int k = 0; k < CE; ++k) {
-        dz[k] = a.gamma != nullptr ? rstd * (g[c][k] - s1 - zh[c][k] * s2) : g[c][k];
-        dp[k] = (a.relu && !(pre[c][k] > 0.f)) ? 0.f : dz[k];
-        dbia[c][k] += dp[k];
+      for (int c = 0; c < NCH; ++c) {
+        const int col = (c * 32 + lane) * CE;
+        float dz[CE], dp[CE];
+#pragma unroll
+        for (int k = 0; k < CE; ++k) {
+          dz[k] = a.gamma != nullptr ? rstd[r] * (g[r][c][k] - m1 - zh[r][c][k] * m2) : g[r][c][k];
+          dp[k] = (a.relu && !(pre[r][c][k] > 0.f)) ? 0.f : dz[k];
+          dbia[c][k] += dp[k];
+        }
+        if (a.dres != nullptr) Vec<TG, CE>::store(static_cast<TG*>(a.dres) + row * D + col, dz);
+        Vec<TG, CE>::store(static_cast<TG*>(a.dx) + row * D + col, dp);
       }
-      if (a.dres != nullptr) Vec<TG, CE>::store(static_cast<TG*>(a.dres) + row * D + col, dz);
-      Vec<TG, CE>::store(static_cast<TG*>(a.dx) + row * D + col, dp);
     }
   }
 #pragma unroll
@@ -298,15 +360,21 @@ __global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
   }
 }
 
+template <typename TIn, typename TOut, int NPL>
+void launch_fwd_n(const FwdArgs& a, cudaStream_t st) {
+  constexpr int R = RowsPerWarp<NPL>::R;
+  const long long warps = (a.rows + R - 1) / R;
+  fwd_kernel<TIn, TOut, NPL><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(a);
+}
+
 template <typename TIn, typename TOut>
 bool launch_fwd(const FwdArgs& a, int d, cudaStream_t st) {
-  const unsigned blocks = (unsigned)((a.rows * 32 + 255) / 256);
   switch (d) {
-    case 64: fwd_kernel<TIn, TOut, 2><<<blocks, 256, 0, st>>>(a); return true;
-    case 128: fwd_kernel<TIn, TOut, 4><<<blocks, 256, 0, st>>>(a); return true;
-    case 256: fwd_kernel<TIn, TOut, 8><<<blocks, 256, 0, st>>>(a); return true;
-    case 512: fwd_kernel<TIn, TOut, 16><<<blocks, 256, 0, st>>>(a); return true;
-    case 1024: fwd_kernel<TIn, TOut, 32><<<blocks, 256, 0, st>>>(a); return true;
+    case 64: launch_fwd_n<TIn, TOut, 2>(a, st); return true;
+    case 128: launch_fwd_n<TIn, TOut, 4>(a, st); return true;
+    case 256: launch_fwd_n<TIn, TOut, 8>(a, st); return true;
+    case 512: launch_fwd_n<TIn, TOut, 16>(a, st); return true;
+    case 1024: launch_fwd_n<TIn, TOut, 32>(a, st); return true;
     default: return false;
   }
 }

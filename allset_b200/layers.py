@@ -149,7 +149,7 @@ class MLP(nn.Module):
 
 
 def _resolve(edge_index, n_src: int) -> Incidence:
-    if isinstance(edge_index, Incidence):
+    if isinstance(edge_index, Incidence) or hasattr(edge_index, 'sharded_segment_reduce'):
         return edge_index.with_n_src(n_src)
     if not isinstance(edge_index, Tensor):
         raise TypeError('edge_index must be a [2, nnz] tensor or an allset_b200.Incidence')
@@ -216,8 +216,18 @@ class PMA(nn.Module):
         tc_v = self._tc_v_ok(x)
         tc_score = tc_v and H * H * C <= 1024               # w_eff must fit the kernel's 4 KB side buffer
         chain = self._chain_ok(x)
-        xf = x if x.dtype == w_eff.dtype else x.to(w_eff.dtype)
-        score = None if tc_score else F.linear(xf, w_eff, b_eff)                           # [n_src, H] fp32
+        cd = self.rFF.compute_dtype()
+        # rows handed to the next half layer: fp32, except while training in bf16 mode (bf16 activations end to end)
+        out_dt = torch.bfloat16 if (chain and cd == torch.bfloat16 and torch.is_grad_enabled()) else w_eff.dtype
+        if tc_score:
+            score = None
+        elif chain and cd == torch.bfloat16:
+            # bf16 mode at scale: the skinny score GEMM takes the same bf16 rows as lin_V (fp32 accumulate AND fp32 result)
+            xb = x if x.dtype == cd else x.to(cd)
+            score = ops.linear_nb(xb, w_eff, out_fp32=True) + b_eff                         # [n_src, H] fp32
+        else:
+            xf = x if x.dtype == w_eff.dtype else x.to(w_eff.dtype)
+            score = F.linear(xf, w_eff, b_eff)                                              # [n_src, H] fp32
         if tc_v:
             # bf16 mode: V = lin_V(x) as ONE tcgen05 kernel that writes the bf16 rows the aggregation gathers; the same
             # launch computes the fp32 scores in its producer warps (no second pass over x)
@@ -249,11 +259,10 @@ class PMA(nn.Module):
         elif chain:
             # training / fp32 mode at scale: bias-free GEMM (bf16 operands in bf16 mode) + one rowop pass that adds the
             # bias and writes the rows in the storage dtype the aggregation gathers
-            cd = self.rFF.compute_dtype()
             xb = x if x.dtype == cd else x.to(cd)
             v = ops.rowop(ops.linear_nb(xb, self.lin_V.weight), self.lin_V.bias, out_dtype=self.agg_dtype or cd)
         else:
-            x_V = self.lin_V(xf)
+            x_V = self.lin_V(x if x.dtype == w_eff.dtype else x.to(w_eff.dtype))
             v = x_V if self.agg_dtype is None else x_V.to(self.agg_dtype)
         if out is None:
             out, alpha = ops.pma_aggregate(v, score, self.att_r, inc, H, self.negative_slope, return_alpha=want_alpha)
@@ -269,7 +278,6 @@ class PMA(nn.Module):
                 out = F.dropout(out, p=pdrop, training=True)
             applied = True
         elif chain and self.rFF._chain_ok(out):
-            cd = self.rFF.compute_dtype()
             y = ops.rowop(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps, out_dtype=cd)   # ln0 (:155)
             a = y
             for lin in self.rFF.lins[:-1]:                                   # rFF: no norms, no dropout (:76-80)
@@ -277,7 +285,7 @@ class PMA(nn.Module):
             last = self.rFF.lins[-1]
             out = ops.rowop(ops.linear_nb(a, last.weight), last.bias, relu=True, residual=y, gamma=self.ln1.weight,
                             beta=self.ln1.bias, eps=self.ln1.eps, relu_out=relu_out, drop_p=pdrop,
-                            out_dtype=score.dtype)                           # ln1(y + relu(rFF(y))) [relu, dropout], one pass
+                            out_dtype=out_dt)                                # ln1(y + relu(rFF(y))) [relu, dropout], one pass
             applied = True
         else:
             out = self.ln0(out.to(score.dtype))
@@ -304,8 +312,10 @@ class PMA(nn.Module):
     PACKED_MIN_SCORE_BYTES = None
 
     def _packed_ok(self, x, inc) -> bool:
-        t = inc.by_tgt
         H, d = self.heads, self.heads * self.hidden
+        if not isinstance(inc, Incidence):
+            return False
+        t = inc.by_tgt
         if self.PACKED_MIN_SCORE_BYTES is None or x.shape[0] * H * 4 < self.PACKED_MIN_SCORE_BYTES or H % 4 != 0:
             return False
         if t.long_ids is not None and t.long_ids.numel() > 0:
@@ -387,7 +397,11 @@ class HalfNLHconv(nn.Module):
         if isinstance(self.f_dec, MLP):
             if not (self.f_dec._tc_ok(x) or self.f_dec._chain_ok(x)):     # the fused paths read the storage dtype directly
                 x = x.to(io_dtype)
-            x = self.f_dec(x, final_relu=True, out_dtype=io_dtype, final_dropout=out_dropout)
+            # rows handed to the next half layer: the caller's dtype, except while training in bf16 mode (bf16 activations
+            # end to end: the next f_enc reads half the bytes)
+            out_dt = torch.bfloat16 if (self.agg_dtype == torch.bfloat16 and torch.is_grad_enabled()
+                                        and self.f_dec._chain_ok(x)) else io_dtype
+            x = self.f_dec(x, final_relu=True, out_dtype=out_dt, final_dropout=out_dropout)
         else:
             x = F.relu(self.f_dec(x.to(io_dtype)))
             if out_dropout > 0:

@@ -15,6 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn import Linear, Parameter
 
+from . import ops
 from .graph import Incidence, attach
 from .layers import MLP, HalfNLHconv
 
@@ -75,6 +76,10 @@ class SetGNN(nn.Module):
         self.agg_dtype = dtype
         for conv in list(self.V2EConvs) + list(self.E2VConvs):
             conv.set_agg_dtype(dtype)
+        tc = dtype if dtype == torch.bfloat16 else None          # bf16 mode: the classifier's Linears take bf16 operands too
+        self.classifier.tc_dtype = tc
+        if self.GPR and self.All_num_layers > 0:
+            self.MLP.tc_dtype = tc
 
     def reset_parameters(self):
         for group in (self.V2EConvs, self.E2VConvs, self.bnV2Es, self.bnE2Vs):
@@ -131,18 +136,22 @@ class SetGNN(nn.Module):
         if self.GPR:
             xs = [F.relu(self.MLP(x))]
             for i, _ in enumerate(self.V2EConvs):
-                x = F.relu(self.V2EConvs[i](x, v2e, norm, self.aggr))
+                x = self.V2EConvs[i](x, v2e, norm, self.aggr, relu_out=True).float()     # = F.relu(conv(.)), :460
                 x = F.dropout(x, p=self.dropout, training=self.training)
-                x = F.relu(self.E2VConvs[i](x, e2v, norm, self.aggr))
+                x = self.E2VConvs[i](x, e2v, norm, self.aggr, relu_out=True).float()     # :464
                 xs.append(x)
                 x = F.dropout(x, p=self.dropout, training=self.training)
             x = torch.stack(xs, dim=-1)
             x = self.GPRweights(x).squeeze()
-            x = self.classifier(x)
+            x = self.classifier(x, out_dtype=torch.float32)
         else:
-            x = F.dropout(x, p=0.2, training=self.training)     # input dropout, hard-coded in the reference
+            if self.training and self.agg_dtype == torch.bfloat16 and torch.is_grad_enabled() and ops.rowop_ok(x) \
+                    and x.shape[0] >= ops.FUSED_DENSE_MIN_ROWS:
+                x = ops.rowop(x, drop_p=0.2, out_dtype=torch.bfloat16)   # input dropout + cast to the bf16 mode's rows, one pass
+            else:
+                x = F.dropout(x, p=0.2, training=self.training)     # input dropout, hard-coded in the reference
             for i, _ in enumerate(self.V2EConvs):
                 x = self._half(self.V2EConvs[i], x, v2e, norm)                    # = dropout(relu(conv(.))), :475-476
                 x = self._half(self.E2VConvs[i], x, e2v, norm)                    # :478-479
-            x = self.classifier(x)
+            x = self.classifier(x, out_dtype=torch.float32)
         return x

@@ -70,6 +70,10 @@ def segment_reduce(x: torch.Tensor, inc: Incidence, weight: Optional[torch.Tenso
     reduce in {'sum', 'add', 'mean'} (torch_scatter spellings reachable from reference src/train.py:38,245)."""
     if reduce not in ('sum', 'add', 'mean'):
         raise ValueError("reduce must be 'sum', 'add' or 'mean', got %r" % (reduce,))
+    if hasattr(inc, 'sharded_segment_reduce'):              # one rank's share of a partitioned graph (sharded_model.py)
+        if x.dim() != 2 or x.shape[0] != inc.n_src:
+            raise ValueError('x must hold the %d source rows this rank owns, got %s' % (inc.n_src, tuple(x.shape)))
+        return inc.sharded_segment_reduce(_storage(x), weight, reduce)
     if not x.is_cuda:
         raise RuntimeError('allset_b200.segment_reduce: CUDA tensors only (no CPU fallback); got %s' % x.device)
     if x.dim() != 2 or x.shape[0] != inc.n_src:
@@ -107,7 +111,13 @@ class _PMA(torch.autograd.Function):
             grad_v, grad_score = _lib.pma_bwd(grad_out, v, score, stats, D, H, C, slope, s.rowptr, s.col, s.n_tgt,
                                               long_ids=s.long_ids, long_threshold=s.long_threshold)
         if ctx.needs_input_grad[2]:
-            grad_seed = grad_out.float().sum(dim=0).reshape(ctx.seed_shape).to(ctx.seed_dtype)
+            if grad_out.dtype == torch.bfloat16:
+                # column sums of a bf16 [n_tgt, d] matrix on the tensor cores (fp32 accumulate) instead of a cast + reduce
+                ones = torch.ones((1, grad_out.shape[0]), dtype=torch.bfloat16, device=grad_out.device)
+                col_sum = torch.mm(ones, grad_out, out_dtype=torch.float32)
+            else:
+                col_sum = grad_out.sum(dim=0)
+            grad_seed = col_sum.reshape(ctx.seed_shape).to(ctx.seed_dtype)
         return grad_v, grad_score, grad_seed, None, None, None, None
 
 
@@ -125,6 +135,12 @@ def pma_aggregate(v: torch.Tensor, score: torch.Tensor, seed: torch.Tensor, inc:
     if d % heads != 0:
         raise ValueError('feature width %d is not divisible by heads=%d' % (d, heads))
     C = d // heads
+    if hasattr(inc, 'sharded_pma_aggregate'):
+        if return_alpha:
+            raise NotImplementedError('attention weights are not assembled across ranks')
+        if v2.shape[0] != inc.n_src or tuple(score.shape) != (inc.n_src, heads) or seed.numel() != d:
+            raise ValueError('pma_aggregate: shape mismatch with the %d source rows this rank owns' % inc.n_src)
+        return inc.sharded_pma_aggregate(_storage(v2), score, seed, heads, negative_slope), None
     if v2.shape[0] != inc.n_src or tuple(score.shape) != (inc.n_src, heads) or seed.numel() != d:
         raise ValueError('pma_aggregate: shape mismatch v%s score%s seed%s n_src=%d'
                          % (tuple(v.shape), tuple(score.shape), tuple(seed.shape), inc.n_src))
@@ -267,18 +283,23 @@ def rowop(x: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = Fal
 
 class _LinearNB(torch.autograd.Function):
     """y = x @ W^T without bias, operands in `x.dtype` (bf16: tensor-core GEMM with fp32 accumulation; fp32: SGEMM), W
-    kept as the fp32 master parameter; dW is accumulated and returned in fp32."""
+    kept as the fp32 master parameter; dW is accumulated and returned in fp32.  `out_fp32` keeps the fp32 accumulator
+    as the result of a bf16 GEMM (attention scores)."""
 
     @staticmethod
-    def forward(ctx, x, w):
+    def forward(ctx, x, w, out_fp32):
         wc = w if w.dtype == x.dtype else w.to(x.dtype)
         ctx.save_for_backward(x, wc)
         ctx.w_dtype = w.dtype
+        if out_fp32 and x.dtype != torch.float32:
+            return torch.mm(x, wc.t(), out_dtype=torch.float32)
         return torch.mm(x, wc.t())
 
     @staticmethod
     def backward(ctx, dy):
         x, wc = ctx.saved_tensors
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
         dy = dy.contiguous()
         dx = torch.mm(dy, wc) if ctx.needs_input_grad[0] else None
         dw = None
@@ -289,11 +310,15 @@ class _LinearNB(torch.autograd.Function):
                 dw = torch.mm(dy.t(), x, out_dtype=torch.float32)
             if dw.dtype != ctx.w_dtype:
                 dw = dw.to(ctx.w_dtype)
-        return dx, dw
+        return dx, dw, None
 
 
-def linear_nb(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """x [rows, in] (bf16 | fp32) @ w[out, in]^T -> [rows, out] in x.dtype; the bias is left to the rowop that follows."""
+def linear_nb(x: torch.Tensor, w: torch.Tensor, out_fp32: bool = False) -> torch.Tensor:
+    """x [rows, in] (bf16 | fp32) @ w[out, in]^T -> [rows, out] in x.dtype (fp32 with `out_fp32`); the bias is left to
+    the rowop that follows."""
     if not torch.is_grad_enabled():
-        return torch.mm(x, (w if w.dtype == x.dtype else w.to(x.dtype)).t())
-    return _LinearNB.apply(x, w)
+        wc = w if w.dtype == x.dtype else w.to(x.dtype)
+        if out_fp32 and x.dtype != torch.float32:
+            return torch.mm(x, wc.t(), out_dtype=torch.float32)
+        return torch.mm(x, wc.t())
+    return _LinearNB.apply(x, w, out_fp32)

@@ -106,6 +106,31 @@ def range_shapes(rowptr: torch.Tensor, ranges: Sequence[Tuple[int, int]]) -> Lis
     return [(hi - lo, int(m)) for (lo, hi), m in zip(ranges, longest)]
 
 
+def peer_need_mask(rowptr: torch.Tensor, col: torch.Tensor, rows: int, ranges: Sequence[Tuple[int, int]], rank: int
+                   ) -> torch.Tensor:
+    """For a CSR slice (row r lists the OTHER side's ids it is incident to) and the other side's partition `ranges`:
+    uint8 [rows], bit j set iff row r has an incidence inside the range of the j-th other rank (ascending, skipping
+    `rank`) -- i.e. that rank will gather row r.  Pure index arithmetic (any device)."""
+    dev = rowptr.device
+    mask = torch.zeros(rows, dtype=torch.uint8, device=dev)
+    nnz = int(col.numel())
+    if rows == 0 or nnz == 0:
+        return mask
+    lens = (rowptr[1:rows + 1] - rowptr[:rows]).long()
+    row_of = torch.repeat_interleave(torch.arange(rows, device=dev), lens)
+    bounds = torch.tensor([hi for _, hi in ranges], device=dev, dtype=col.dtype)
+    owner = torch.bucketize(col[:nnz], bounds, right=True)             # range index of every incidence
+    j = 0
+    for q in range(len(ranges)):
+        if q == rank:
+            continue
+        hit = torch.zeros(rows, dtype=torch.bool, device=dev)
+        hit[row_of[owner == q]] = True
+        mask |= hit.to(torch.uint8) << j
+        j += 1
+    return mask
+
+
 class ReplicatedRows(object):
     """A [rows, d] feature buffer replicated on every rank of the group, allocated in SYMMETRIC memory
     (torch.distributed._symmetric_memory) so that each rank holds peer-mapped pointers to all replicas: the fused
@@ -137,10 +162,11 @@ class ReplicatedRows(object):
             except Exception:  # noqa
                 self.multicast_ptr = 0
 
-    def peer_ptrs(self, first_row: int):
+    def peer_ptrs(self, first_row: int, unicast: bool = False):
         """Where the kernel must ALSO store row `first_row`...: the multicast address when the switch can replicate,
-        else that row in every other rank's replica."""
-        if self.multicast_ptr:
+        else (or with `unicast`: a selective exchange addresses peers one by one) that row in every other rank's replica,
+        in ascending rank order -- the bit order of `peer_need_mask`."""
+        if self.multicast_ptr and not unicast:
             return [self.multicast_ptr + first_row * self.row_bytes]
         return [q + first_row * self.row_bytes for r, q in enumerate(self.ptrs) if r != self.rank]
 
@@ -175,6 +201,7 @@ class ShardedIncidence(object):
         # Every rank holds the full rowptr, so no collective is needed to agree.
         self.e_shapes = range_shapes(t.rowptr, self.e_ranges)
         self.v_shapes = range_shapes(s.rowptr, self.v_ranges)
+        self._need_masks = {}
         if world == 1:
             self.e_csr, self.v_csr = t, s
         else:
@@ -183,44 +210,62 @@ class ShardedIncidence(object):
             rp, col, p0 = slice_csr(s.rowptr, s.col, self.v_lo, self.v_hi)
             self.v_csr = Csr(rp, col, s.perm[p0:p0 + col.numel()], self.v_hi - self.v_lo, self.n_e)
 
-    def fused_ok(self, direction: str, x_src, out_full) -> bool:
+    def fused_ok(self, direction: str, x_src, out_full, heads: int = 0) -> bool:
         """Whether EVERY rank's range of `direction` ('e': V->E, 'v': E->V) is taken by the fused-exchange stream
-        kernel for rows shaped like x_src.  Pure function of (graph, world, dtype, width): identical on all ranks."""
+        kernel for rows shaped like x_src (heads > 0: the PMA kernel).  Pure function of (graph, world, dtype, width):
+        identical on all ranks."""
         from . import _lib
         if self.world == 1 or not isinstance(out_full, ReplicatedRows):
             return False
         shapes = self.e_shapes if direction == 'e' else self.v_shapes
-        return all(_lib.fused_exchange_eligible(x_src.dtype, x_src.shape[1], rows, longest) for rows, longest in shapes)
+        return all(_lib.fused_exchange_eligible(x_src.dtype, x_src.shape[1], rows, heads) for rows, _ in shapes)
+
+    def need_mask(self, direction: str) -> torch.Tensor:
+        """uint8 [rows of this rank's range]: bit j set = peer j (the j-th OTHER rank in ascending order) needs the row.
+        direction 'v': vertex rows, needed by the ranks whose hyperedge range contains the vertex (what the next V->E
+        gathers); 'e': hyperedge rows, needed by the ranks whose vertex range meets the hyperedge.  Built on first use
+        from the CSR slice this rank already holds."""
+        hit = self._need_masks.get(direction)
+        if hit is None:
+            if direction == 'v':
+                csr, ranges = self.v_csr, self.e_ranges          # vertex -> hyperedges it belongs to
+            else:
+                csr, ranges = self.e_csr, self.v_ranges          # hyperedge -> member vertices
+            hit = self._need_masks[direction] = peer_need_mask(csr.rowptr, csr.col, csr.n_tgt, ranges, self.rank)
+        return hit
 
     # -- AllDeepSets ------------------------------------------------------------------------------------------
-    def _reduce(self, direction, csr, x_src, out_full, lo, hi, mean):
+    def _reduce(self, direction, csr, x_src, out_full, lo, hi, mean, selective=False):
         """Reduce this rank's target range into rows [lo, hi) of the replicated buffer.  `out_full` is a plain tensor
         (exchange = a later all-gather) or a ReplicatedRows (exchange fused into the kernel's epilogue).  Returns True
         when the exchange has already been issued by the kernel -- the same value on every rank (`fused_ok`); a fused
-        launch the library then rejects raises instead of silently diverging from the peers."""
+        launch the library then rejects raises instead of silently diverging from the peers.  `selective`: send a row
+        only to the peers that will gather it (`need_mask`; needs per-peer addresses, not the multicast one)."""
         from . import _lib
         if self.fused_ok(direction, x_src, out_full):
+            mask = self.need_mask(direction) if selective else None
             _lib.segreduce_fwd_bcast(x_src, csr.rowptr, csr.col, csr.n_tgt, mean, out_full.tensor[lo:hi],
-                                     out_full.peer_ptrs(lo))
+                                     out_full.peer_ptrs(lo, unicast=selective), peer_mask=mask)
             return True
         t = out_full.tensor if isinstance(out_full, ReplicatedRows) else out_full
         _lib.segreduce_fwd(x_src, csr.rowptr, csr.col, csr.n_tgt, mean, long_ids=csr.long_ids,
                            long_threshold=csr.long_threshold, out=t[lo:hi], max_segment_len=csr.max_len)
         return False
 
-    def v2e_reduce(self, x_v, x_e_full, mean: bool = False):
-        return self._reduce('e', self.e_csr, _plain(x_v), x_e_full, self.e_lo, self.e_hi, mean)
+    def v2e_reduce(self, x_v, x_e_full, mean: bool = False, selective: bool = False):
+        return self._reduce('e', self.e_csr, _plain(x_v), x_e_full, self.e_lo, self.e_hi, mean, selective)
 
-    def e2v_reduce(self, x_e, x_v_full, mean: bool = False):
-        return self._reduce('v', self.v_csr, _plain(x_e), x_v_full, self.v_lo, self.v_hi, mean)
+    def e2v_reduce(self, x_e, x_v_full, mean: bool = False, selective: bool = False):
+        return self._reduce('v', self.v_csr, _plain(x_e), x_v_full, self.v_lo, self.v_hi, mean, selective)
 
     # -- AllSetTransformer ------------------------------------------------------------------------------------
-    def _pma(self, direction, csr, v, score, seed, heads, out_full, lo, hi, slope):
+    def _pma(self, direction, csr, v, score, seed, heads, out_full, lo, hi, slope, selective=False):
         from . import _lib
         C = v.shape[1] // heads
-        if heads % 4 == 0 and self.fused_ok(direction, v, out_full):
+        if self.fused_ok(direction, v, out_full, heads):
+            mask = self.need_mask(direction) if selective else None
             _lib.pma_fwd_bcast(v, score, seed, heads, C, slope, csr.rowptr, csr.col, csr.n_tgt,
-                               out_full.tensor[lo:hi], out_full.peer_ptrs(lo))
+                               out_full.tensor[lo:hi], out_full.peer_ptrs(lo, unicast=selective), peer_mask=mask)
             return True
         t = out_full.tensor if isinstance(out_full, ReplicatedRows) else out_full
         _lib.pma_fwd(v, score, seed, heads, C, slope, csr.rowptr, csr.col, csr.n_tgt, want_stats=False,
@@ -228,11 +273,13 @@ class ShardedIncidence(object):
                      max_segment_len=csr.max_len)
         return False
 
-    def v2e_pma(self, v_v, score_v, seed, heads, out_e_full, slope: float = 0.2):
-        return self._pma('e', self.e_csr, _plain(v_v), score_v, seed, heads, out_e_full, self.e_lo, self.e_hi, slope)
+    def v2e_pma(self, v_v, score_v, seed, heads, out_e_full, slope: float = 0.2, selective: bool = False):
+        return self._pma('e', self.e_csr, _plain(v_v), score_v, seed, heads, out_e_full, self.e_lo, self.e_hi, slope,
+                         selective)
 
-    def e2v_pma(self, v_e, score_e, seed, heads, out_v_full, slope: float = 0.2):
-        return self._pma('v', self.v_csr, _plain(v_e), score_e, seed, heads, out_v_full, self.v_lo, self.v_hi, slope)
+    def e2v_pma(self, v_e, score_e, seed, heads, out_v_full, slope: float = 0.2, selective: bool = False):
+        return self._pma('v', self.v_csr, _plain(v_e), score_e, seed, heads, out_v_full, self.v_lo, self.v_hi, slope,
+                         selective)
 
     # -- exchanges --------------------------------------------------------------------------------------------
     def gather_e(self, x_e_full, fused: bool = False):

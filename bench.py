@@ -63,6 +63,9 @@ def parse_args():
     ap.add_argument('--no-mlp', action='store_true')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'fused', 'nccl'],
                     help='N>1: fused = P2P stores from the kernel epilogue into symmetric memory; nccl = all-gather after')
+    ap.add_argument('--full-xv', action='store_true',
+                    help='N>1 with X_v replication: send every updated vertex row to every rank (north_star\'s plain all-gather) '
+                         'instead of only to the ranks that gather it')
     ap.add_argument('--replicate-xv', action='store_true',
                     help='N>1: also replicate the updated X_v inside every step (needed only when another layer follows)')
     return ap.parse_args()
@@ -229,6 +232,41 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def bind_host_memory_near_gpu(dev_index):
+    """Pinned staging buffers should live on the NUMA node the GPU hangs off: with 8 ranks allocating on one node every
+    H2D / D2H crosses the socket interconnect (round 1: the 8-GPU e2e moved 60 GB/s in aggregate).  Best effort, no
+    dependency: reads the GPU's node from sysfs and sets this thread's memory policy to PREFER it (raw set_mempolicy
+    syscall; libnuma is not in the image).  Returns what it did for the JSON line."""
+    import ctypes
+    import torch
+    info = {'gpu_numa_node': None, 'nodes': None, 'policy': 'unchanged'}
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        bus = '%04x:%02x:%02x.0' % (getattr(pr, 'pci_domain_id', 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
+        nodes = [n for n in os.listdir('/sys/devices/system/node') if n.startswith('node')]
+        info.update(gpu_numa_node=node, nodes=len(nodes), pci=bus)
+        if node >= 0 and len(nodes) > 1:
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))      # set_mempolicy(MPOL_PREFERRED, ...)
+            info['policy'] = 'MPOL_PREFERRED node %d' % node if rc == 0 else 'set_mempolicy failed errno %d' % ctypes.get_errno()
+            try:
+                cpus = set()
+                for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+                    lo, _, hi = part.partition('-')
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+                allowed = cpus & os.sched_getaffinity(0)
+                if allowed:
+                    os.sched_setaffinity(0, allowed)
+                    info['cpus'] = '%d cpus of node %d' % (len(allowed), node)
+            except Exception as exc:  # noqa
+                info['cpus'] = repr(exc)
+    except Exception as exc:  # noqa
+        info['error'] = repr(exc)
+    return info
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------------
@@ -336,12 +374,15 @@ def run_b200(a):
         if marks: marks[1].record()
         sh.gather_e(x_e, fe)
         if marks: marks[2].record()
-        fv = sh.e2v_reduce(x_e, x_v2 if replicate[0] else plain(x_v2))
+        # the updated X_v goes only to the ranks whose hyperedge range gathers the row (per-row peer mask): what the
+        # next layer's V->E reads, about half of north_star's full all-gather on this graph at 8 ranks
+        fv = sh.e2v_reduce(x_e, x_v2 if replicate[0] else plain(x_v2), selective=selective_xv)
         if marks: marks[3].record()
         if replicate[0]:
             sh.gather_v(x_v2, fv)
         if marks: marks[4].record()
 
+    selective_xv = world > 1 and not a.full_xv and isinstance(x_v2, sharding.ReplicatedRows)
     sampler = ClockSampler(local_rank)
     sampler.start()
     total_ms, ph = timed_steps(sum_step, 4, a.steps, a.warmup)
@@ -356,7 +397,20 @@ def run_b200(a):
         t, sgl = v2e.by_tgt, v2e.by_src
         ref_e = _lib.segreduce_fwd(x_v, t.rowptr, t.col, t.n_tgt, False, long_ids=t.long_ids, long_threshold=t.long_threshold)
         ref_v = _lib.segreduce_fwd(ref_e, sgl.rowptr, sgl.col, sgl.n_tgt, False, long_ids=sgl.long_ids, long_threshold=sgl.long_threshold)
-        ok = bool(torch.equal(plain(x_e), ref_e)) and bool(torch.equal(plain(x_v2), ref_v))
+        if selective_xv:
+            # a rank holds its own vertex rows and the rows its hyperedge range gathers -- exactly what the next
+            # layer's V->E reads: check those rows, then the next V->E itself
+            need = torch.zeros(Nv, dtype=torch.bool, device=dev)
+            need[sh.v_lo:sh.v_hi] = True
+            need[sh.e_csr.col.long()] = True
+            ok = bool(torch.equal(plain(x_e), ref_e)) and bool(torch.equal(plain(x_v2)[need], ref_v[need]))
+            nxt = torch.empty((sh.e_hi - sh.e_lo, d), dtype=dtype, device=dev)
+            _lib.segreduce_fwd(plain(x_v2), sh.e_csr.rowptr, sh.e_csr.col, sh.e_csr.n_tgt, False, out=nxt)
+            ref_nxt = _lib.segreduce_fwd(ref_v, t.rowptr, t.col, t.n_tgt, False)
+            ok = ok and bool(torch.equal(nxt, ref_nxt[sh.e_lo:sh.e_hi]))
+            del nxt, ref_nxt, need
+        else:
+            ok = bool(torch.equal(plain(x_e), ref_e)) and bool(torch.equal(plain(x_v2), ref_v))
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         verified = bool(flag.item())
@@ -379,7 +433,8 @@ def run_b200(a):
         replicate[0] = not a.replicate_xv
         o_ms, o_ph = timed_steps(sum_step, 4, max(5, a.steps // 2), 2)
         o_steps = max(5, a.steps // 2)
-        other = {'replicate_xv': replicate[0], 'value': Me / (o_ms / o_steps * 1e-3), 'unit': UNIT,
+        other = {'replicate_xv': replicate[0], 'xv_exchange': 'rows go to the ranks that gather them (per-row peer mask)'
+                 if selective_xv else 'every row to every rank', 'value': Me / (o_ms / o_steps * 1e-3), 'unit': UNIT,
                  'ms_per_step': o_ms / o_steps,
                  'phases_ms': {'v2e': o_ph[0], 'exchange_x_e': o_ph[1], 'e2v': o_ph[2], 'exchange_x_v': o_ph[3]}}
         replicate[0] = a.replicate_xv
@@ -390,10 +445,20 @@ def run_b200(a):
         # Serving-style pipeline: every step still copies ITS input from pinned host memory and ITS result back to
         # the host, but the H2D of step k+1 and the D2H of step k-1 run on their own streams (PCIe is full duplex) while
         # step k computes.  Double-buffered on both sides; the timed region ends when the last D2H has landed.
-        x_host = torch.empty((Nv, d), dtype=dtype).pin_memory()
-        x_host.copy_(x_v)
+        numa = bind_host_memory_near_gpu(local_rank) if world > 1 else None
         out_rows = sh.v_hi - sh.v_lo
+        if world == 1:
+            x_host = torch.empty((Nv, d), dtype=dtype).pin_memory()
+            x_host.copy_(x_v)
+            x_host_mine = x_host
+        else:
+            # a rank only ever reads ITS rows of the host matrix: pin just those (8 ranks x 2.56 GB of pinned memory on one
+            # node was part of round 1's 8-GPU e2e collapse)
+            x_host = None
+            x_host_mine = torch.empty((out_rows, d), dtype=dtype).pin_memory()
+            x_host_mine.copy_(x_v[sh.v_lo:sh.v_hi])
         out_host = [torch.empty((out_rows, d), dtype=dtype).pin_memory() for _ in range(2)]
+        ph_ev = {'h2d': [], 'gather': [], 'compute': [], 'd2h': []}
         x_in = [torch.empty_like(x_v) for _ in range(2)]
         xv_out = [torch.empty_like(x_v) for _ in range(2)] if world > 1 else None
         inc_v2e, inc_e2v = v2e, v2e.reversed()
@@ -408,16 +473,24 @@ def run_b200(a):
                     s_in.wait_event(state['comp_done'][b])                   # x_in[b] no longer being read
                 else:
                     s_in.wait_stream(cur)
+                t0 = torch.cuda.Event(enable_timing=True); t0.record(s_in)
                 if world == 1:
                     x_in[b].copy_(x_host, non_blocking=True)                 # H2D of this step's input
+                    t1 = torch.cuda.Event(enable_timing=True); t1.record(s_in)
+                    t2 = t1
                 else:
                     # every rank pulls 1/N of the input over ITS PCIe link, NVLink replicates it (V->E needs all rows)
-                    x_in[b][sh.v_lo:sh.v_hi].copy_(x_host[sh.v_lo:sh.v_hi], non_blocking=True)
+                    x_in[b][sh.v_lo:sh.v_hi].copy_(x_host_mine, non_blocking=True)
+                    t1 = torch.cuda.Event(enable_timing=True); t1.record(s_in)
                     sharding.allgather_rows(x_in[b], sh.v_ranges, rank)
+                    t2 = torch.cuda.Event(enable_timing=True); t2.record(s_in)
+                if _marks is not None:
+                    ph_ev['h2d'].append((t0, t1)); ph_ev['gather'].append((t1, t2))
                 ev = torch.cuda.Event(); ev.record(s_in); state['in_done'][b] = ev
             cur.wait_event(state['in_done'][b])
             if state['out_done'][b] is not None:
                 cur.wait_event(state['out_done'][b])                         # result buffer b has been read back
+            c0 = torch.cuda.Event(enable_timing=True); c0.record(cur)
             if world == 1:
                 xe = allset_b200.segment_reduce(x_in[b], inc_v2e, None, 'sum')   # the call a user makes
                 res = allset_b200.segment_reduce(xe, inc_e2v, None, 'sum')
@@ -425,11 +498,14 @@ def run_b200(a):
             else:
                 sh.layer_pair_sum(x_in[b], x_e, xv_out[b], replicate_v=False)
                 res = xv_out[b][sh.v_lo:sh.v_hi]                             # each rank reads back the rows it owns
-            ev = torch.cuda.Event(); ev.record(cur); state['comp_done'][b] = ev
+            ev = torch.cuda.Event(enable_timing=True); ev.record(cur); state['comp_done'][b] = ev
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev)
+                d0 = torch.cuda.Event(enable_timing=True); d0.record(s_out)
                 out_host[b].copy_(res, non_blocking=True)                    # D2H of the result
-                ev2 = torch.cuda.Event(); ev2.record(s_out); state['out_done'][b] = ev2
+                ev2 = torch.cuda.Event(enable_timing=True); ev2.record(s_out); state['out_done'][b] = ev2
+            if _marks is not None:
+                ph_ev['compute'].append((c0, ev)); ph_ev['d2h'].append((d0, ev2))
             state['k'] = k + 1
 
         def e2e_run(steps, warmup):
@@ -440,7 +516,7 @@ def run_b200(a):
             start, end = ev(), ev()
             start.record()
             for _ in range(steps):
-                e2e_step(None)
+                e2e_step(True)
             torch.cuda.current_stream().wait_stream(s_out)                   # the last result must be on the host
             end.record()
             barrier()
@@ -448,14 +524,15 @@ def run_b200(a):
 
         e2e_steps = max(4, min(a.steps, 20))
         e2e_ms = e2e_run(e2e_steps, 3)
-        e2e = {'value': Me / (e2e_ms / e2e_steps * 1e-3), 'unit': UNIT,
+        e2e_phases = {k: max_over_ranks(sum(a_.elapsed_time(b_) for a_, b_ in v) / max(len(v), 1)) for k, v in ph_ev.items()}
+        e2e = {'value': Me / (e2e_ms / e2e_steps * 1e-3), 'unit': UNIT, 'phases_ms': e2e_phases, 'numa': numa,
                'h2d_bytes_per_step': int(Nv * d * es), 'd2h_bytes_per_step': int(Nv * d * es),
                'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
                'pipeline': 'H2D(k+1) || compute(k) || D2H(k-1), double-buffered, 3 streams' + ('' if world == 1 else
                             '; each rank copies 1/N of X_v from the host and NCCL all-gathers it over NVLink'),
                'api': 'allset_b200.segment_reduce(x, Incidence, None, "sum") x2' if world == 1
                       else 'allset_b200.sharding.ShardedIncidence.layer_pair_sum'}
-        del x_host, out_host, x_in, xv_out
+        del x_host, x_host_mine, out_host, x_in, xv_out
     clocks = sampler.stop()
 
     # ---- AllSetTransformer (PMA, heads=H) on the same graph: reported beside the headline -----------------------
@@ -588,7 +665,7 @@ def run_b200(a):
                        'hyperedge-sharded V->E / vertex-sharded E->V x%d; X_e exchanged between the directions every '
                        'step; updated X_v %s' % (world, 'replicated every step (another layer can follow)' if a.replicate_xv
                                                 else 'left vertex-sharded (last layer: the next op is row-parallel); see other_mode'),
-                       'exchange': exchange,
+                       'exchange': exchange, 'push': os.environ.get('ALLSET_PUSH', 'bulk (TMA cp.async.bulk from a staging slot)'),
                        'l2': 'inputs larger than L2 (X_v %.2f GB, col %.2f GB per step; no flush)'
                              % (Nv * d * es / 1e9, nnz * 4 / 1e9)},
             'clocks': clocks,

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ALLSET_ABI_VERSION 1
+#define ALLSET_ABI_VERSION 2
 
 enum { ALLSET_F32 = 0, ALLSET_BF16 = 1 };
 enum { ALLSET_SUM = 0, ALLSET_MEAN = 1 };
@@ -54,10 +54,19 @@ int allset_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* allset_last_error(void);
 
-/* 1 when (dtype, d, n_tgt) takes the STREAM kernels (rows of 128/256/512/1024 bytes, enough target segments).  Those
- * kernels reduce a segment of any length inside one warp's stream, so a caller whose longest segment is moderate
- * (<= ~2K incidences) should then pass n_long = 0 instead of bucketing long segments for the CTA kernels. */
+/* 1 when (dtype, d, n_tgt) takes the STREAM kernels (rows of 128/256/512/1024 bytes, enough target segments).  Given a
+ * workspace (below) those kernels reduce segments of ANY length at full rate -- a chunk boundary that falls inside a long
+ * segment cuts it and the pieces are combined in stream order -- so a caller should then pass n_long = 0 instead of
+ * bucketing long segments for the CTA kernels.  allset_pma_stream_eligible: the same question for the PMA kernel, which
+ * additionally needs H % 4 == 0 and lane chunks that do not straddle heads. */
 int allset_stream_eligible(int dtype, int32_t d, int64_t n_tgt);
+int allset_pma_stream_eligible(int dtype, int32_t H, int32_t C, int64_t n_tgt);
+
+/* Bytes of the optional workspace of the stream kernels for rows of d elements (any dtype, any H).  The caller
+ * zero-initialises it ONCE; every launch leaves it zeroed, so it can be reused by successive launches on one stream
+ * (not by concurrent launches on different streams).  It holds the partial results and ready flags of the pieces of
+ * long segments that were cut at a warp-chunk boundary.  ws == NULL: segments are never cut. */
+size_t allset_stream_workspace_bytes(int32_t d);
 
 /* --- incidence container ------------------------------------------------------------------
  * Replaces the implicit work torch_scatter does on every call (unsorted COO index + a
@@ -93,14 +102,19 @@ int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d,
                          const float* w, const float* src_scale,
                          int64_t n_tgt, int op,
                          const int32_t* long_ids, int32_t n_long, int32_t long_threshold,
-                         void* out, void* stream);
+                         void* out, void* ws, size_t ws_bytes, void* stream);
 
 /* Fused compute + exchange (multi-GPU, one process per GPU; no counterpart in the single-device reference).
- * Same reduction as allset_segreduce_fwd, but every reduced row is ALSO stored, from the kernel's epilogue, into the
- * same row of `n_peers` (<= 7) peer replicas over NVLink (P2P stores), so the all-gather of the rank's row range that
- * would follow the kernel costs no extra launch and overlaps the reduce.
+ * Same reduction as allset_segreduce_fwd, but every reduced row is ALSO sent, from the kernel's epilogue, to the same row
+ * of `n_peers` (<= 7) peer replicas over NVLink, so the all-gather of the rank's row range that would follow the kernel
+ * costs no extra launch and overlaps the reduce.  By default the row is parked in a shared-memory staging slot and handed
+ * to the TMA (cp.async.bulk shared -> global, one bulk store per peer) so that NVLink back-pressure never stalls the
+ * gathering warps; ALLSET_PUSH=direct makes the reducing warp store to the peers itself.
  *   out          this rank's rows inside its own replica (row 0 of the rank's range)
  *   peer_outs    HOST array of n_peers peer-mapped DEVICE pointers: the address of that same row in each peer replica
+ *                (or ONE multicast address that the NVSwitch replicates into every replica)
+ *   peer_mask    DEVICE [n_tgt] bytes or NULL: bit j of byte t set = peer j needs row t (a vertex row is needed only by
+ *                the ranks whose hyperedge range contains the vertex); NULL = every peer gets every row
  * The caller must order a cross-rank barrier after the kernel before any rank reads the gathered rows.
  * Returns ALLSET_EUNSUPPORTED when the shape is not eligible for the stream kernel (row bytes not in
  * {128,256,512,1024}, too few segments): call allset_segreduce_fwd and all-gather instead. */
@@ -108,7 +122,15 @@ int allset_segreduce_fwd_bcast(const void* x, int dtype, int64_t n_src, int32_t 
                                const int32_t* rowptr, const int32_t* col,
                                const float* w, const float* src_scale,
                                int64_t n_tgt, int op,
-                               void* out, void* const* peer_outs, int32_t n_peers, void* stream);
+                               void* out, void* const* peer_outs, int32_t n_peers, const uint8_t* peer_mask,
+                               void* ws, size_t ws_bytes, void* stream);
+
+/* The exchange by itself: send rows [0, n_rows) of this rank's range (already stored in its own replica at `rows`) to the
+ * same rows of n_peers (<= 7) peer replicas; peer_rows / peer_mask as in allset_segreduce_fwd_bcast.  For rows whose
+ * producer is not one of the fused-exchange kernels (the output of a GEMM + glue pass in a sharded SetGNN layer).
+ * row_bytes must be a multiple of 16. */
+int allset_push_rows(const void* rows, int64_t n_rows, int64_t row_bytes, void* const* peer_rows, int32_t n_peers,
+                     const uint8_t* peer_mask, void* stream);
 
 /* --- dense glue of MLP / PMA ----------------------------------------------------------------
  * out[r, :] = LayerNorm_{gamma,beta,eps}( residual[r, :] + relu( x[r, :] + bias ) ), each stage optional
@@ -221,7 +243,7 @@ int allset_pma_fwd(const void* v, const float* score, const float* seed, int dty
                    int32_t H, int32_t C, float slope,
                    const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
                    const int32_t* long_ids, int32_t n_long, int32_t long_threshold,
-                   void* out, float* stats, void* stream);
+                   void* out, float* stats, void* ws, size_t ws_bytes, void* stream);
 
 /* allset_pma_fwd with STRIDED sources: value row i at (char*)v + i * v_pitch, its H fp32 scores at (char*)score +
  * i * s_pitch (both pitches in bytes, multiples of 16).  With v_pitch == s_pitch and score == v + H*C*sizeof(T) the
@@ -232,13 +254,14 @@ int allset_pma_fwd(const void* v, const float* score, const float* seed, int dty
 int allset_pma_fwd_strided(const void* v, int64_t v_pitch, const float* score, int64_t s_pitch, const float* seed,
                            int dtype, int32_t H, int32_t C, float slope,
                            const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
-                           void* out, float* stats, void* stream);
+                           void* out, float* stats, void* ws, size_t ws_bytes, void* stream);
 
 /* allset_pma_fwd with the fused exchange of allset_segreduce_fwd_bcast (same contract for out / peer_outs). */
 int allset_pma_fwd_bcast(const void* v, const float* score, const float* seed, int dtype,
                          int32_t H, int32_t C, float slope,
                          const int32_t* rowptr, const int32_t* col, int64_t n_tgt,
-                         void* out, float* stats, void* const* peer_outs, int32_t n_peers, void* stream);
+                         void* out, float* stats, void* const* peer_outs, int32_t n_peers,
+                         const uint8_t* peer_mask, void* ws, size_t ws_bytes, void* stream);
 
 /* Attention weights per incidence in CSR order (PMA.forward(return_attention_weights=True),
  * src/layers.py:159-166): alpha[k, h] for k in segment t from score and stats. */

@@ -526,33 +526,86 @@ def test_cuda_graph_replay_matches_eager():
     assert torch.equal(g(), eager2)
 
 
-def test_stream_kernels_own_moderately_long_segments():
-    """Power-law graph large enough for the stream kernels: the 2048-row hyperedge is reduced inside one warp's stream
-    (no CTA bucket), for sum / mean / PMA, and matches the oracle."""
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_stream_kernels_cut_long_segments(dtype):
+    """Power-law graph large enough for the stream kernels, with 4096-row hyperedges: a chunk boundary that falls inside
+    a long segment cuts it, the pieces are combined through the workspace (decoupled look-back) -- sum / mean / weighted
+    / PMA (incl. the softmax statistics) match the oracle and the bucketed group + CTA path, forward and backward, and
+    the workspace is left zeroed."""
     from allset_b200 import _lib, synthetic
     n, m, d, heads = 300_000, 120_000, 128, 8
-    ei = synthetic.powerlaw_hypergraph(n, m, 2, 2048, 2.0, seed=11, device=dev())
+    ei = synthetic.powerlaw_hypergraph(n, m, 2, 4096, 1.5, seed=11, device=dev())      # alpha 1.5: many long hyperedges
     he = ei[1] - n
     v2e = ab().Incidence.from_coo(ei[0], he, n_src=n, n_tgt=m)
     t = v2e.by_tgt
-    assert t.long_ids is not None and t.max_len == 2048
-    x = synthetic.features(n, d, torch.float32, device=dev())
-    assert _lib.stream_takes_long_segments(x, m, t.max_len)
+    lens = (t.rowptr[1:] - t.rowptr[:-1])
+    assert t.long_ids is not None and int(lens.max()) == 4096 and int((lens >= 256).sum()) > 1000
+    assert _lib.stream_eligible(dtype, d, m) and _lib.stream_eligible(dtype, d, m, heads)
+    x = synthetic.features(n, d, dtype, device=dev())
+    xr = x.float().cpu()
     src_c, he_c = ei[0].cpu(), he.cpu()
-    for reduce in ('sum', 'mean'):
-        out = ab().segment_reduce(x, v2e, None, reduce)
-        ref = O.aggregate_sum_mean(x.cpu(), src_c, he_c, None, reduce)
-        torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=2e-3)
+    w = (torch.rand(v2e.nnz, generator=torch.Generator().manual_seed(5)) + 0.5)
+    lo = dtype == torch.bfloat16
+    for reduce, weight in (('sum', None), ('mean', None), ('sum', w)):
+        out = ab().segment_reduce(x, v2e, None if weight is None else weight.to(dev()), reduce)
+        ref = O.aggregate_sum_mean(xr, src_c, he_c, weight, reduce)
+        torch.testing.assert_close(out.float().cpu(), ref, rtol=1e-2 if lo else 1e-4, atol=0.5 if lo else 3e-3)
+        # same answer as the bucketed group + CTA kernels (per-segment association differs for cut segments only)
+        w_csr = None if weight is None else weight.to(dev()).index_select(0, t.perm64)
+        out_group = _lib.segreduce_fwd(x, t.rowptr, t.col, m, reduce == 'mean', w=w_csr, long_ids=t.long_ids,
+                                       long_threshold=t.long_threshold, allow_stream=False)
+        torch.testing.assert_close(out.float(), out_group.float(), rtol=1e-2 if lo else 1e-5, atol=0.5 if lo else 2e-3)
+        short = (lens < 256).nonzero().squeeze(1)[:50_000]
+        if weight is None and not lo:
+            assert torch.equal(out[short], out_group[short])                 # uncut segments: the same sequential sums
+    ws = _lib.stream_workspace(x.device, d)
+    assert int(ws.view(torch.int32)[: 148 * 24 * 8].abs().max()) == 0        # every flag consumed and cleared
     score = torch.randn(n, heads, device=dev())
     seed = torch.randn(1, heads, d // heads, device=dev())
-    out, _ = ab().pma_aggregate(x, score, seed, v2e, heads)
-    ref, _ = O.aggregate_pma(x.cpu().view(n, heads, -1), score.cpu(), seed.cpu(), src_c, he_c)
-    torch.testing.assert_close(out.cpu(), ref.reshape(m, d), **FP32)
-    # same answer as the bucketed group + CTA path
-    out_group = _lib.segreduce_fwd(x, t.rowptr, t.col, m, False, long_ids=t.long_ids, long_threshold=t.long_threshold)
-    out_stream = _lib.segreduce_fwd(x, t.rowptr, t.col, m, False, long_ids=t.long_ids, long_threshold=t.long_threshold,
-                                    max_segment_len=t.max_len)
-    torch.testing.assert_close(out_stream, out_group, rtol=1e-5, atol=1e-3)
+    out, alpha = ab().pma_aggregate(x, score, seed, v2e, heads, return_alpha=True)
+    ref, ref_alpha = O.aggregate_pma(xr.view(n, heads, -1), score.cpu(), seed.cpu(), src_c, he_c)
+    torch.testing.assert_close(out.float().cpu(), ref.reshape(m, d), **(BF16 if lo else FP32))
+    torch.testing.assert_close(alpha.cpu(), ref_alpha, rtol=1e-4, atol=1e-6)   # from the (max, sum) of the merged pieces
+    assert int(ws.view(torch.int32)[: 148 * 24 * 8].abs().max()) == 0
+    # backward of the sum (the same kernel on the transposed CSR, whose long segments are high-degree vertices -- none here)
+    if not lo:
+        xg = x.clone().requires_grad_(True)
+        go = torch.randn(m, d, device=dev())
+        (ab().segment_reduce(xg, v2e, None, 'sum') * go).sum().backward()
+        xc = xr.clone().requires_grad_(True)
+        (O.aggregate_sum_mean(xc, src_c, he_c, None, 'sum') * go.cpu()).sum().backward()
+        torch.testing.assert_close(xg.grad.cpu(), xc.grad, rtol=1e-4, atol=1e-3)
+
+
+def test_stream_kernels_cut_high_degree_vertices_in_the_transposed_direction():
+    """E->V over a graph where a few vertices sit in tens of thousands of hyperedges (hub vertices): the by-node CSR has
+    segments far longer than a warp chunk, cut into many pieces (middle pieces publish flag 2)."""
+    from allset_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    n, m, d = 200_000, 150_000, 64
+    nnz = 1_500_000
+    node = torch.randint(0, n, (nnz,), generator=g)
+    hub = torch.rand(nnz, generator=g) < 0.08
+    node[hub] = torch.randint(0, 3, (int(hub.sum()),), generator=g)            # vertices 0..2: ~40 000 incidences each
+    he = torch.randint(0, m, (nnz,), generator=g)
+    node, order = torch.sort(node, stable=True)
+    he = he[order]
+    e2v = ab().Incidence.from_coo(he.to(dev()), node.to(dev()), n_src=m, n_tgt=n)
+    lens = e2v.by_tgt.rowptr[1:] - e2v.by_tgt.rowptr[:-1]
+    assert int(lens.max()) > 30_000 and _lib.stream_eligible(torch.float32, d, n)
+    x = torch.randn(m, d, generator=g)
+    for reduce in ('sum', 'mean'):
+        out = ab().segment_reduce(x.to(dev()), e2v, None, reduce)
+        ref = O.aggregate_sum_mean(x, he, node, None, reduce)
+        torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=2e-2 if reduce == 'sum' else 1e-4)
+    heads = 4
+    score = torch.randn(m, heads, generator=g)
+    seed = torch.randn(1, heads, d // heads, generator=g)
+    out, _ = ab().pma_aggregate(x.to(dev()), score.to(dev()), seed.to(dev()), e2v, heads)
+    ref, _ = O.aggregate_pma(x.view(m, heads, -1), score, seed, he, node)
+    torch.testing.assert_close(out.cpu(), ref.reshape(n, d), **FP32)
+    ws = _lib.stream_workspace(torch.device(dev()), d)
+    assert int(ws.view(torch.int32)[: 148 * 24 * 8].abs().max()) == 0
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,202 @@
+"""Multi-GPU pieces: the fused exchange (direct and TMA-bulk peer stores, per-row peer masks), the stand-alone row push,
+and `ShardedSetGNN` -- forward and backward -- against the unsharded module.  The one-GPU tests use local buffers as
+"peer replicas" (a peer-mapped pointer is just a device address) and world == 1; the two-GPU test spawns one process
+per GPU over NCCL + symmetric memory and is skipped on one-GPU boxes."""
+import os
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import allset_oracle as O
+from test_gpu_parity import ab, assert_grad_close, dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(n=600_000, m=320_000, mean=6, seed=5):
+    from allset_b200 import synthetic
+    ei = synthetic.poisson_hypergraph(n, m, mean, seed=seed, device=dev())
+    return ei, ab().Incidence.from_coo(ei[0], ei[1] - n, n_src=n, n_tgt=m)
+
+
+@pytest.mark.parametrize('push', ['direct', 'bulk'])
+@pytest.mark.parametrize('dtype,d', [(torch.bfloat16, 128), (torch.float32, 64), (torch.bfloat16, 256)])
+def test_fused_exchange_push_modes_and_masks(push, dtype, d, monkeypatch):
+    from allset_b200 import _lib, sharding, synthetic
+    monkeypatch.setenv('ALLSET_PUSH', push)
+    n, m, heads = 600_000, 320_000, 8
+    ei, v2e = _graph(n, m)
+    x = synthetic.features(n, d, dtype, seed=3, device=dev())
+    t = v2e.by_tgt
+    ref = _lib.segreduce_fwd(x, t.rowptr, t.col, m, False)
+    lo, hi = 50_000, 200_000
+    rp, col, _ = sharding.slice_csr(t.rowptr, t.col, lo, hi)
+    mine = torch.zeros(m, d, dtype=dtype, device=dev())
+    peers = [torch.zeros_like(mine) for _ in range(3)]
+    ptrs = [p[lo:hi].data_ptr() for p in peers]
+    # every peer gets every row
+    _lib.segreduce_fwd_bcast(x, rp, col, hi - lo, False, mine[lo:hi], ptrs)
+    torch.cuda.synchronize()
+    for buf in [mine] + peers:
+        assert torch.equal(buf[lo:hi], ref[lo:hi]) and bool((buf[:lo] == 0).all()) and bool((buf[hi:] == 0).all())
+    # per-row peer masks: a row lands exactly where its bit is set
+    mask = torch.randint(0, 8, (hi - lo,), dtype=torch.uint8, device=dev())
+    for p in peers:
+        p.zero_()
+    _lib.segreduce_fwd_bcast(x, rp, col, hi - lo, True, mine[lo:hi], ptrs, peer_mask=mask)
+    torch.cuda.synchronize()
+    refm = _lib.segreduce_fwd(x, t.rowptr, t.col, m, True)
+    assert torch.equal(mine[lo:hi], refm[lo:hi])
+    for j, p in enumerate(peers):
+        want = torch.where(((mask >> j) & 1).bool().unsqueeze(1), refm[lo:hi], torch.zeros_like(refm[lo:hi]))
+        assert torch.equal(p[lo:hi], want)
+    # PMA through the same epilogue
+    score = torch.randn(n, heads, device=dev())
+    seed = torch.randn(d, device=dev())
+    for p in peers:
+        p.zero_()
+    _lib.pma_fwd_bcast(x, score, seed, heads, d // heads, 0.2, rp, col, hi - lo, mine[lo:hi], ptrs, peer_mask=mask)
+    torch.cuda.synchronize()
+    for j, p in enumerate(peers):
+        want = torch.where(((mask >> j) & 1).bool().unsqueeze(1), mine[lo:hi], torch.zeros_like(mine[lo:hi]))
+        assert torch.equal(p[lo:hi], want)
+    refp, _ = _lib.pma_fwd(x, score, seed, heads, d // heads, 0.2, t.rowptr, t.col, m, want_stats=False)
+    torch.testing.assert_close(mine[lo:hi].float(), refp[lo:hi].float(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize('width,dtype', [(128, torch.bfloat16), (8, torch.float32), (16, torch.float32), (256, torch.float32)])
+def test_push_rows(width, dtype):
+    from allset_b200 import _lib
+    rows = 100_003
+    g = torch.Generator().manual_seed(width)
+    full = torch.randn(rows + 50, width, generator=g).to(dtype).to(dev())
+    lo, hi = 17, 17 + rows
+    peers = [torch.zeros_like(full) for _ in range(7)]
+    mask = torch.randint(0, 128, (rows,), dtype=torch.uint8, device=dev())
+    _lib.push_rows(full[lo:hi], [p[lo:hi].data_ptr() for p in peers], mask)
+    torch.cuda.synchronize()
+    for j, p in enumerate(peers):
+        want = torch.where(((mask >> j) & 1).bool().unsqueeze(1), full[lo:hi], torch.zeros_like(full[lo:hi]))
+        assert torch.equal(p[lo:hi], want) and bool((p[:lo] == 0).all()) and bool((p[hi:] == 0).all())
+    _lib.push_rows(full[lo:hi], [peers[0][lo:hi].data_ptr()])
+    assert torch.equal(peers[0][lo:hi], full[lo:hi])
+
+
+def _model_and_data(pma, n=40_000, m=9_000, d=128, layers=2, seed=0, agg=None, dropout=0.0):
+    from allset_b200 import synthetic, preprocessing as P
+    v2e = synthetic.poisson_hypergraph(n, m, 8, seed=3, device=dev())
+    ei, tot = P.add_self_loops(v2e, n, m)
+    norm = P.norm_construction(ei)
+    x = synthetic.features(n, d, torch.float32, device=dev())
+    args = O.config_namespace(num_features=d, num_classes=7, MLP_hidden=d, Classifier_hidden=d, heads=8 if pma else 1,
+                              All_num_layers=layers, Classifier_num_layers=1, PMA=pma, aggregate='add' if not pma else 'mean',
+                              dropout=dropout)
+    torch.manual_seed(seed)
+    model = ab().SetGNN(args, agg_dtype=agg).to(dev())
+    return model, SimpleNamespace(x=x, edge_index=ei, norm=norm)
+
+
+@pytest.mark.parametrize('pma', [False, True])
+@pytest.mark.parametrize('aggregate', ['add', 'mean'])
+def test_sharded_setgnn_world1_matches_setgnn(pma, aggregate):
+    """world == 1: the partitioned forward / backward (publish -> reduce over the slices, transposed slices for the
+    gradients) is the same computation as SetGNN's."""
+    from allset_b200.sharded_model import ShardedSetGNN
+    model, data = _model_and_data(pma)
+    model.aggr = aggregate
+    model.eval()
+    go = torch.randn(data.x.shape[0], 7, device=dev())
+    ref = model(SimpleNamespace(x=data.x, edge_index=data.edge_index.clone(), norm=data.norm))
+    (ref * go).sum().backward()
+    ref_grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    sm = ShardedSetGNN(model)
+    out = sm(SimpleNamespace(x=data.x, edge_index=data.edge_index.clone(), norm=data.norm))
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    (out * go).sum().backward()
+    for k, p in model.named_parameters():
+        if k in ref_grads:
+            assert_grad_close(p.grad, ref_grads[k], k, rel=1e-4)
+
+
+def _sharded_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    d_ = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=d_)
+    ok, why = True, []
+    try:
+        import allset_b200
+        from allset_b200 import ops, synthetic, preprocessing as P
+        from allset_b200.sharded_model import ShardedSetGNN
+        n, m, d = 200_000, 40_000, 128
+        v2e = synthetic.poisson_hypergraph(n, m, 8, seed=3, device=d_)
+        ei, tot = P.add_self_loops(v2e, n, m)
+        norm = P.norm_construction(ei)
+        x = synthetic.features(n, d, torch.float32, device=d_)
+        go = torch.randn(n, 7, generator=torch.Generator().manual_seed(1)).to(d_)
+        for pma in (False, True):
+            for agg in (None, torch.bfloat16):
+                args = O.config_namespace(num_features=d, num_classes=7, MLP_hidden=d, Classifier_hidden=d,
+                                          heads=8 if pma else 1, All_num_layers=2, Classifier_num_layers=1, PMA=pma,
+                                          aggregate='add', dropout=0.0)
+                torch.manual_seed(0)
+                model = allset_b200.SetGNN(args, agg_dtype=agg).to(d_).eval()
+                data = SimpleNamespace(x=x, edge_index=ei.clone(), norm=norm)
+                ref = model(data)
+                (ref * go).sum().backward()
+                ref_grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+                model.zero_grad(set_to_none=True)
+                sm = ShardedSetGNN(model)
+                sh_data = SimpleNamespace(x=x, edge_index=ei.clone(), norm=norm)
+                out = sm(sh_data)
+                full = sm.gather_logits(out.detach())
+                lo_, hi_ = sm._state[2].v_lo, sm._state[2].v_hi
+                (out * go[lo_:hi_]).sum().backward()
+                sm.allreduce_gradients()
+                tol = 1e-4 if agg is None else 3e-2
+                scale = ref.abs().max().item()
+                err = (full - ref.detach()).abs().max().item()
+                if not err <= tol * max(scale, 1.0):
+                    ok = False
+                    why.append(('logits', pma, str(agg), err, scale))
+                for k, p in model.named_parameters():
+                    if k in ref_grads:
+                        e = (p.grad - ref_grads[k]).abs().max().item()
+                        b = (1e-3 if agg is None else 5e-2) * ref_grads[k].abs().max().item() + 1e-5
+                        if not e <= b:
+                            ok = False
+                            why.append((k, pma, str(agg), e, b))
+                # inference in bf16 mode takes the tcgen05 kernels, which are row-independent: the owned rows are bit-equal
+                if agg is not None:
+                    with torch.no_grad():
+                        a = model(SimpleNamespace(x=x, edge_index=ei.clone(), norm=norm))
+                        b = sm(SimpleNamespace(x=x, edge_index=sh_data.edge_index, norm=norm))
+                    if not (a[lo_:hi_] - b).abs().max().item() <= 1e-3 * max(a.abs().max().item(), 1.0):
+                        ok = False
+                        why.append(('nograd', pma, (a[lo_:hi_] - b).abs().max().item()))
+        q.put((rank, ok, why))
+    except Exception as exc:  # noqa
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_sharded_setgnn_two_gpus_forward_backward():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res

@@ -114,3 +114,26 @@ def test_sharded_layer_pair_world2(ragged):
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in res), res
     assert res[0][2] == res[1][2] and res[0][3] == res[1][3]          # every rank plans the same partition
+
+
+def test_peer_need_mask_matches_brute_force():
+    """bit j of row r = the j-th OTHER rank's range contains a neighbour of r (pure index arithmetic, CPU)."""
+    g = torch.Generator().manual_seed(4)
+    rows, other = 500, 90
+    nnz = 4000
+    src = torch.sort(torch.randint(0, rows, (nnz,), generator=g))[0]
+    col = torch.randint(0, other, (nnz,), generator=g).int()
+    rowptr = torch.zeros(rows + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(torch.bincount(src, minlength=rows), 0).int()
+    ranges = [(0, 20), (20, 20), (20, 55), (55, 90)]                   # rank 1 owns nothing
+    for rank in range(4):
+        mask = sharding.peer_need_mask(rowptr, col, rows, ranges, rank)
+        others = [q for q in range(4) if q != rank]
+        for r in range(0, rows, 7):
+            nb = col[int(rowptr[r]):int(rowptr[r + 1])].tolist()
+            want = 0
+            for j, q in enumerate(others):
+                lo, hi = ranges[q]
+                if any(lo <= c < hi for c in nb):
+                    want |= 1 << j
+            assert int(mask[r]) == want, (rank, r)
