@@ -5,6 +5,7 @@ Public surface (mirrors the reference's module API, reference src/layers.py + sr
     Incidence                               the sorted incidence container (CSR by target + CSR by source)
     segment_reduce, pma_aggregate           the two differentiable aggregation operators
     UniGCNII, UniGCNIIConv                  the reference's UniGCNII baseline on the same kernels (V->E mean, E->V sum)
+    HypergraphConv/HCHA, HNHNConv/HNHN, UniGNN (+ UniSAGE/GIN/GCN/GAT convs)   the other incidence-list baselines (baselines.py)
     GraphedForward                          CUDA-graph replay of a SetGNN forward (launch-bound real datasets)
     preprocessing, sharding, synthetic      incidence preprocessing, multi-GPU partition + fused exchange, generators
     ingest                                  star expansion of a hyperedge dictionary + flat memory-mapped dataset cache
@@ -17,5 +18,7 @@ from .layers import MLP, PMA, HalfNLHconv  # noqa: F401
 from .models import SetGNN  # noqa: F401
 from .graphs import GraphedForward  # noqa: F401
 from .uni import UniGCNII, UniGCNIIConv  # noqa: F401
+from . import baselines  # noqa: F401
+from .baselines import HypergraphConv, HCHA, HNHNConv, HNHN, UniGNN  # noqa: F401
 
 __version__ = '0.1.0'

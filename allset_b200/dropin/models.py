@@ -1,6 +1,7 @@
 """Drop-in `models` module: `SetGNN` is the B200-native one (same ctor / forward / state_dict as reference
 src/models.py:295-484); `UniGCNII` / `UniGCNIIConv` (reference src/models.py:909-995) run on the same segmented-reduce kernels; the other
-baseline models are forwarded from the reference unchanged."""
+the HCHA / HGNN, HNHN and UniGNN-family baselines (reference src/models.py:207-292,601-907) likewise; the remaining baseline
+models (HyperGCN, CEGCN / CEGAT: clique-expansion GCNs, no incidence-list reduce) are forwarded from the reference."""
 import os as _os
 import sys as _sys
 
@@ -22,3 +23,5 @@ else:
         def __init__(self, args, norm=None, agg_dtype=getattr(_torch, _AGG)):
             super().__init__(args, norm, agg_dtype=agg_dtype)
 from allset_b200.uni import UniGCNII, UniGCNIIConv  # noqa: E402,F401  (same kernels)
+from allset_b200.baselines import (HCHA, HNHN, UniGNN, UniSAGEConv, UniGINConv, UniGCNConv, UniGCNConv2,  # noqa: E402,F401
+                                   UniGATConv)

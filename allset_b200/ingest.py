@@ -17,6 +17,11 @@ src/convert_datasets_to_pygDataset.py:163-175, src/load_other_datasets.py:121-19
                                              draws the noise from numpy's global RNG, so features match in distribution,
                                              labels / incidence exactly)
 
+    load_citation_dataset(dir, name)      == load_citation_dataset (load_other_datasets.py:121-196): the three HyperGCN pickles
+    load_yelp_dataset(dir)                == load_yelp_dataset (load_other_datasets.py:198-291): five csv files
+    HypergraphDataset(root, name, p2raw)  the `dataset_Hypergraph` wrapper train.py constructs (train.py:308-327) on top of
+                                          those loaders and the binary cache
+
 Host-side code (numpy / torch CPU); the arrays it yields are what `allset_b200.preprocessing` consumes on the GPU.
 """
 from __future__ import annotations
@@ -47,17 +52,21 @@ def star_expansion(hyperedges: Union[Mapping[object, Sequence[int]], Iterable[Se
     row0 = np.concatenate([nodes, edges])
     row1 = np.concatenate([edges, nodes])
     total = n_nodes + len(lists)                                # coalesce(m = n = edge_index.max() + 1)
-    key = np.unique(row0 * total + row1)                        # sort by (row 0, row 1) and drop duplicates
-    ei = np.stack([key // total, key % total])
-    return torch.from_numpy(ei), len(lists)
+    return _sorted_unique_pairs(row0, row1, total), len(lists)
 
 
 def _coalesced_star(nodes: np.ndarray, edges: np.ndarray, total: int) -> torch.Tensor:
     """[V|E ; E|V] sorted by (row 0, row 1) with duplicates dropped == torch_sparse.coalesce(edge_index, None, total, total)."""
     row0 = np.concatenate([nodes, edges]).astype(np.int64)
     row1 = np.concatenate([edges, nodes]).astype(np.int64)
-    key = np.unique(row0 * total + row1)
-    return torch.from_numpy(np.stack([key // total, key % total]))
+    return _sorted_unique_pairs(row0, row1, total)
+
+
+def _sorted_unique_pairs(row0: np.ndarray, row1: np.ndarray, total: int) -> torch.Tensor:
+    """Sort (row0, row1) pairs lexicographically and drop duplicates, through one int64 key per pair.  torch.unique
+    (a radix sort) does 9 M keys in 0.3 s where numpy 2.3's np.unique takes 9 s on the yelp incidence list."""
+    key = torch.unique(torch.from_numpy(row0 * total + row1), sorted=True)
+    return torch.stack([torch.div(key, total, rounding_mode='floor'), key % total])
 
 
 def load_le_dataset(path: str, dataset: str):
@@ -103,6 +112,126 @@ def load_cornell_dataset(path: str, dataset: str, feature_noise: float = 0.1, fe
     total = int(max(nodes.max(), edges.max())) + 1
     return SimpleNamespace(x=torch.from_numpy(feats.astype(np.float32)), y=torch.from_numpy(labels.copy()),
                            edge_index=_coalesced_star(nodes, edges, total), n_x=n_x, num_hyperedges=len(lines))
+
+
+def load_citation_dataset(path: str, dataset: str):
+    """`<path>/<dataset>/{features,labels,hypergraph}.pickle` (HyperGCN's cocitation / coauthorship layout) -> namespace(x,
+    edge_index, y, n_x, num_hyperedges) equal to the reference's load_citation_dataset (load_other_datasets.py:121-196):
+    dense float features, the star expansion of the hyperedge dictionary, labels as given."""
+    import pickle
+    d = os.path.join(path, dataset)
+    with open(os.path.join(d, 'features.pickle'), 'rb') as f:
+        feats = pickle.load(f)
+    with open(os.path.join(d, 'labels.pickle'), 'rb') as f:
+        labels = pickle.load(f)
+    with open(os.path.join(d, 'hypergraph.pickle'), 'rb') as f:
+        hyperedges = pickle.load(f)
+    x = np.asarray(feats.todense() if hasattr(feats, 'todense') else feats, dtype=np.float32)
+    y = torch.as_tensor(np.asarray(labels), dtype=torch.int64)
+    if x.shape[0] != y.numel():
+        raise ValueError('%d feature rows but %d labels' % (x.shape[0], y.numel()))
+    edge_index, n_he = star_expansion(hyperedges, x.shape[0])
+    return SimpleNamespace(x=torch.from_numpy(x), y=y, edge_index=edge_index, n_x=int(x.shape[0]), num_hyperedges=n_he)
+
+
+def load_yelp_dataset(path: str, dataset: str = 'yelp', name_dictionary_size: int = 1000):
+    """The yelp restaurant hypergraph (reference load_other_datasets.py:198-291): nodes = restaurants, one hyperedge per
+    user.  Features = [latitude, longitude | one-hot state | one-hot city | bag of words of the name (the 1000 most
+    frequent terms; sklearn CountVectorizer with the reference's settings)], labels = star bins, incidence from the
+    (node, he) pairs of `yelp_restaurant_incidence_H.csv` (1-based in the file).  `path` holds the five csv files."""
+    import pandas as pd
+    from sklearn.feature_extraction.text import CountVectorizer
+    latlong = pd.read_csv(os.path.join(path, 'yelp_restaurant_latlong.csv')).values
+    loc = pd.read_csv(os.path.join(path, 'yelp_restaurant_locations.csv'))
+    n_x = loc.shape[0]
+    rows = np.arange(n_x)
+
+    def one_hot(ids):
+        m = np.zeros((n_x, int(ids.max())), dtype=np.float64)
+        m[rows, ids - 1] = 1
+        return m
+
+    names = pd.read_csv(os.path.join(path, 'yelp_restaurant_name.csv')).values.reshape(-1)
+    bow = CountVectorizer(max_features=name_dictionary_size, stop_words='english', strip_accents='ascii').fit_transform(names)
+    feats = np.hstack([latlong, one_hot(loc.state_int.values), one_hot(loc.city_int.values), np.asarray(bow.todense())])
+    labels = pd.read_csv(os.path.join(path, 'yelp_restaurant_business_stars.csv')).values.reshape(-1)
+    if labels.size != n_x or feats.shape[0] != n_x:
+        raise ValueError('yelp: %d locations, %d labels, %d feature rows' % (n_x, labels.size, feats.shape[0]))
+    H = pd.read_csv(os.path.join(path, 'yelp_restaurant_incidence_H.csv'))
+    nodes = H.node.values.astype(np.int64) - 1
+    edges = H.he.values.astype(np.int64) - 1 + n_x
+    total = int(max(nodes.max(), edges.max())) + 1
+    return SimpleNamespace(x=torch.from_numpy(feats.astype(np.float32)), y=torch.from_numpy(labels.astype(np.int64)),
+                           edge_index=_coalesced_star(nodes, edges, total), n_x=n_x, num_hyperedges=int(H.he.values.max()))
+
+
+# dataset name -> (directory under the raw root, loader); the names reference train.py accepts (train.py:293-299)
+_LE = ('20newsW100', 'ModelNet40', 'zoo', 'NTU2012', 'Mushroom')
+_CORNELL = ('amazon-reviews', 'walmart-trips', 'house-committees')
+
+
+class HypergraphDataset(object):
+    """Replacement for the reference's `dataset_Hypergraph` (convert_datasets_to_pygDataset.py:39-175): same constructor
+    arguments and the attributes train.py reads (`.data`, `.num_features`, `.num_classes`), but the first load parses the
+    raw files with the vectorised loaders above and writes ONE flat binary cache (`<root>/<name>/processed/data[...].allset`)
+    that later loads memory-map -- instead of pickling a list-built PyG `Data` twice (raw/ and processed/data.pt)."""
+
+    def __init__(self, root='../data/pyg_data/hypergraph_dataset_updated/', name=None, p2raw=None, train_percent=0.01,
+                 feature_noise=None, transform=None, pre_transform=None):
+        known = _LE + _CORNELL + ('walmart-trips-100', 'house-committees-100', 'coauthor_cora', 'coauthor_dblp', 'yelp',
+                                  'cora', 'citeseer', 'pubmed')
+        if name not in known:
+            raise ValueError('name of hypergraph dataset must be one of: %s' % (list(known),))
+        if p2raw is not None and not os.path.isdir(p2raw):
+            raise ValueError('path to raw hypergraph dataset "%s" does not exist!' % p2raw)
+        self.name, self.root, self.p2raw, self.feature_noise = name, root, p2raw, feature_noise
+        self._train_percent = train_percent
+        fname = 'data.allset' if feature_noise is None else 'data_noise_%s.allset' % feature_noise
+        self.processed_path = os.path.join(root, name, 'processed', fname)
+        if not os.path.isfile(self.processed_path):
+            os.makedirs(os.path.dirname(self.processed_path), exist_ok=True)
+            d = self._parse()
+            if pre_transform is not None:
+                d = pre_transform(d)
+            save_cache(self.processed_path, d.x, d.edge_index, d.y, n_x=d.n_x, num_hyperedges=d.num_hyperedges)
+        self.data = load_cache(self.processed_path)
+        # train.py indexes these as 1-element tensors (train.py:334-339; PyG's collate made them so)
+        self.data.n_x = torch.tensor([self.data.n_x])
+        self.data.num_hyperedges = torch.tensor([self.data.num_hyperedges])
+        self.data.train_percent = torch.tensor([train_percent])
+        self.train_percent = train_percent
+        if transform is not None:
+            self.data = transform(self.data)
+
+    def _parse(self):
+        n, raw = self.name, self.p2raw
+        if raw is None:
+            raise ValueError('no cache at %s and no p2raw to build it from' % self.processed_path)
+        if n in ('cora', 'citeseer', 'pubmed'):
+            return load_citation_dataset(raw, n)
+        if n in ('coauthor_cora', 'coauthor_dblp'):
+            return load_citation_dataset(raw, n.split('_')[-1])
+        if n in _CORNELL or n in ('walmart-trips-100', 'house-committees-100'):
+            if self.feature_noise is None:
+                raise ValueError('for cornell datasets, feature noise cannot be %s' % self.feature_noise)
+            dim = int(n.split('-')[-1]) if n.endswith('-100') else None
+            base = '-'.join(n.split('-')[:-1]) if n.endswith('-100') else n
+            return load_cornell_dataset(raw, base, feature_noise=float(self.feature_noise), feature_dim=dim)
+        if n == 'yelp':
+            return load_yelp_dataset(raw, n)
+        return load_le_dataset(raw, n)
+
+    @property
+    def num_features(self) -> int:
+        return int(self.data.x.shape[1])
+
+    @property
+    def num_classes(self) -> int:
+        y = self.data.y
+        return int(y.max()) + 1 if y.dim() == 1 else int(y.shape[1])
+
+    def __repr__(self):
+        return '{}()'.format(self.name)
 
 
 def _to_numpy(t: torch.Tensor):

@@ -1,6 +1,7 @@
 """PyG 1.6.3 `MessagePassing.propagate` restated for Tensor `edge_index`.
 
-flow='source_to_target': j = edge_index[0] (source), i = edge_index[1] (target). Arguments of message()/
+flow='source_to_target': j = edge_index[0] (source), i = edge_index[1] (target); 'target_to_source' swaps the rows.
+`size` = (N_j, N_i) for either flow, dim_size = N_i (1.6.3 `__collect__`).  Arguments of message()/
 aggregate()/update() are resolved by NAME: `<k>_j` / `<k>_i` -> index_select of kwargs[k] along node_dim,
 specials `index, ptr, size_i, size_j, dim_size, edge_index*`, everything else passed through from kwargs.
 Test infrastructure only.
@@ -34,16 +35,18 @@ class MessagePassing(torch.nn.Module):
         idx = {'_i': i, '_j': j}
 
         def lift(name):
+            # PyG 1.6.3 __collect__: `size` is (N_j, N_i) -- slot 0 belongs to the `_j` (source) set and slot 1 to the
+            # `_i` (target) set WHATEVER the flow; only the row of edge_index that is lifted depends on the flow.
             for suf in ('_i', '_j'):
                 if name.endswith(suf):
+                    slot = 0 if suf == '_j' else 1
                     data = kwargs.get(name[:-2], None)
                     if isinstance(data, (tuple, list)):
-                        data = data[1 - idx[suf]] if suf == '_j' else data[idx[suf]]
+                        data = data[slot]
                     if isinstance(data, torch.Tensor):
-                        k = idx[suf]
-                        if size[k] is None:
-                            size[k] = data.size(self.node_dim)
-                        return True, data.index_select(self.node_dim, edge_index[k])
+                        if size[slot] is None:
+                            size[slot] = data.size(self.node_dim)
+                        return True, data.index_select(self.node_dim, edge_index[idx[suf]])
                     return True, data
             return False, None
 
@@ -61,11 +64,11 @@ class MessagePassing(torch.nn.Module):
                     wanted[p.name] = p.default
                 else:
                     raise TypeError('missing argument %r for propagate' % p.name)
-        size[0] = size[1] if size[0] is None else size[0]
-        size[1] = size[0] if size[1] is None else size[1]
+        size_i = size[1] if size[1] is not None else size[0]
+        size_j = size[0] if size[0] is not None else size[1]
         wanted.update(edge_index=edge_index, edge_index_i=edge_index[i], edge_index_j=edge_index[j],
-                      index=edge_index[i], ptr=None, size=size, size_i=size[i], size_j=size[j],
-                      dim_size=size[i], adj_t=None)
+                      index=edge_index[i], ptr=None, size=size, size_i=size_i, size_j=size_j,
+                      dim_size=size_i, adj_t=None)
 
         def call(fn, first, skip):
             kw = {p.name: wanted[p.name] for p in self._params(fn, skip)}

@@ -22,7 +22,9 @@ assert SetGNN is allset_b200.SetGNN and HalfNLHconv is allset_b200.HalfNLHconv a
 assert UniGCNII is allset_b200.UniGCNII and UniGCNIIConv is allset_b200.UniGCNIIConv
 for name in ('HyperGCN', 'CEGCN', 'CEGAT', 'HCHA', 'HNHN', 'HGNN', 'MLP_model', 'UniGCNII', 'HypergraphConv', 'HNHNConv'):
     assert name in globals(), name
-assert HCHA.__module__.startswith('_allset_reference_')
+assert HCHA.__module__ == 'allset_b200.baselines' and HNHN.__module__ == 'allset_b200.baselines'
+assert HypergraphConv.__module__ == 'allset_b200.baselines' and UniGNN.__module__ == 'allset_b200.baselines'
+assert HyperGCN.__module__.startswith('_allset_reference_') and CEGCN.__module__.startswith('_allset_reference_')
 from types import SimpleNamespace
 args = SimpleNamespace(All_num_layers=1, dropout=0.5, aggregate='add', normalization='ln', deepset_input_norm=True,
                        GPR=False, LearnMask=False, num_features=10, MLP_hidden=8, MLP_num_layers=2, heads=1, PMA=False,

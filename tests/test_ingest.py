@@ -108,3 +108,37 @@ def test_cornell_loader_equals_reference(tmp_path):
     torch.testing.assert_close(mine.x, ref.x, rtol=0, atol=0)            # noise 0: one-hot of the label on both sides
     noisy = ingest.load_cornell_dataset(str(tmp_path), name, feature_noise=0.5, feature_dim=10)
     assert noisy.x.shape == (mine.n_x, 10) and 0.3 < float((noisy.x - torch.nn.functional.pad(mine.x, (0, 10 - mine.x.shape[1]))).std()) < 0.7
+
+
+@pytest.mark.skipif(not os.path.isfile(RAW_ZIP), reason='reference raw data not present')
+def test_citation_loader_and_dataset_cache_equal_reference(tmp_path):
+    """load_citation_dataset + the HypergraphDataset cache wrapper against the reference's loader on cora cocitation."""
+    base = 'cocitation/cora/'
+    _extract(tmp_path, [(base + f, 'raw/cora/' + f) for f in ('features.pickle', 'labels.pickle', 'hypergraph.pickle')])
+    loaders, quiet = _reference_loaders()
+    with quiet():
+        ref = loaders.load_citation_dataset(path=str(tmp_path / 'raw'), dataset='cora')
+    mine = ingest.load_citation_dataset(str(tmp_path / 'raw'), 'cora')
+    assert mine.n_x == int(ref.n_x) and mine.num_hyperedges == int(ref.num_hyperedges)
+    assert torch.equal(mine.edge_index, ref.edge_index) and torch.equal(mine.y, ref.y) and torch.equal(mine.x, ref.x)
+    ds = ingest.HypergraphDataset(root=str(tmp_path / 'pyg'), name='cora', p2raw=str(tmp_path / 'raw'))
+    assert os.path.isfile(ds.processed_path) and ds.num_features == 1433 and ds.num_classes == 7
+    assert int(ds.data.n_x[0]) == 2708 and torch.equal(ds.data.edge_index, ref.edge_index)
+    again = ingest.HypergraphDataset(root=str(tmp_path / 'pyg'), name='cora', p2raw=None)       # served from the cache
+    assert torch.equal(again.data.x, ref.x) and torch.equal(again.data.y, ref.y)
+    with pytest.raises(ValueError):
+        ingest.HypergraphDataset(root=str(tmp_path / 'pyg'), name='not-a-dataset')
+
+
+@pytest.mark.skipif(not os.path.isfile(RAW_ZIP), reason='reference raw data not present')
+def test_yelp_loader_equals_reference(tmp_path):
+    files = ('yelp_restaurant_latlong.csv', 'yelp_restaurant_locations.csv', 'yelp_restaurant_name.csv',
+             'yelp_restaurant_business_stars.csv', 'yelp_restaurant_incidence_H.csv')
+    _extract(tmp_path, [('yelp/' + f, 'yelp/' + f) for f in files])
+    loaders, quiet = _reference_loaders()
+    with quiet():
+        ref = loaders.load_yelp_dataset(path=str(tmp_path / 'yelp') + '/', dataset='yelp')
+    mine = ingest.load_yelp_dataset(str(tmp_path / 'yelp'))
+    assert mine.n_x == int(ref.n_x) == 50758 and mine.num_hyperedges == int(ref.num_hyperedges)
+    assert torch.equal(mine.edge_index, ref.edge_index) and torch.equal(mine.y, ref.y)
+    assert mine.x.shape == ref.x.shape and torch.equal(mine.x, ref.x)
