@@ -512,10 +512,20 @@ __device__ __forceinline__ Cut chunk_cut(const int* __restrict__ rowptr, long lo
     const int beg = __ldg(rowptr + s);
     const long long o = target - ((long long)beg + s);      // 0 < o <= len + 1: where the target falls inside segment s
     const long long len = (long long)c.k - beg;
-    if (len >= kSplitMinLen && o >= kSplitMinPiece && len - o >= kSplitMinPiece) {
-      c.seg = s;
-      c.k = beg + (int)o;
-      c.inside = 1;
+    // Every target maps to a position inside ITS OWN segment's closed range [beg, end], monotonically in the target, so
+    // consecutive cuts can never cross: short segments round up to their end (as without a workspace); a long segment
+    // rounds DOWN to its start when the target is within kSplitMinPiece of it, is cut in the middle, and rounds up near
+    // its end.  (Rounding a long segment's early target UP would hand the whole segment to the previous chunk while the
+    // next target cuts it in the middle -- the next chunk would then wait for a first piece nobody publishes.)
+    if (len >= kSplitMinLen) {
+      if (o < kSplitMinPiece) {
+        c.seg = s;
+        c.k = beg;
+      } else if (len - o >= kSplitMinPiece) {
+        c.seg = s;
+        c.k = beg + (int)o;
+        c.inside = 1;
+      }
     }
   }
   return c;
@@ -531,16 +541,28 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 }
 
 struct StreamWs {           // views into the caller's workspace
+  int* status;              // [4]: word 0 != 0 if a look-back wait ever timed out (diagnostic; never in a correct run)
   int* flags;               // [kStreamMaxChunks]
   float* tail;              // [kStreamMaxChunks][stride]: published non-final pieces
   float* head;              // [kStreamMaxChunks][stride]: a warp's own parked final piece
 };
 __device__ __forceinline__ StreamWs stream_ws(void* ws, int stride) {
   StreamWs v;
-  v.flags = reinterpret_cast<int*>(ws);
-  v.tail = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + kStreamMaxChunks * 4);
+  v.status = reinterpret_cast<int*>(ws);
+  v.flags = v.status + 4;
+  v.tail = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + 16 + kStreamMaxChunks * 4);
   v.head = v.tail + kStreamMaxChunks * (long long)stride;
   return v;
+}
+// Wait for the flag of a preceding chunk.  Bounded: a logic error must flag the status word, not hang the GPU.
+__device__ __forceinline__ int wait_piece_flag(const StreamWs& wsv, long long q, int lane) {
+  int f = 0;
+  for (int spins = 0; spins < (1 << 24); ++spins) {
+    f = ld_acquire_gpu(wsv.flags + q);
+    if (f != 0) return f;
+  }
+  if (lane == 0) atomicExch(wsv.status, 1);
+  return 1;                 // give up: treat it as the first piece
 }
 
 // One lane's share of a staged row: LB bytes (LB = row_bytes / 32).  LB >= 16 is read as LB/16 16-byte chunks,
@@ -851,12 +873,7 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
   }
   if (c0.inside && nseg > 0) {
     long long q0 = chunk - 1;
-    while (true) {                                // walk back to the chunk holding the first piece
-      int f;
-      do { f = ld_acquire_gpu(wsv.flags + q0); } while (f == 0);
-      if (f == 1) break;
-      --q0;
-    }
+    while (wait_piece_flag(wsv, q0, lane) != 1 && q0 > 0) --q0;      // walk back to the chunk holding the first piece
     float tot[NA];
 #pragma unroll
     for (int i = 0; i < NA; ++i) tot[i] = 0.f;
@@ -1207,12 +1224,7 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
   }
   if (c0.inside && nseg > 0) {
     long long q0 = chunk - 1;
-    while (true) {
-      int f;
-      do { f = ld_acquire_gpu(wsv.flags + q0); } while (f == 0);
-      if (f == 1) break;
-      --q0;
-    }
+    while (wait_piece_flag(wsv, q0, lane) != 1 && q0 > 0) --q0;
     float tm[CH], tl[CH], ta[NA];
 #pragma unroll
     for (int c = 0; c < CH; ++c) { tm[c] = -INFINITY; tl[c] = 0.f; }
@@ -2298,7 +2310,7 @@ int allset_long_segments(const int32_t* rowptr, int64_t n_tgt, int32_t threshold
 
 namespace {
 size_t stream_ws_bytes(int32_t d) {
-  return (size_t)kStreamMaxChunks * 4 + 2 * (size_t)kStreamMaxChunks * (size_t)(d + 128) * 4;
+  return 16 + (size_t)kStreamMaxChunks * 4 + 2 * (size_t)kStreamMaxChunks * (size_t)(d + 128) * 4;
 }
 // the workspace that lets the stream kernels cut long segments; NULL = never cut (long segments then need the buckets)
 int check_ws(const char* what, void* ws, size_t ws_bytes, int32_t d) {
@@ -2419,7 +2431,7 @@ int allset_bias_act_norm(const float* x, const float* bias, int relu, const floa
 int32_t allset_bias_act_norm_bwd_blocks(int64_t rows) {
   // persistent-style grid: each warp walks rows with a grid stride so the column sums amortise
   long long b = (rows + 7) / 8;
-  const long long cap = 148LL * 4;
+  const long long cap = 148LL * 3;                   // = the resident CTAs of the rowop backward kernel (80 registers)
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int32_t)b;

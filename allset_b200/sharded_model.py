@@ -229,7 +229,8 @@ class ShardedSetGNN(nn.Module):
         st = self._state
         if st is not None and st[0] is edge_index and st[1] == edge_index._version:
             return st[2], st[3], st[4]
-        v2e, _ = self.model._graph(edge_index, data.x.size(0))
+        n_nodes = int(getattr(data, 'num_nodes', None) or data.x.size(0))
+        v2e, _ = self.model._graph(edge_index, n_nodes)
         sh = ShardedIncidence(v2e, self.rank, self.world, self.group)
         sh.full = v2e
         ex = _Exchange(sh, data.x.device, self.group)
@@ -242,7 +243,9 @@ class ShardedSetGNN(nn.Module):
         if m.All_num_layers == 0 or m.GPR or m.LearnMask:
             raise NotImplementedError('ShardedSetGNN covers the plain layer stack (no GPR / LearnMask / classifier-only)')
         sh, dv2e, de2v = self._directions(data)
-        x = data.x[sh.v_lo:sh.v_hi]                                        # row-parallel from the first operator on
+        # row-parallel from the first operator on; `data.x` is the full [N, F] matrix (as the reference's `data`) or, with
+        # `data.num_nodes` set, just the rows this rank owns
+        x = data.x if (getattr(data, 'num_nodes', None) and data.x.shape[0] == sh.v_hi - sh.v_lo) else data.x[sh.v_lo:sh.v_hi]
         norm = data.norm
         if norm is not None and not norm.is_floating_point():
             norm = None if dv2e.weights_all_one(norm) else norm

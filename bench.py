@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument('--nodes', type=int, default=10_000_000, help='|V|')
     ap.add_argument('--hyperedges', type=int, default=2_000_000, help='|E|')
     ap.add_argument('--mean-size', type=float, default=30.0)
+    ap.add_argument('--graph', default='poisson', choices=['poisson', 'powerlaw'],
+                    help='hyperedge sizes: 1+Poisson(mean-1) (configs 3, 4) or P(s)~s^-2 on [2,4096] with a forced 4096 (config 5)')
     ap.add_argument('--d', type=int, default=128)
     ap.add_argument('--heads', type=int, default=8)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
@@ -72,8 +74,18 @@ def parse_args():
 
 
 def workload_name(a):
+    if a.graph == 'powerlaw':
+        return ('synthetic power-law |V|=%s |E|=%s max-deg=4096 AllDeepSets(sum) V->E+E->V d=%d %s'
+                % (_si(a.nodes), _si(a.hyperedges), a.d, a.dtype))
     return ('synthetic |V|=%s |E|=%s mean-deg=%g AllDeepSets(sum) V->E+E->V d=%d %s'
             % (_si(a.nodes), _si(a.hyperedges), a.mean_size, a.d, a.dtype))
+
+
+def make_graph(a, n, m, device):
+    from allset_b200 import synthetic
+    if a.graph == 'powerlaw':
+        return synthetic.powerlaw_hypergraph(n, m, 2, 4096, 2.0, seed=a.seed, device=device)
+    return synthetic.poisson_hypergraph(n, m, a.mean_size, seed=a.seed, device=device)
 
 
 def _si(n):
@@ -151,7 +163,7 @@ def cpu_sample_graph(a):
     import torch
     from allset_b200 import synthetic
     n, m = max(a.nodes // a.cpu_scale, 1000), max(a.hyperedges // a.cpu_scale, 200)
-    ei = synthetic.poisson_hypergraph(n, m, a.mean_size, seed=a.seed, device='cpu')
+    ei = make_graph(a, n, m, 'cpu')
     node, he = ei[0], ei[1] - n
     x = torch.randn(n, a.d, generator=torch.Generator().manual_seed(a.seed))
     norm = torch.ones(ei.shape[1], dtype=torch.int64)        # data.norm = ones_like(edge_index[0]) (int64), preprocessing.py:454
@@ -305,7 +317,7 @@ def run_b200(a):
     Nv, Me, d, H = a.nodes, a.hyperedges, a.d, a.heads
 
     # ---- graph (resident; built once like the reference's data.to(device)) ------------------------------------
-    ei = synthetic.poisson_hypergraph(Nv, Me, a.mean_size, seed=a.seed, device=dev)
+    ei = make_graph(a, Nv, Me, dev)
     he = ei[1] - Nv
     v2e = allset_b200.Incidence.from_coo(ei[0], he, n_src=Nv, n_tgt=Me)
     nnz = v2e.nnz

@@ -559,14 +559,14 @@ def test_stream_kernels_cut_long_segments(dtype):
         if weight is None and not lo:
             assert torch.equal(out[short], out_group[short])                 # uncut segments: the same sequential sums
     ws = _lib.stream_workspace(x.device, d)
-    assert int(ws.view(torch.int32)[: 148 * 24 * 8].abs().max()) == 0        # every flag consumed and cleared
+    assert int(ws.view(torch.int32)[: 4 + 148 * 24 * 8].abs().max()) == 0        # every flag consumed and cleared
     score = torch.randn(n, heads, device=dev())
     seed = torch.randn(1, heads, d // heads, device=dev())
     out, alpha = ab().pma_aggregate(x, score, seed, v2e, heads, return_alpha=True)
     ref, ref_alpha = O.aggregate_pma(xr.view(n, heads, -1), score.cpu(), seed.cpu(), src_c, he_c)
     torch.testing.assert_close(out.float().cpu(), ref.reshape(m, d), **(BF16 if lo else FP32))
     torch.testing.assert_close(alpha.cpu(), ref_alpha, rtol=1e-4, atol=1e-6)   # from the (max, sum) of the merged pieces
-    assert int(ws.view(torch.int32)[: 148 * 24 * 8].abs().max()) == 0
+    assert int(ws.view(torch.int32)[: 4 + 148 * 24 * 8].abs().max()) == 0
     # backward of the sum (the same kernel on the transposed CSR, whose long segments are high-degree vertices -- none here)
     if not lo:
         xg = x.clone().requires_grad_(True)
@@ -605,7 +605,7 @@ def test_stream_kernels_cut_high_degree_vertices_in_the_transposed_direction():
     ref, _ = O.aggregate_pma(x.view(m, heads, -1), score, seed, he, node)
     torch.testing.assert_close(out.cpu(), ref.reshape(n, d), **FP32)
     ws = _lib.stream_workspace(torch.device(dev()), d)
-    assert int(ws.view(torch.int32)[: 148 * 24 * 8].abs().max()) == 0
+    assert int(ws.view(torch.int32)[: 4 + 148 * 24 * 8].abs().max()) == 0
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -228,3 +228,73 @@ def test_tensor_core_paths_are_cuda_eval_bf16_only():
     odd.tc_dtype = torch.bfloat16
     with torch.no_grad():
         assert not odd._tc_ok(x)                     # not square
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Work split of the stream kernels (csrc/allset_kernels.cu: chunk_boundary / chunk_cut), restated in Python: the
+# invariants the decoupled look-back relies on.  A model check of the ALGORITHM (the device code is exercised on the GPU).
+# ----------------------------------------------------------------------------------------------------------------------
+def _cuts(rowptr, n_chunks, split_min_len=256, split_min_piece=32):
+    import bisect
+    n = len(rowptr) - 1
+    cost = [rowptr[s] + s for s in range(n + 1)]
+    total = cost[n]
+    out = []
+    for c in range(n_chunks + 1):
+        if c <= 0:
+            out.append((0, rowptr[0], 0)); continue
+        if c >= n_chunks:
+            out.append((n, rowptr[n], 0)); continue
+        target = total * c // n_chunks
+        hi = 0 if target <= 0 else bisect.bisect_left(cost, target)          # smallest s with cost(s) >= target
+        seg, k, inside = hi, rowptr[hi], 0
+        if hi > 0:
+            s = hi - 1
+            beg, ln = rowptr[s], rowptr[hi] - rowptr[s]
+            o = target - (beg + s)
+            if ln >= split_min_len:
+                if o < split_min_piece:
+                    seg, k = s, beg
+                elif ln - o >= split_min_piece:
+                    seg, k, inside = s, beg + o, 1
+        out.append((seg, k, inside))
+    return out
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_stream_chunk_cuts_cover_every_incidence_once_and_chain_consistently(seed):
+    import random
+    rnd = random.Random(seed)
+    n = rnd.choice([400, 2000, 5000])
+    lens = [rnd.choice([0, 1, 2, 3, 5, 8]) for _ in range(n)]
+    for _ in range(rnd.choice([3, 20, 80])):                                    # long segments, some adjacent
+        i = rnd.randrange(n - 2)
+        lens[i] = rnd.choice([256, 300, 1000, 4096, 20000])
+        if rnd.random() < 0.5:
+            lens[i + 1] = rnd.choice([257, 4096])
+    rowptr = [0]
+    for ln in lens:
+        rowptr.append(rowptr[-1] + ln)
+    n_chunks = max(2, n // 16)
+    cuts = _cuts(rowptr, n_chunks)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        assert a[0] <= b[0] and a[1] <= b[1], (a, b)                             # monotone in segment and position
+        if b[2]:
+            assert rowptr[b[0]] + 32 <= b[1] <= rowptr[b[0] + 1] - 32            # both pieces keep >= 32 incidences
+    covered = 0
+    published = {}                                                               # chunk -> flag
+    for c in range(n_chunks):
+        (s0, k0, in0), (s1, k1, in1) = cuts[c], cuts[c + 1]
+        covered += k1 - k0
+        nseg = s1 - s0
+        assert nseg >= 0
+        if in1:
+            published[c] = 2 if (in0 and nseg == 0) else 1
+            assert k1 > k0                                                       # a publisher never returns early
+        if in0 and nseg > 0:                                                     # owner: walk back to the first piece
+            q = c - 1
+            while published[q] != 1:                                             # KeyError = waiting for a piece nobody publishes
+                assert cuts[q][0] == s0 and cuts[q][2]                           # middle chunks lie inside the same segment
+                q -= 1
+            assert cuts[q + 1][0] == s0
+    assert covered == rowptr[-1]
