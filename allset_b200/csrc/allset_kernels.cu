@@ -752,13 +752,13 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
   int cur_end = nseg > 0 ? __ldg(rp + 1) : INT32_MAX, nxt_end = __ldg(rp + min(2, max(nseg, 0)));
 
   // a finished row: scale (mean), store, exchange
-  auto emit = [&](long long s_idx, float cnt, float (&val)[NA]) {
+  auto emit = [&](T* row, long long s_idx, int cnt_i, float (&val)[NA]) {
     if (mean) {
+      const float cnt = (float)max(cnt_i, 1);
       const float rc = __frcp_rn(cnt);
 #pragma unroll
       for (int i = 0; i < NA; ++i) val[i] = div_count(val[i], cnt, rc);
     }
-    T* row = out + (size_t)s_idx * (size_t)d;
     LR::store(row, lane, val);
     if (PUSH != 0) {
       const unsigned m = peer_mask != nullptr ? (unsigned)__ldg(peer_mask + s_idx) : 0xffu;
@@ -766,14 +766,18 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
       else bulk_to_peers<T, LR, NA, ROWB>(row, peers, m, lane, stage_out, nslot, val);
     }
   };
+  T* __restrict__ ob = out + (size_t)s_first * (size_t)d;           // output row of the current segment
+  bool head_pending = c0.inside != 0;                                // the first flush parks a cut segment's final piece
   auto flush = [&]() {
-    if (seg == 0 && c0.inside) {
+    if (head_pending) {
       // final piece of a segment that began in an earlier chunk: park it, combine after the stream (see below)
 #pragma unroll
       for (int i = 0; i < NA; ++i) wsv.head[chunk * PS + i * 32 + lane] = acc[i];
+      head_pending = false;
     } else {
-      emit(s_first + seg, (float)max(cur_end - cur_beg, 1), acc);
+      emit(ob, s_first + seg, cur_end - cur_beg, acc);
     }
+    ob += d;
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.f;
     ++seg;
@@ -886,7 +890,7 @@ segreduce_stream_kernel(const T* __restrict__ x, const int* __restrict__ rowptr,
     __syncwarp();
     if (lane == 0)
       for (long long q = q0; q < chunk; ++q) wsv.flags[q] = 0;      // leave the workspace zeroed for the next launch
-    emit(s_first, (float)max(__ldg(rp + 1) - __ldg(rp), 1), tot);
+    emit(out + (size_t)s_first * (size_t)d, s_first, __ldg(rp + 1) - __ldg(rp), tot);
   }
   if (PUSH == 2) {
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1010,9 +1014,9 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
   int cur_end = nseg > 0 ? __ldg(rp + 1) : INT32_MAX, nxt_end = __ldg(rp + min(2, max(nseg, 0)));
 
   // a finished segment: out = acc / (l + 1e-16) + seed, statistics, exchange
-  auto emit = [&](long long s_idx, const float (&mm)[CH], const float (&ll)[CH], const float (&aa)[NA]) {
+  auto emit = [&](T* row, float* sb_out, long long s_idx, const float (&mm)[CH], const float (&ll)[CH],
+                  const float (&aa)[NA]) {
     float o[NA];
-    float* sb_out = stats != nullptr ? stats + (size_t)s_idx * H * 2 : nullptr;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const float denom = ll[c] + 1e-16f;
@@ -1024,7 +1028,6 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
         sb_out[hc[c] * 2 + 1] = denom;
       }
     }
-    T* row = out + (size_t)s_idx * (size_t)d;
     LR::store(row, lane, o);
     if (PUSH != 0) {
       const unsigned m = peer_mask != nullptr ? (unsigned)__ldg(peer_mask + s_idx) : 0xffu;
@@ -1032,6 +1035,9 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
       else bulk_to_peers<T, LR, NA, ROWB>(row, peers, m, lane, stage_out, nslot, o);
     }
   };
+  T* __restrict__ ob = out + (size_t)s_first * (size_t)d;
+  float* __restrict__ sbo = stats != nullptr ? stats + (size_t)s_first * H * 2 : nullptr;
+  bool head_pending = c0.inside != 0;
   auto park = [&](float* slot) {                 // (acc, m2, l) of a piece of a cut segment
 #pragma unroll
     for (int i = 0; i < NA; ++i) slot[i * 32 + lane] = acc[i];
@@ -1042,8 +1048,14 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
     }
   };
   auto flush = [&]() {
-    if (seg == 0 && c0.inside) park(wsv.head + chunk * PS);       // final piece of a cut segment: combined after the stream
-    else emit(s_first + seg, m2, l, acc);
+    if (head_pending) {                       // final piece of a cut segment: combined after the stream
+      park(wsv.head + chunk * PS);
+      head_pending = false;
+    } else {
+      emit(ob, sbo, s_first + seg, m2, l, acc);
+    }
+    ob += d;
+    if (sbo != nullptr) sbo += 2 * H;
 #pragma unroll
     for (int c = 0; c < CH; ++c) { m2[c] = -INFINITY; l[c] = 0.f; }
 #pragma unroll
@@ -1249,7 +1261,7 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
     __syncwarp();
     if (lane == 0)
       for (long long q = q0; q < chunk; ++q) wsv.flags[q] = 0;
-    emit(s_first, tm, tl, ta);
+    emit(out + (size_t)s_first * (size_t)d, stats != nullptr ? stats + (size_t)s_first * H * 2 : nullptr, s_first, tm, tl, ta);
   }
   if (PUSH == 2) {
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -2431,7 +2443,7 @@ int allset_bias_act_norm(const float* x, const float* bias, int relu, const floa
 int32_t allset_bias_act_norm_bwd_blocks(int64_t rows) {
   // persistent-style grid: each warp walks rows with a grid stride so the column sums amortise
   long long b = (rows + 7) / 8;
-  const long long cap = 148LL * 3;                   // = the resident CTAs of the rowop backward kernel (80 registers)
+  const long long cap = 148LL * 4;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int32_t)b;

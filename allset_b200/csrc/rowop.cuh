@@ -38,18 +38,10 @@ struct Vec;                                     // CE consecutive elements of ty
 
 template <int CE>
 struct Vec<float, CE> {
-  struct Raw { float f[CE]; };
-  __device__ static __forceinline__ Raw load_raw(const float* p) {
-    Raw r;
-    if (CE == 4) { const float4 v = __ldcs(reinterpret_cast<const float4*>(p)); r.f[0] = v.x; r.f[1] = v.y; r.f[2] = v.z; r.f[3] = v.w; }
-    else { const float2 v = __ldcs(reinterpret_cast<const float2*>(p)); r.f[0] = v.x; r.f[1] = v.y; }
-    return r;
+  __device__ static __forceinline__ void load(const float* p, float (&f)[CE]) {
+    if (CE == 4) { const float4 v = __ldcs(reinterpret_cast<const float4*>(p)); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+    else { const float2 v = __ldcs(reinterpret_cast<const float2*>(p)); f[0] = v.x; f[1] = v.y; }
   }
-  __device__ static __forceinline__ void unpack(const Raw& r, float (&f)[CE]) {
-#pragma unroll
-    for (int k = 0; k < CE; ++k) f[k] = r.f[k];
-  }
-  __device__ static __forceinline__ void load(const float* p, float (&f)[CE]) { unpack(load_raw(p), f); }
   __device__ static __forceinline__ void store(float* p, const float (&f)[CE]) {
     if (CE == 4) *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
     else *reinterpret_cast<float2*>(p) = make_float2(f[0], f[1]);
@@ -58,25 +50,20 @@ struct Vec<float, CE> {
 
 template <int CE>
 struct Vec<bf16, CE> {
-  struct Raw { unsigned w[CE / 2]; };                      // packed pairs: half the registers of the unpacked row
-  __device__ static __forceinline__ Raw load_raw(const bf16* p) {
-    Raw r;
-    if (CE == 4) { const uint2 v = __ldcs(reinterpret_cast<const uint2*>(p)); r.w[0] = v.x; r.w[CE / 2 - 1] = v.y; }
-    else { r.w[0] = __ldcs(reinterpret_cast<const unsigned*>(p)); }
-    return r;
-  }
-  __device__ static __forceinline__ void unpack(const Raw& r, float (&f)[CE]) {
-#pragma unroll
-    for (int q = 0; q < CE / 2; ++q) {
-      f[2 * q] = __uint_as_float(r.w[q] << 16);
-      f[2 * q + 1] = __uint_as_float(r.w[q] & 0xffff0000u);
+  __device__ static __forceinline__ void load(const bf16* p, float (&f)[CE]) {
+    if (CE == 4) {
+      const uint2 v = __ldcs(reinterpret_cast<const uint2*>(p));
+      f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+      f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    } else {
+      const unsigned v = __ldcs(reinterpret_cast<const unsigned*>(p));
+      f[0] = __uint_as_float(v << 16); f[1] = __uint_as_float(v & 0xffff0000u);
     }
   }
-  __device__ static __forceinline__ void load(const bf16* p, float (&f)[CE]) { unpack(load_raw(p), f); }
   __device__ static __forceinline__ void store(bf16* p, const float (&f)[CE]) {
     const __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
     if (CE == 4) {
-      const __nv_bfloat162 b = __floats2bfloat162_rn(f[CE - 2], f[CE - 1]);
+      const __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
       *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b));
     } else {
       *reinterpret_cast<unsigned*>(p) = *reinterpret_cast<const unsigned*>(&a);
@@ -111,49 +98,34 @@ struct FwdArgs {
 
 // rows a warp holds at once: the loads of all of them are issued before the first use, so a warp has R row-sized
 // requests in flight (a 256-byte bf16 row per warp is far too little to cover HBM latency: measured 2.3 TB/s with R = 1)
-template <int NPL, int ES>
-struct RowsPerWarp {
-  static constexpr int ROWB = 32 * NPL * ES;
-  static constexpr int R = ROWB >= 2048 ? 1 : (2048 / ROWB > 8 ? 8 : 2048 / ROWB);   // forward: ~2 KB of rows per warp in flight
-  static constexpr int RB = ROWB >= 1024 ? 1 : (1024 / ROWB > 4 ? 4 : 1024 / ROWB);  // backward: x AND dy are loaded per row
-};
+template <int NPL>
+struct RowsPerWarp { static constexpr int R = NPL <= 4 ? 4 : (NPL == 8 ? 2 : 1); };
 
-template <typename TIn, typename TOut, int NPL, bool RES>
-__global__ void __launch_bounds__(256, 3) fwd_kernel(FwdArgs a) {
+template <typename TIn, typename TOut, int NPL>
+__global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
   constexpr int D = 32 * NPL;
   constexpr int CE = NPL < 4 ? NPL : 4;
   constexpr int NCH = NPL / CE;
-  constexpr int R = RowsPerWarp<NPL, sizeof(TIn)>::R;
-  using VI = Vec<TIn, CE>;
+  constexpr int R = RowsPerWarp<NPL>::R;
   const int lane = threadIdx.x & 31;
-  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
-  const long long groups = (a.rows + R - 1) / R;
-  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (g >= groups) return;
-
-  // persistent warps with a one-group prefetch of the RAW rows (packed bf16 pairs: half the registers): the loads of
-  // group g + nw are in flight while group g is normalised and stored.  A warp that loads, reduces and stores strictly
-  // in turn leaves the memory system idle for the length of its shuffle chains (measured 3.8 TB/s).
-  typename VI::Raw nx[R][NCH], nres[RES ? R : 1][NCH];
-  auto fetch = [&](long long grp) {
-    const long long row0 = grp * R;
+  const long long row0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R;
+  if (row0 >= a.rows) return;
+  const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+  float v[R][NCH][CE];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const TIn* xr = static_cast<const TIn*>(a.x) + (row0 + (r < nr ? r : 0)) * D;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) Vec<TIn, CE>::load(xr + (c * 32 + lane) * CE, v[r][c]);
+  }
+  if (a.residual != nullptr) {
+    float rs[R][NCH][CE];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const long long row = row0 + r < a.rows ? row0 + r : a.rows - 1;
-      const TIn* xr = static_cast<const TIn*>(a.x) + row * D;
+      const TIn* rr = static_cast<const TIn*>(a.residual) + (row0 + (r < nr ? r : 0)) * D;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) nx[r][c] = VI::load_raw(xr + (c * 32 + lane) * CE);
-      if (RES) {
-        const TIn* rr = static_cast<const TIn*>(a.residual) + row * D;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) nres[r][c] = VI::load_raw(rr + (c * 32 + lane) * CE);
-      }
+      for (int c = 0; c < NCH; ++c) Vec<TIn, CE>::load(rr + (c * 32 + lane) * CE, rs[r][c]);
     }
-  };
-  fetch(g);
-  while (true) {
-    float v[R][NCH][CE];
-    // unpack the fetched group, then immediately issue the loads of the next one
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       float b[CE];
@@ -161,92 +133,94 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(FwdArgs a) {
       for (int k = 0; k < CE; ++k) b[k] = 0.f;
       if (a.bias != nullptr) load_param<CE>(a.bias + (c * 32 + lane) * CE, b);
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        float rs[CE];
-        VI::unpack(nx[r][c], v[r][c]);
-        if (RES) VI::unpack(nres[r][c], rs);
+      for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int k = 0; k < CE; ++k) {
-          float t = v[r][c][k] + b[k];
-          if (a.relu) t = fmaxf(t, 0.f);
-          v[r][c][k] = RES ? t + rs[k] : t;
+          const float t = v[r][c][k] + b[k];
+          v[r][c][k] = (a.relu ? fmaxf(t, 0.f) : t) + rs[r][c][k];
         }
-      }
     }
-    const long long row0 = g * R;
-    const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
-    const long long gn = g + nw;
-    const bool more = gn < groups;
-    if (more) fetch(gn);
-
-    if (a.gamma != nullptr) {
-      float mean[R], rstd[R];
+  } else if (a.bias != nullptr || a.relu) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        float sum = 0.f;
+    for (int c = 0; c < NCH; ++c) {
+      float b[CE];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
+      for (int k = 0; k < CE; ++k) b[k] = 0.f;
+      if (a.bias != nullptr) load_param<CE>(a.bias + (c * 32 + lane) * CE, b);
 #pragma unroll
-          for (int k = 0; k < CE; ++k) sum += v[r][c][k];
-        mean[r] = sum;
-      }
+      for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);     // R independent chains
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        mean[r] *= (1.f / D);
-        float sq = 0.f;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-          for (int k = 0; k < CE; ++k) { const float t = v[r][c][k] - mean[r]; sq += t * t; }
-        rstd[r] = sq;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int r = 0; r < R; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        rstd[r] = rsqrtf(rstd[r] * (1.f / D) + a.eps);
-        if (a.stats != nullptr && lane == 0 && r < nr)
-          *reinterpret_cast<float2*>(a.stats + (row0 + r) * 2) = make_float2(mean[r], rstd[r]);
-      }
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        float gm[CE], b[CE];
-        load_param<CE>(a.gamma + (c * 32 + lane) * CE, gm);
-#pragma unroll
-        for (int k = 0; k < CE; ++k) b[k] = 0.f;
-        if (a.beta != nullptr) load_param<CE>(a.beta + (c * 32 + lane) * CE, b);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int k = 0; k < CE; ++k) v[r][c][k] = (v[r][c][k] - mean[r]) * rstd[r] * gm[k] + b[k];
-      }
+        for (int k = 0; k < CE; ++k) {
+          const float t = v[r][c][k] + b[k];
+          v[r][c][k] = a.relu ? fmaxf(t, 0.f) : t;
+        }
     }
+  }
+  if (a.gamma != nullptr) {
+    float mean[R], rstd[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (r >= nr) break;
-      const long long row = row0 + r;
+      float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        if (a.relu_out) {
+      for (int c = 0; c < NCH; ++c)
 #pragma unroll
-          for (int k = 0; k < CE; ++k) v[r][c][k] = fmaxf(v[r][c][k], 0.f);
-        }
-        if (a.thr16 != 0u) {
-          const unsigned keep = keep_bits<CE>(a.seed, row, D, (c * 32 + lane) * CE, a.thr16);
-#pragma unroll
-          for (int k = 0; k < CE; ++k) v[r][c][k] = ((keep >> k) & 1u) ? v[r][c][k] * a.keep_scale : 0.f;
-        }
-        Vec<TOut, CE>::store(static_cast<TOut*>(a.out) + row * D + (c * 32 + lane) * CE, v[r][c]);
-      }
+        for (int k = 0; k < CE; ++k) sum += v[r][c][k];
+      mean[r] = sum;
     }
-    if (!more) break;
-    g = gn;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);     // R independent chains
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mean[r] *= (1.f / D);
+      float sq = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int k = 0; k < CE; ++k) { const float t = v[r][c][k] - mean[r]; sq += t * t; }
+      rstd[r] = sq;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      rstd[r] = rsqrtf(rstd[r] * (1.f / D) + a.eps);
+      if (a.stats != nullptr && lane == 0 && r < nr)
+        *reinterpret_cast<float2*>(a.stats + (row0 + r) * 2) = make_float2(mean[r], rstd[r]);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float g[CE], b[CE];
+      load_param<CE>(a.gamma + (c * 32 + lane) * CE, g);
+#pragma unroll
+      for (int k = 0; k < CE; ++k) b[k] = 0.f;
+      if (a.beta != nullptr) load_param<CE>(a.beta + (c * 32 + lane) * CE, b);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < CE; ++k) v[r][c][k] = (v[r][c][k] - mean[r]) * rstd[r] * g[k] + b[k];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (r >= nr) break;
+    const long long row = row0 + r;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (a.relu_out) {
+#pragma unroll
+        for (int k = 0; k < CE; ++k) v[r][c][k] = fmaxf(v[r][c][k], 0.f);
+      }
+      if (a.thr16 != 0u) {
+        const unsigned keep = keep_bits<CE>(a.seed, row, D, (c * 32 + lane) * CE, a.thr16);
+#pragma unroll
+        for (int k = 0; k < CE; ++k) v[r][c][k] = ((keep >> k) & 1u) ? v[r][c][k] * a.keep_scale : 0.f;
+      }
+      Vec<TOut, CE>::store(static_cast<TOut*>(a.out) + row * D + (c * 32 + lane) * CE, v[r][c]);
+    }
   }
 }
 
@@ -263,42 +237,42 @@ struct BwdArgs {
 //   dz = rstd * (g - mean_d(g) - zh * mean_d(g * zh))        (dz = g0 without LayerNorm)
 //   d(residual) = dz;   d(x) = dz * [x + bias > 0]  (relu)  else dz
 template <typename TG, typename TX, int NPL>
-__global__ void __launch_bounds__(256, 3) bwd_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
   constexpr int D = 32 * NPL;
   constexpr int CE = NPL < 4 ? NPL : 4;
   constexpr int NCH = NPL / CE;
-  constexpr int R = RowsPerWarp<NPL, (sizeof(TX) > sizeof(TG) ? sizeof(TX) : sizeof(TG))>::RB;
   __shared__ float red[8][3][32 * CE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long nwarps = (long long)gridDim.x * 8;
-  const bool has_res = a.residual != nullptr, has_ln = a.gamma != nullptr;
-  // Occupancy is what this kernel lives on (three resident CTAs per SM: 80 registers): the column-sum accumulators are
-  // the only per-lane state that persists across rows; bias / gamma / beta are re-read from L1 where they are used and
-  // the sign of the pre-activation is kept as one bit per element.
-  float dgam[NCH][CE], dbet[NCH][CE], dbia[NCH][CE];
+  float bsv[NCH][CE], gmv[NCH][CE], btv[NCH][CE], dgam[NCH][CE], dbet[NCH][CE], dbia[NCH][CE];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+  for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-    for (int k = 0; k < CE; ++k) dgam[c][k] = dbet[c][k] = dbia[c][k] = 0.f;
-  const long long groups = (a.rows + R - 1) / R;
-  for (long long grp = (long long)blockIdx.x * 8 + warp; grp < groups; grp += nwarps) {
-    const long long row0 = grp * R;
+    for (int k = 0; k < CE; ++k) { bsv[c][k] = 0.f; gmv[c][k] = 1.f; btv[c][k] = 0.f; dgam[c][k] = dbet[c][k] = dbia[c][k] = 0.f; }
+    if (a.bias != nullptr) load_param<CE>(a.bias + (c * 32 + lane) * CE, bsv[c]);
+    if (a.gamma != nullptr) load_param<CE>(a.gamma + (c * 32 + lane) * CE, gmv[c]);
+    if (a.relu_out && a.beta != nullptr) load_param<CE>(a.beta + (c * 32 + lane) * CE, btv[c]);
+  }
+  constexpr int R = RowsPerWarp<NPL>::R;
+  for (long long row0 = ((long long)blockIdx.x * 8 + warp) * R; row0 < a.rows; row0 += nwarps * R) {
     const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
-    float g[R][NCH][CE], zh[R][NCH][CE];
+    float pre[R][NCH][CE], g[R][NCH][CE], zh[R][NCH][CE];
     float mean[R], rstd[R], s1[R], s2[R];
-    unsigned pos[R];                                   // bit (c * CE + k): pre-activation > 0
     // all loads of the R rows first (independent requests in flight), then the arithmetic
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const long long row = row0 + (r < nr ? r : 0);
+      const TX* xr = static_cast<const TX*>(a.x) + row * D;
+      const TG* dyr = static_cast<const TG*>(a.dy) + row * D;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        Vec<TX, CE>::load(static_cast<const TX*>(a.x) + row * D + (c * 32 + lane) * CE, zh[r][c]);
-        Vec<TG, CE>::load(static_cast<const TG*>(a.dy) + row * D + (c * 32 + lane) * CE, g[r][c]);
+        Vec<TX, CE>::load(xr + (c * 32 + lane) * CE, pre[r][c]);
+        Vec<TG, CE>::load(dyr + (c * 32 + lane) * CE, g[r][c]);
+        if (a.residual != nullptr) Vec<TX, CE>::load(static_cast<const TX*>(a.residual) + row * D + (c * 32 + lane) * CE, zh[r][c]);
       }
       mean[r] = 0.f;
       rstd[r] = 1.f;
-      if (has_ln) {
+      if (a.gamma != nullptr) {
         const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats + row * 2));
         mean[r] = st.x;
         rstd[r] = st.y;
@@ -308,34 +282,25 @@ __global__ void __launch_bounds__(256, 3) bwd_kernel(BwdArgs a) {
     for (int r = 0; r < R; ++r) {
       s1[r] = 0.f;
       s2[r] = 0.f;
-      pos[r] = 0u;
       const bool live = r < nr;                       // rows beyond the end contribute nothing to the column sums
-      const long long row = row0 + (r < nr ? r : 0);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int col = (c * 32 + lane) * CE;
-        float bs[CE], gm[CE], bt[CE], rs[CE];
-#pragma unroll
-        for (int k = 0; k < CE; ++k) { bs[k] = 0.f; gm[k] = 1.f; bt[k] = 0.f; rs[k] = 0.f; }
-        if (a.bias != nullptr) load_param<CE>(a.bias + col, bs);
-        if (has_ln) load_param<CE>(a.gamma + col, gm);
-        if (a.relu_out && a.beta != nullptr) load_param<CE>(a.beta + col, bt);
-        if (has_res) Vec<TX, CE>::load(static_cast<const TX*>(a.residual) + row * D + col, rs);
         unsigned keep = 0xfu;
         if (a.thr16 != 0u) keep = keep_bits<CE>(a.seed, row0 + r, D, col, a.thr16);
 #pragma unroll
         for (int k = 0; k < CE; ++k) {
-          const float p = zh[r][c][k] + bs[k];
-          if (p > 0.f) pos[r] |= 1u << (c * CE + k);
-          const float z = (a.relu ? fmaxf(p, 0.f) : p) + rs[k];
+          pre[r][c][k] += bsv[c][k];
+          float z = a.relu ? fmaxf(pre[r][c][k], 0.f) : pre[r][c][k];
+          if (a.residual != nullptr) z += zh[r][c][k];
           float g0 = live ? g[r][c][k] : 0.f;
           if (a.thr16 != 0u) g0 = ((keep >> k) & 1u) ? g0 * a.keep_scale : 0.f;
           const float h = (z - mean[r]) * rstd[r];
           zh[r][c][k] = h;
-          if (a.relu_out && !(h * gm[k] + bt[k] > 0.f)) g0 = 0.f;
-          const float gg = g0 * gm[k];
+          if (a.relu_out && !(h * gmv[c][k] + btv[c][k] > 0.f)) g0 = 0.f;
+          const float gg = g0 * gmv[c][k];
           g[r][c][k] = gg;
-          if (has_ln) {
+          if (a.gamma != nullptr) {
             dgam[c][k] += g0 * h;
             dbet[c][k] += g0;
             s1[r] += gg;
@@ -344,7 +309,7 @@ __global__ void __launch_bounds__(256, 3) bwd_kernel(BwdArgs a) {
         }
       }
     }
-    if (has_ln) {
+    if (a.gamma != nullptr) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -364,8 +329,8 @@ __global__ void __launch_bounds__(256, 3) bwd_kernel(BwdArgs a) {
         float dz[CE], dp[CE];
 #pragma unroll
         for (int k = 0; k < CE; ++k) {
-          dz[k] = has_ln ? rstd[r] * (g[r][c][k] - m1 - zh[r][c][k] * m2) : g[r][c][k];
-          dp[k] = (a.relu && !((pos[r] >> (c * CE + k)) & 1u)) ? 0.f : dz[k];
+          dz[k] = a.gamma != nullptr ? rstd[r] * (g[r][c][k] - m1 - zh[r][c][k] * m2) : g[r][c][k];
+          dp[k] = (a.relu && !(pre[r][c][k] > 0.f)) ? 0.f : dz[k];
           dbia[c][k] += dp[k];
         }
         if (a.dres != nullptr) Vec<TG, CE>::store(static_cast<TG*>(a.dres) + row * D + col, dz);
@@ -397,11 +362,9 @@ __global__ void __launch_bounds__(256, 3) bwd_kernel(BwdArgs a) {
 
 template <typename TIn, typename TOut, int NPL>
 void launch_fwd_n(const FwdArgs& a, cudaStream_t st) {
-  constexpr int R = RowsPerWarp<NPL, sizeof(TIn)>::R;
-  long long blocks = ((a.rows + R - 1) / R + 7) / 8;
-  if (blocks > 148 * 3) blocks = 148 * 3;                  // persistent: every resident warp walks row groups with a grid stride
-  if (a.residual != nullptr) fwd_kernel<TIn, TOut, NPL, true><<<(unsigned)blocks, 256, 0, st>>>(a);
-  else fwd_kernel<TIn, TOut, NPL, false><<<(unsigned)blocks, 256, 0, st>>>(a);
+  constexpr int R = RowsPerWarp<NPL>::R;
+  const long long warps = (a.rows + R - 1) / R;
+  fwd_kernel<TIn, TOut, NPL><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(a);
 }
 
 template <typename TIn, typename TOut>

@@ -684,13 +684,17 @@ def test_c_abi_error_codes():
     assert h.allset_csr_from_coo(None, None, 2 ** 31, 10, rp.data_ptr(), None, None, None, 0, None) == -2       # ERANGE
     assert b'int32' in h.allset_last_error()
     assert h.allset_segreduce_fwd(x.data_ptr(), 7, 4, 8, rp.data_ptr(), col.data_ptr(), None, None, 4, 0, None, 0, 0,
-                                  out.data_ptr(), None) == -1                                                    # dtype
+                                  out.data_ptr(), None, 0, None) == -1                                           # dtype
     assert h.allset_segreduce_fwd(x.data_ptr(), 0, 4, 8, rp.data_ptr(), col.data_ptr(), None, None, 4, 9, None, 0, 0,
-                                  out.data_ptr(), None) == -1                                                    # op
+                                  out.data_ptr(), None, 0, None) == -1                                           # op
     assert h.allset_segreduce_fwd(x.data_ptr(), 0, 4, 8, None, col.data_ptr(), None, None, 4, 0, None, 0, 0,
-                                  out.data_ptr(), None) == -1                                                    # null rowptr
+                                  out.data_ptr(), None, 0, None) == -1                                           # null rowptr
     assert h.allset_pma_fwd(x.data_ptr(), x.data_ptr(), x.data_ptr(), 0, 2, 4, float('nan'), rp.data_ptr(), col.data_ptr(), 4,
-                            None, 0, 0, out.data_ptr(), None, None) == -1                                        # slope
+                            None, 0, 0, out.data_ptr(), None, None, 0, None) == -1                               # slope
+    small = torch.zeros(64, dtype=torch.uint8, device=dev())
+    assert h.allset_segreduce_fwd(x.data_ptr(), 0, 4, 8, rp.data_ptr(), col.data_ptr(), None, None, 4, 0, None, 0, 0,
+                                  out.data_ptr(), small.data_ptr(), 64, None) == -3                              # workspace too small
+    assert h.allset_stream_workspace_bytes(128) >= 148 * 24 * 8 * (4 + 2 * 128 * 4)
     ws = torch.zeros(16, dtype=torch.uint8, device=dev())
     t = torch.zeros(3, dtype=torch.int64, device=dev())
     assert h.allset_csr_from_coo(t.data_ptr(), t.data_ptr(), 3, 4, rp.data_ptr(), col.data_ptr(), col.data_ptr(),
