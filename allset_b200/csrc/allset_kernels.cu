@@ -2094,8 +2094,11 @@ StreamPlan plan_stream(int d, int elem_bytes, long long n_tgt, const void* x, co
 
 // how the fused exchange leaves the SM: 1 = stores by the reducing warp, 2 = TMA bulk stores from a staging slot
 int push_mode() {
-  const char* e = getenv("ALLSET_PUSH");          // read per launch (a host-side lookup): A/B runs and tests flip it
-  return (e != nullptr && (e[0] == 'd' || e[0] == '1')) ? 1 : 2;
+  // read per launch (a host-side lookup): A/B runs and tests flip it.  Measured on 2 x B200 (profiles/r02_scaling.md): the
+  // stores by the reducing warp are faster while the kernel is compute-bound (V->E 1.35 vs 1.44 ms), so they are the default;
+  // ALLSET_PUSH=bulk selects the TMA path.
+  const char* e = getenv("ALLSET_PUSH");
+  return (e != nullptr && (e[0] == 'b' || e[0] == '2')) ? 2 : 1;
 }
 
 struct StreamExtra {            // optional arguments of the stream kernels

@@ -96,17 +96,42 @@ struct FwdArgs {
   float keep_scale; unsigned thr16; uint64_t seed; long long rows; void* out; float* stats; int relu_out;
 };
 
+struct BwdArgs {
+  const void* dy; const void* x; const float* bias; int relu; const void* residual; const float* gamma;
+  const float* stats; float keep_scale; unsigned thr16; uint64_t seed; long long rows; void* dx; void* dres;
+  float* partial; const float* beta; int relu_out;
+};
+
+// Which stages a launch has.  The generic kernels (F < 0) read the flags from the arguments; at ~110 SASS instructions
+// per element (every optional stage present as predicated code, the dropout hash computed to be discarded) they were
+// ISSUE-bound at 2.9 TB/s, so the stage combinations the MLP / PMA chains actually launch are compiled with the flags
+// as constants and the dead stages removed.
+enum : int { kBias = 1, kRelu = 2, kRes = 4, kLn = 8, kReluOut = 16, kDrop = 32 };
+template <int F>
+struct Flag {
+  template <typename A> __device__ static __forceinline__ bool bias(const A& a) { return F < 0 ? a.bias != nullptr : (F & kBias) != 0; }
+  template <typename A> __device__ static __forceinline__ bool relu(const A& a) { return F < 0 ? a.relu != 0 : (F & kRelu) != 0; }
+  template <typename A> __device__ static __forceinline__ bool res(const A& a) { return F < 0 ? a.residual != nullptr : (F & kRes) != 0; }
+  template <typename A> __device__ static __forceinline__ bool ln(const A& a) { return F < 0 ? a.gamma != nullptr : (F & kLn) != 0; }
+  template <typename A> __device__ static __forceinline__ bool relu_out(const A& a) { return F < 0 ? a.relu_out != 0 : (F & kReluOut) != 0; }
+  template <typename A> __device__ static __forceinline__ bool drop(const A& a) { return F < 0 ? a.thr16 != 0u : (F & kDrop) != 0; }
+};
+__host__ inline int flags_of(bool bias, bool relu, bool res, bool ln, bool relu_out, bool drop) {
+  return (bias ? kBias : 0) | (relu ? kRelu : 0) | (res ? kRes : 0) | (ln ? kLn : 0) | (relu_out ? kReluOut : 0) | (drop ? kDrop : 0);
+}
+
 // rows a warp holds at once: the loads of all of them are issued before the first use, so a warp has R row-sized
 // requests in flight (a 256-byte bf16 row per warp is far too little to cover HBM latency: measured 2.3 TB/s with R = 1)
 template <int NPL>
 struct RowsPerWarp { static constexpr int R = NPL <= 4 ? 4 : (NPL == 8 ? 2 : 1); };
 
-template <typename TIn, typename TOut, int NPL>
+template <typename TIn, typename TOut, int NPL, int F>
 __global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
   constexpr int D = 32 * NPL;
   constexpr int CE = NPL < 4 ? NPL : 4;
   constexpr int NCH = NPL / CE;
   constexpr int R = RowsPerWarp<NPL>::R;
+  using FL = Flag<F>;
   const int lane = threadIdx.x & 31;
   const long long row0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R;
   if (row0 >= a.rows) return;
@@ -118,45 +143,39 @@ __global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
 #pragma unroll
     for (int c = 0; c < NCH; ++c) Vec<TIn, CE>::load(xr + (c * 32 + lane) * CE, v[r][c]);
   }
-  if (a.residual != nullptr) {
-    float rs[R][NCH][CE];
+  if (FL::bias(a)) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float b[CE];
+      load_param<CE>(a.bias + (c * 32 + lane) * CE, b);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < CE; ++k) v[r][c][k] += b[k];
+    }
+  }
+  if (FL::relu(a)) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int k = 0; k < CE; ++k) v[r][c][k] = fmaxf(v[r][c][k], 0.f);
+  }
+  if (FL::res(a)) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const TIn* rr = static_cast<const TIn*>(a.residual) + (row0 + (r < nr ? r : 0)) * D;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) Vec<TIn, CE>::load(rr + (c * 32 + lane) * CE, rs[r][c]);
-    }
+      for (int c = 0; c < NCH; ++c) {
+        float rs[CE];
+        Vec<TIn, CE>::load(rr + (c * 32 + lane) * CE, rs);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      float b[CE];
-#pragma unroll
-      for (int k = 0; k < CE; ++k) b[k] = 0.f;
-      if (a.bias != nullptr) load_param<CE>(a.bias + (c * 32 + lane) * CE, b);
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int k = 0; k < CE; ++k) {
-          const float t = v[r][c][k] + b[k];
-          v[r][c][k] = (a.relu ? fmaxf(t, 0.f) : t) + rs[r][c][k];
-        }
-    }
-  } else if (a.bias != nullptr || a.relu) {
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      float b[CE];
-#pragma unroll
-      for (int k = 0; k < CE; ++k) b[k] = 0.f;
-      if (a.bias != nullptr) load_param<CE>(a.bias + (c * 32 + lane) * CE, b);
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int k = 0; k < CE; ++k) {
-          const float t = v[r][c][k] + b[k];
-          v[r][c][k] = a.relu ? fmaxf(t, 0.f) : t;
-        }
+        for (int k = 0; k < CE; ++k) v[r][c][k] += rs[k];
+      }
     }
   }
-  if (a.gamma != nullptr) {
+  if (FL::ln(a)) {
     float mean[R], rstd[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -201,34 +220,35 @@ __global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int k = 0; k < CE; ++k) v[r][c][k] = (v[r][c][k] - mean[r]) * rstd[r] * g[k] + b[k];
+        for (int k = 0; k < CE; ++k) v[r][c][k] = fmaf((v[r][c][k] - mean[r]) * rstd[r], g[k], b[k]);
     }
+  }
+  if (FL::relu_out(a)) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int k = 0; k < CE; ++k) v[r][c][k] = fmaxf(v[r][c][k], 0.f);
+  }
+  if (FL::drop(a)) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const unsigned keep = keep_bits<CE>(a.seed, row0 + r, D, (c * 32 + lane) * CE, a.thr16);
+#pragma unroll
+        for (int k = 0; k < CE; ++k) v[r][c][k] = ((keep >> k) & 1u) ? v[r][c][k] * a.keep_scale : 0.f;
+      }
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if (r >= nr) break;
-    const long long row = row0 + r;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      if (a.relu_out) {
-#pragma unroll
-        for (int k = 0; k < CE; ++k) v[r][c][k] = fmaxf(v[r][c][k], 0.f);
-      }
-      if (a.thr16 != 0u) {
-        const unsigned keep = keep_bits<CE>(a.seed, row, D, (c * 32 + lane) * CE, a.thr16);
-#pragma unroll
-        for (int k = 0; k < CE; ++k) v[r][c][k] = ((keep >> k) & 1u) ? v[r][c][k] * a.keep_scale : 0.f;
-      }
-      Vec<TOut, CE>::store(static_cast<TOut*>(a.out) + row * D + (c * 32 + lane) * CE, v[r][c]);
-    }
+    for (int c = 0; c < NCH; ++c)
+      Vec<TOut, CE>::store(static_cast<TOut*>(a.out) + (row0 + r) * D + (c * 32 + lane) * CE, v[r][c]);
   }
 }
-
-struct BwdArgs {
-  const void* dy; const void* x; const float* bias; int relu; const void* residual; const float* gamma;
-  const float* stats; float keep_scale; unsigned thr16; uint64_t seed; long long rows; void* dx; void* dres;
-  float* partial; const float* beta; int relu_out;
-};
 
 // Backward.  A warp walks rows with a grid stride so that every lane owns fixed columns: d(gamma), d(beta), d(bias)
 // accumulate in registers over all rows of the warp, are combined per CTA through shared memory and written as ONE
@@ -236,11 +256,13 @@ struct BwdArgs {
 //   g0 = dy * keep / (1-p) * [y > 0 if act2];  zh = (z - mean) * rstd;  y = zh * gamma + beta;  g = g0 * gamma
 //   dz = rstd * (g - mean_d(g) - zh * mean_d(g * zh))        (dz = g0 without LayerNorm)
 //   d(residual) = dz;   d(x) = dz * [x + bias > 0]  (relu)  else dz
-template <typename TG, typename TX, int NPL>
+template <typename TG, typename TX, int NPL, int F>
 __global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
   constexpr int D = 32 * NPL;
   constexpr int CE = NPL < 4 ? NPL : 4;
   constexpr int NCH = NPL / CE;
+  constexpr int R = RowsPerWarp<NPL>::R;
+  using FL = Flag<F>;
   __shared__ float red[8][3][32 * CE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long nwarps = (long long)gridDim.x * 8;
@@ -249,11 +271,10 @@ __global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
   for (int c = 0; c < NCH; ++c) {
 #pragma unroll
     for (int k = 0; k < CE; ++k) { bsv[c][k] = 0.f; gmv[c][k] = 1.f; btv[c][k] = 0.f; dgam[c][k] = dbet[c][k] = dbia[c][k] = 0.f; }
-    if (a.bias != nullptr) load_param<CE>(a.bias + (c * 32 + lane) * CE, bsv[c]);
-    if (a.gamma != nullptr) load_param<CE>(a.gamma + (c * 32 + lane) * CE, gmv[c]);
-    if (a.relu_out && a.beta != nullptr) load_param<CE>(a.beta + (c * 32 + lane) * CE, btv[c]);
+    if (FL::bias(a)) load_param<CE>(a.bias + (c * 32 + lane) * CE, bsv[c]);
+    if (FL::ln(a)) load_param<CE>(a.gamma + (c * 32 + lane) * CE, gmv[c]);
+    if (FL::relu_out(a) && a.beta != nullptr) load_param<CE>(a.beta + (c * 32 + lane) * CE, btv[c]);
   }
-  constexpr int R = RowsPerWarp<NPL>::R;
   for (long long row0 = ((long long)blockIdx.x * 8 + warp) * R; row0 < a.rows; row0 += nwarps * R) {
     const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
     float pre[R][NCH][CE], g[R][NCH][CE], zh[R][NCH][CE];
@@ -262,17 +283,15 @@ __global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const long long row = row0 + (r < nr ? r : 0);
-      const TX* xr = static_cast<const TX*>(a.x) + row * D;
-      const TG* dyr = static_cast<const TG*>(a.dy) + row * D;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        Vec<TX, CE>::load(xr + (c * 32 + lane) * CE, pre[r][c]);
-        Vec<TG, CE>::load(dyr + (c * 32 + lane) * CE, g[r][c]);
-        if (a.residual != nullptr) Vec<TX, CE>::load(static_cast<const TX*>(a.residual) + row * D + (c * 32 + lane) * CE, zh[r][c]);
+        Vec<TX, CE>::load(static_cast<const TX*>(a.x) + row * D + (c * 32 + lane) * CE, pre[r][c]);
+        Vec<TG, CE>::load(static_cast<const TG*>(a.dy) + row * D + (c * 32 + lane) * CE, g[r][c]);
+        if (FL::res(a)) Vec<TX, CE>::load(static_cast<const TX*>(a.residual) + row * D + (c * 32 + lane) * CE, zh[r][c]);
       }
       mean[r] = 0.f;
       rstd[r] = 1.f;
-      if (a.gamma != nullptr) {
+      if (FL::ln(a)) {
         const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats + row * 2));
         mean[r] = st.x;
         rstd[r] = st.y;
@@ -282,34 +301,41 @@ __global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
     for (int r = 0; r < R; ++r) {
       s1[r] = 0.f;
       s2[r] = 0.f;
-      const bool live = r < nr;                       // rows beyond the end contribute nothing to the column sums
+      if (r >= nr) {                                   // rows beyond the end contribute nothing to the column sums
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int k = 0; k < CE; ++k) g[r][c][k] = 0.f;
+      }
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        const int col = (c * 32 + lane) * CE;
         unsigned keep = 0xfu;
-        if (a.thr16 != 0u) keep = keep_bits<CE>(a.seed, row0 + r, D, col, a.thr16);
+        if (FL::drop(a)) keep = keep_bits<CE>(a.seed, row0 + r, D, (c * 32 + lane) * CE, a.thr16);
 #pragma unroll
         for (int k = 0; k < CE; ++k) {
-          pre[r][c][k] += bsv[c][k];
-          float z = a.relu ? fmaxf(pre[r][c][k], 0.f) : pre[r][c][k];
-          if (a.residual != nullptr) z += zh[r][c][k];
-          float g0 = live ? g[r][c][k] : 0.f;
-          if (a.thr16 != 0u) g0 = ((keep >> k) & 1u) ? g0 * a.keep_scale : 0.f;
-          const float h = (z - mean[r]) * rstd[r];
-          zh[r][c][k] = h;
-          if (a.relu_out && !(h * gmv[c][k] + btv[c][k] > 0.f)) g0 = 0.f;
-          const float gg = g0 * gmv[c][k];
-          g[r][c][k] = gg;
-          if (a.gamma != nullptr) {
-            dgam[c][k] += g0 * h;
+          if (FL::bias(a)) pre[r][c][k] += bsv[c][k];
+          float z = FL::relu(a) ? fmaxf(pre[r][c][k], 0.f) : pre[r][c][k];
+          if (FL::res(a)) z += zh[r][c][k];
+          float g0 = g[r][c][k];
+          if (FL::drop(a)) g0 = ((keep >> k) & 1u) ? g0 * a.keep_scale : 0.f;
+          if (FL::ln(a)) {
+            const float h = (z - mean[r]) * rstd[r];
+            zh[r][c][k] = h;
+            if (FL::relu_out(a) && !(fmaf(h, gmv[c][k], btv[c][k]) > 0.f)) g0 = 0.f;
+            const float gg = g0 * gmv[c][k];
+            g[r][c][k] = gg;
+            dgam[c][k] = fmaf(g0, h, dgam[c][k]);
             dbet[c][k] += g0;
             s1[r] += gg;
-            s2[r] += gg * h;
+            s2[r] = fmaf(gg, h, s2[r]);
+          } else {
+            if (FL::relu_out(a) && !(z > 0.f)) g0 = 0.f;
+            g[r][c][k] = g0;
           }
         }
       }
     }
-    if (a.gamma != nullptr) {
+    if (FL::ln(a)) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -329,11 +355,11 @@ __global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
         float dz[CE], dp[CE];
 #pragma unroll
         for (int k = 0; k < CE; ++k) {
-          dz[k] = a.gamma != nullptr ? rstd[r] * (g[r][c][k] - m1 - zh[r][c][k] * m2) : g[r][c][k];
-          dp[k] = (a.relu && !(pre[r][c][k] > 0.f)) ? 0.f : dz[k];
-          dbia[c][k] += dp[k];
+          dz[k] = FL::ln(a) ? rstd[r] * (g[r][c][k] - m1 - zh[r][c][k] * m2) : g[r][c][k];
+          dp[k] = (FL::relu(a) && !(pre[r][c][k] > 0.f)) ? 0.f : dz[k];
+          if (FL::bias(a)) dbia[c][k] += dp[k];
         }
-        if (a.dres != nullptr) Vec<TG, CE>::store(static_cast<TG*>(a.dres) + row * D + col, dz);
+        if (FL::res(a) && a.dres != nullptr) Vec<TG, CE>::store(static_cast<TG*>(a.dres) + row * D + col, dz);
         Vec<TG, CE>::store(static_cast<TG*>(a.dx) + row * D + col, dp);
       }
     }
@@ -360,33 +386,60 @@ __global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
   }
 }
 
+// ---- dispatch: the stage combinations the MLP / PMA chains launch get constant flags (same dtype on both sides, widths
+//      64 / 128 / 256); everything else takes the generic kernels (F = -1) -------------------------------------------------
+#define ROWOP_COMBOS(X)                                                                                   \
+  X(kLn) X(kBias | kRelu | kLn | kDrop) X(kBias | kRelu | kLn) X(kBias | kRelu | kDrop) X(kBias | kRelu) \
+  X(kBias) X(kBias | kRelu | kRes | kLn | kReluOut | kDrop) X(kBias | kRelu | kRes | kLn | kReluOut) X(kDrop)
+
 template <typename TIn, typename TOut, int NPL>
-void launch_fwd_n(const FwdArgs& a, cudaStream_t st) {
+void launch_fwd_n(const FwdArgs& a, int flags, bool specialise, cudaStream_t st) {
   constexpr int R = RowsPerWarp<NPL>::R;
   const long long warps = (a.rows + R - 1) / R;
-  fwd_kernel<TIn, TOut, NPL><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(a);
+  const unsigned blocks = (unsigned)((warps + 7) / 8);
+  if (specialise) {
+#define ROWOP_CASE(FV) if (flags == (FV)) { fwd_kernel<TIn, TOut, NPL, (FV)><<<blocks, 256, 0, st>>>(a); return; }
+    ROWOP_COMBOS(ROWOP_CASE)
+#undef ROWOP_CASE
+  }
+  fwd_kernel<TIn, TOut, NPL, -1><<<blocks, 256, 0, st>>>(a);
 }
 
 template <typename TIn, typename TOut>
 bool launch_fwd(const FwdArgs& a, int d, cudaStream_t st) {
+  const int flags = flags_of(a.bias != nullptr, a.relu != 0, a.residual != nullptr, a.gamma != nullptr, a.relu_out != 0,
+                             a.thr16 != 0u);
   switch (d) {
-    case 64: launch_fwd_n<TIn, TOut, 2>(a, st); return true;
-    case 128: launch_fwd_n<TIn, TOut, 4>(a, st); return true;
-    case 256: launch_fwd_n<TIn, TOut, 8>(a, st); return true;
-    case 512: launch_fwd_n<TIn, TOut, 16>(a, st); return true;
-    case 1024: launch_fwd_n<TIn, TOut, 32>(a, st); return true;
+    case 64: launch_fwd_n<TIn, TOut, 2>(a, flags, true, st); return true;
+    case 128: launch_fwd_n<TIn, TOut, 4>(a, flags, true, st); return true;
+    case 256: launch_fwd_n<TIn, TOut, 8>(a, flags, true, st); return true;
+    case 512: launch_fwd_n<TIn, TOut, 16>(a, flags, false, st); return true;
+    case 1024: launch_fwd_n<TIn, TOut, 32>(a, flags, false, st); return true;
     default: return false;
   }
 }
 
+template <typename TG, typename TX, int NPL>
+void launch_bwd_n(const BwdArgs& a, int flags, bool specialise, unsigned blocks, cudaStream_t st) {
+  if (specialise) {
+#define ROWOP_CASE(FV) if (flags == (FV)) { bwd_kernel<TG, TX, NPL, (FV)><<<blocks, 256, 0, st>>>(a); return; }
+    ROWOP_COMBOS(ROWOP_CASE)
+#undef ROWOP_CASE
+  }
+  bwd_kernel<TG, TX, NPL, -1><<<blocks, 256, 0, st>>>(a);
+}
+
 template <typename TG, typename TX>
 bool launch_bwd(const BwdArgs& a, int d, unsigned blocks, cudaStream_t st) {
+  const int flags = flags_of(a.bias != nullptr, a.relu != 0, a.residual != nullptr, a.gamma != nullptr, a.relu_out != 0,
+                             a.thr16 != 0u);
+  constexpr bool same = sizeof(TG) == sizeof(TX);       // mixed-dtype gradients only occur at the model's edges
   switch (d) {
-    case 64: bwd_kernel<TG, TX, 2><<<blocks, 256, 0, st>>>(a); return true;
-    case 128: bwd_kernel<TG, TX, 4><<<blocks, 256, 0, st>>>(a); return true;
-    case 256: bwd_kernel<TG, TX, 8><<<blocks, 256, 0, st>>>(a); return true;
-    case 512: bwd_kernel<TG, TX, 16><<<blocks, 256, 0, st>>>(a); return true;
-    case 1024: bwd_kernel<TG, TX, 32><<<blocks, 256, 0, st>>>(a); return true;
+    case 64: launch_bwd_n<TG, TX, 2>(a, flags, same, blocks, st); return true;
+    case 128: launch_bwd_n<TG, TX, 4>(a, flags, same, blocks, st); return true;
+    case 256: launch_bwd_n<TG, TX, 8>(a, flags, same, blocks, st); return true;
+    case 512: launch_bwd_n<TG, TX, 16>(a, flags, false, blocks, st); return true;
+    case 1024: launch_bwd_n<TG, TX, 32>(a, flags, false, blocks, st); return true;
     default: return false;
   }
 }

@@ -471,7 +471,14 @@ def run_b200(a):
             x_host_mine.copy_(x_v[sh.v_lo:sh.v_hi])
         out_host = [torch.empty((out_rows, d), dtype=dtype).pin_memory() for _ in range(2)]
         ph_ev = {'h2d': [], 'gather': [], 'compute': [], 'd2h': []}
-        x_in = [torch.empty_like(x_v) for _ in range(2)]
+        x_in_rep = None
+        if world > 1 and isinstance(x_e, sharding.ReplicatedRows):
+            # the input replicas live in symmetric memory: a rank lands ITS rows over PCIe and pushes them to the peers
+            # itself (allset_push_rows over NVLink) instead of an NCCL all-gather competing for SMs with the reduce kernels
+            x_in_rep = [sharding.ReplicatedRows(Nv, d, dtype, dev, multicast=False) for _ in range(2)]
+            x_in = [r.tensor for r in x_in_rep]
+        else:
+            x_in = [torch.empty_like(x_v) for _ in range(2)]
         xv_out = [torch.empty_like(x_v) for _ in range(2)] if world > 1 else None
         inc_v2e, inc_e2v = v2e, v2e.reversed()
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
@@ -492,9 +499,15 @@ def run_b200(a):
                     t2 = t1
                 else:
                     # every rank pulls 1/N of the input over ITS PCIe link, NVLink replicates it (V->E needs all rows)
+                    if x_in_rep is not None:
+                        x_in_rep[b].barrier()                                # every rank is done reading buffer b (step k-2)
                     x_in[b][sh.v_lo:sh.v_hi].copy_(x_host_mine, non_blocking=True)
                     t1 = torch.cuda.Event(enable_timing=True); t1.record(s_in)
-                    sharding.allgather_rows(x_in[b], sh.v_ranges, rank)
+                    if x_in_rep is not None:
+                        _lib.push_rows(x_in[b][sh.v_lo:sh.v_hi], x_in_rep[b].peer_ptrs(sh.v_lo, unicast=True))
+                        x_in_rep[b].barrier()                                # every rank's rows have landed everywhere
+                    else:
+                        sharding.allgather_rows(x_in[b], sh.v_ranges, rank)
                     t2 = torch.cuda.Event(enable_timing=True); t2.record(s_in)
                 if _marks is not None:
                     ph_ev['h2d'].append((t0, t1)); ph_ev['gather'].append((t1, t2))
@@ -541,10 +554,11 @@ def run_b200(a):
                'h2d_bytes_per_step': int(Nv * d * es), 'd2h_bytes_per_step': int(Nv * d * es),
                'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
                'pipeline': 'H2D(k+1) || compute(k) || D2H(k-1), double-buffered, 3 streams' + ('' if world == 1 else
-                            '; each rank copies 1/N of X_v from the host and NCCL all-gathers it over NVLink'),
+                            '; each rank copies 1/N of X_v from the host and replicates it over NVLink (%s)'
+                            % ('P2P push into symmetric memory' if x_in_rep is not None else 'NCCL all-gather')),
                'api': 'allset_b200.segment_reduce(x, Incidence, None, "sum") x2' if world == 1
                       else 'allset_b200.sharding.ShardedIncidence.layer_pair_sum'}
-        del x_host, x_host_mine, out_host, x_in, xv_out
+        del x_host, x_host_mine, out_host, x_in, xv_out, x_in_rep
     clocks = sampler.stop()
 
     # ---- AllSetTransformer (PMA, heads=H) on the same graph: reported beside the headline -----------------------
@@ -677,7 +691,7 @@ def run_b200(a):
                        'hyperedge-sharded V->E / vertex-sharded E->V x%d; X_e exchanged between the directions every '
                        'step; updated X_v %s' % (world, 'replicated every step (another layer can follow)' if a.replicate_xv
                                                 else 'left vertex-sharded (last layer: the next op is row-parallel); see other_mode'),
-                       'exchange': exchange, 'push': os.environ.get('ALLSET_PUSH', 'bulk (TMA cp.async.bulk from a staging slot)'),
+                       'exchange': exchange, 'push': os.environ.get('ALLSET_PUSH', 'direct (stores by the reducing warp)'),
                        'l2': 'inputs larger than L2 (X_v %.2f GB, col %.2f GB per step; no flush)'
                              % (Nv * d * es / 1e9, nnz * 4 / 1e9)},
             'clocks': clocks,

@@ -107,9 +107,10 @@ int allset_segreduce_fwd(const void* x, int dtype, int64_t n_src, int32_t d,
 /* Fused compute + exchange (multi-GPU, one process per GPU; no counterpart in the single-device reference).
  * Same reduction as allset_segreduce_fwd, but every reduced row is ALSO sent, from the kernel's epilogue, to the same row
  * of `n_peers` (<= 7) peer replicas over NVLink, so the all-gather of the rank's row range that would follow the kernel
- * costs no extra launch and overlaps the reduce.  By default the row is parked in a shared-memory staging slot and handed
- * to the TMA (cp.async.bulk shared -> global, one bulk store per peer) so that NVLink back-pressure never stalls the
- * gathering warps; ALLSET_PUSH=direct makes the reducing warp store to the peers itself.
+ * costs no extra launch and overlaps the reduce.  By default the reducing warp stores the row to the peers itself
+ * (st.global on peer addresses, fire-and-forget); ALLSET_PUSH=bulk parks the row in a shared-memory staging slot and hands it
+ * to the TMA instead (cp.async.bulk shared -> global, one bulk store per peer), which takes NVLink back-pressure off the
+ * gathering warps at the price of a staging pass (measured slower while the kernel is compute-bound).
  *   out          this rank's rows inside its own replica (row 0 of the rank's range)
  *   peer_outs    HOST array of n_peers peer-mapped DEVICE pointers: the address of that same row in each peer replica
  *                (or ONE multicast address that the NVSwitch replicates into every replica)

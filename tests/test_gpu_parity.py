@@ -98,9 +98,29 @@ def test_setgnn_real_fp32(name):
     assert torch.equal(out2, out)
 
 
+def _inherent_bf16(rec):
+    """The reference's own arithmetic (CPU oracle, fp32 everywhere) with ONLY the rows the aggregation gathers and the rows
+    it writes rounded to bf16: the definition of the bf16 storage mode, no kernel involved.  -> (logits, taps)"""
+    bf = lambda t: t.to(torch.bfloat16).float()                                                    # noqa: E731
+    orig_sum, orig_pma = O.aggregate_sum_mean, O.aggregate_pma
+    O.aggregate_sum_mean = lambda x, s, t, n, g: bf(orig_sum(bf(x), s, t, n, g))
+    O.aggregate_pma = lambda v, sc, sd, s, t, sl=0.2: (lambda o: (bf(o[0]), o[1]))(orig_pma(bf(v), sc, sd, s, t, sl))
+    try:
+        a = rec['args']
+        with torch.no_grad():
+            return O.setgnn(rec['state_dict'], golden_x(rec), rec['edge_index'], rec['norm'], PMA=a['PMA'], heads=a['heads'],
+                            aggregate=a['aggregate'])
+    finally:
+        O.aggregate_sum_mean, O.aggregate_pma = orig_sum, orig_pma
+
+
 @pytest.mark.parametrize('name', ['cora_alldeepsets.pt', 'citeseer_allsettransformer.pt'])
 def test_setgnn_real_bf16_storage(name):
-    """bf16 rows in the aggregation kernels (fp32 accumulate), everything else fp32: <= 1e-2 of the reference."""
+    """bf16 rows in the aggregation kernels (fp32 accumulate), everything else fp32.  Operator level (first tap): within
+    north_star's 1e-2.  Model level: the mode ITSELF -- the reference's arithmetic with bf16-rounded rows, emulated on the
+    CPU -- is 1.1e-2 (cora) / 0.8e-2 (citeseer) of the logit scale away from fp32, because each LayerNorm'd half layer
+    amplifies a 2^-9 rounding ~3x (profiles/r02_bf16_error_budget.md); the GPU path must stay within that inherent error
+    plus 0.75e-2, and within 1e-2 of the emulation wherever the emulation applies exactly (AllDeepSets)."""
     rec = load_golden(name)
     model, data = _build(rec, agg_dtype=torch.bfloat16)
     taps, hooks = _taps(model)
@@ -108,11 +128,15 @@ def test_setgnn_real_bf16_storage(name):
     for h in hooks:
         h.remove()
     s = rec['tap_stride']
-    # first aggregation output: single bf16 rounding of inputs + outputs
-    torch.testing.assert_close(taps[0][::s], F.relu(rec['taps'][0]), rtol=2e-2, atol=2e-2)
+    q_out, _ = _inherent_bf16(rec)
+    tap0 = F.relu(rec['taps'][0])
+    assert (taps[0][::s] - tap0).abs().max().item() <= 1e-2 * max(tap0.abs().max().item(), 1.0)
+    scale = max(rec['logits'].abs().max().item(), 1.0)
     err = (out.detach().cpu() - rec['logits']).abs().max().item()
-    scale = rec['logits'].abs().max().item()
-    assert err <= 1e-2 * max(scale, 1.0) * 2, (err, scale)
+    inherent = (q_out - rec['logits']).abs().max().item()
+    assert err <= inherent + 0.75e-2 * scale, (err, inherent, scale)
+    if not rec['args']['PMA']:
+        assert (out.detach().cpu() - q_out).abs().max().item() <= 1e-2 * scale
 
 
 @pytest.mark.parametrize('idx', range(12))
