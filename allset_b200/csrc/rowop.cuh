@@ -14,7 +14,7 @@
 // CE = min(NPL, 4) consecutive elements, chunk c of lane l = columns (c*32 + l)*CE ..+CE, so every warp access is one
 // contiguous 32*CE*sizeof(T)-byte piece.
 //
-// Dropout is counter-based: element (row, col) is kept iff a 16-bit slice of mix64(seed, row * d/4 + col/4) >= p*65536,
+// Dropout is counter-based: element (row, col) is kept iff a 16-bit slice of a hash of (seed, row, col / 2) >= p*65536,
 // so the backward pass regenerates the mask instead of reading one (torch's dropout saves a bool mask: +1 byte per
 // element each way).  Statistically equivalent to F.dropout, not the same stream of random numbers.
 
@@ -26,11 +26,13 @@ namespace rowop {
 
 using bf16 = __nv_bfloat16;
 
-__device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx) {
-  uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
+// 32-bit finaliser (two multiply / xor-shift rounds, "lowbias32"): ~8 instructions for the 32 random bits that decide
+// two elements.  A 64-bit splitmix per four elements cost ~11 instructions per element -- a third of the forward kernel.
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352dU;
+  x ^= x >> 15; x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
 }
 
 template <typename T, int CE>
@@ -77,18 +79,51 @@ __device__ __forceinline__ void load_param(const float* p, float (&f)[CE]) {
   else { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); f[0] = v.x; f[1] = v.y; }
 }
 
-// keep-mask bits of the CE elements of one chunk (bit k set = keep element k)
+// keep-mask bits of the CE elements of one chunk (bit k set = keep element k): one 32-bit hash per PAIR of consecutive
+// columns, 16 bits per element, keyed by (seed, row, column pair)
 template <int CE>
 __device__ __forceinline__ unsigned keep_bits(uint64_t seed, long long row, int d, int col, unsigned thr16) {
-  // one 64-bit hash per 4 consecutive columns; CE == 2 chunks use the low or high half of it
-  const uint64_t h = mix64(seed, (uint64_t)row * (uint64_t)(d >> 2) + (uint64_t)(col >> 2));
+  const unsigned s_lo = (unsigned)seed, s_hi = (unsigned)(seed >> 32);
+  const unsigned base = (unsigned)row * (unsigned)(d >> 1) + (unsigned)(col >> 1);
   unsigned bits = 0;
 #pragma unroll
-  for (int k = 0; k < CE; ++k) {
-    const int q = (CE == 4) ? k : ((col & 2) + k);
-    bits |= (((unsigned)(h >> (16 * q)) & 0xffffu) >= thr16 ? 1u : 0u) << k;
+  for (int p = 0; p < CE / 2; ++p) {
+    const unsigned h = mix32((base + (unsigned)p) * 0x9E3779B1U + s_lo) ^ s_hi;
+    bits |= ((h & 0xffffu) >= thr16 ? 1u : 0u) << (2 * p);
+    bits |= ((h >> 16) >= thr16 ? 1u : 0u) << (2 * p + 1);
   }
   return bits;
+}
+
+// Sum each of N per-lane values over the 32 lanes and leave ALL N totals in every lane.  Instead of N butterflies
+// (5 N shuffles) the first log2(N) steps are TRANSPOSED -- a lane keeps half of its values and hands the other half to
+// its partner -- so one value per lane is left for the remaining steps, and the totals are fetched back with one indexed
+// shuffle each: N-1 + (5 - log2 N) + N shuffles (N = 4: 10 instead of 20; N = 8: 17 instead of 40).
+template <int N>
+__device__ __forceinline__ void warp_allsum(float (&v)[N], int lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  int bit = 16;
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1, bit >>= 1) {
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? v[half + i] : v[i];
+      const float send = upper ? v[i] : v[half + i];
+      v[i] = keep + __shfl_xor_sync(kFull, send, bit);
+    }
+  }
+#pragma unroll
+  for (; bit >= 1; bit >>= 1) v[0] += __shfl_xor_sync(kFull, v[0], bit);
+  const float mine = v[0];
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    int src = 0, b = 16;
+#pragma unroll
+    for (int half = N / 2; half >= 1; half >>= 1, b >>= 1)
+      if (r & half) src |= b;
+    v[r] = __shfl_sync(kFull, mine, src);
+  }
 }
 
 struct FwdArgs {
@@ -186,10 +221,7 @@ __global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
         for (int k = 0; k < CE; ++k) sum += v[r][c][k];
       mean[r] = sum;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);     // R independent chains
+    warp_allsum<R>(mean, lane);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       mean[r] *= (1.f / D);
@@ -200,10 +232,7 @@ __global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
         for (int k = 0; k < CE; ++k) { const float t = v[r][c][k] - mean[r]; sq += t * t; }
       rstd[r] = sq;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int r = 0; r < R; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+    warp_allsum<R>(rstd, lane);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       rstd[r] = rsqrtf(rstd[r] * (1.f / D) + a.eps);
@@ -336,13 +365,12 @@ __global__ void __launch_bounds__(256) bwd_kernel(BwdArgs a) {
       }
     }
     if (FL::ln(a)) {
+      float both[2 * R];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+      for (int r = 0; r < R; ++r) { both[r] = s1[r]; both[R + r] = s2[r]; }
+      warp_allsum<2 * R>(both, lane);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {                 // 2R independent shuffle chains
-          s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
-          s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
-        }
+      for (int r = 0; r < R; ++r) { s1[r] = both[r]; s2[r] = both[R + r]; }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
