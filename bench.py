@@ -54,7 +54,8 @@ def parse_args():
     ap.add_argument('--mean-size', type=float, default=30.0)
     ap.add_argument('--graph', default='poisson', choices=['poisson', 'powerlaw'],
                     help='hyperedge sizes: 1+Poisson(mean-1) (configs 3, 4) or P(s)~s^-2 on [2,4096] with a forced 4096 (config 5)')
-    ap.add_argument('--d', type=int, default=128)
+    ap.add_argument('--d', '--width', dest='d', type=int, default=128,
+                    help='feature width (use --width under torchrun: its own parser treats --d as an ambiguous prefix)')
     ap.add_argument('--heads', type=int, default=8)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
     ap.add_argument('--seed', type=int, default=1234)
