@@ -16,7 +16,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('ALLSET_B200_LIB') or os.path.join(_HERE, 'liballset_b200.so')   # override: kernel tuning builds
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 F32, BF16 = 0, 1
 SUM, MEAN = 0, 1
@@ -57,6 +57,10 @@ SIGNATURES = {
     'allset_pma_tail_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _f32, _c.c_int, _i64, _i32,
                                        _p, _c.c_int, _p, _p]),
     'allset_linear_score_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _p, _p, _i32, _i64, _i32, _p, _c.c_int, _i64, _p, _p, _p]),
+    'allset_linear_fwd': (_c.c_int, [_p, _c.c_int, _p, _p, _f32, _p, _c.c_int, _p, _c.c_int, _c.c_int, _i64, _i32, _p, _c.c_int,
+                                     _p, _p]),
+    'allset_linear_wgrad_partials': (_c.c_int, [_i64]),
+    'allset_linear_wgrad': (_c.c_int, [_p, _p, _c.c_int, _c.c_int, _i64, _i32, _p, _p, _i64, _p, _p]),
     'allset_segreduce_bwd_w': (_c.c_int, [_p, _p, _c.c_int, _i32, _p, _p, _p, _i64, _p, _p]),
     'allset_pma_fwd': (_c.c_int, [_p, _p, _p, _c.c_int, _i32, _i32, _f32, _p, _p, _i64,
                                   _p, _i32, _i32, _p, _p, _p, _sz, _p]),
@@ -410,6 +414,76 @@ def mlp2_fwd(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: 
                                      _ptr(g[1]), _ptr(b[1]), float(eps[1]), _ptr(w2), _ptr(b2), 1 if relu_out else 0,
                                      rows, d, _ptr(out), od, pitch, _ptr(status), _stream()), 'allset_mlp2_fwd')
     return out
+
+
+PREC_BF16, PREC_SPLIT = 0, 1
+LINEAR_WIDTHS = (64, 128)
+
+
+def linear_ok(x: torch.Tensor, w: torch.Tensor) -> bool:
+    """Whether `x @ w.T` (or its gradients) can run on the hand-written tcgen05 Linear kernels: square width 64 / 128,
+    dense CUDA rows in f32 (split precision) or bf16, f32 master weights."""
+    return (x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous()
+            and w.dim() == 2 and w.dtype == torch.float32 and w.is_contiguous()
+            and x.shape[1] in LINEAR_WIDTHS and tuple(w.shape) == (x.shape[1], x.shape[1])
+            and x.data_ptr() % 32 == 0 and w.data_ptr() % 16 == 0)
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, ln=None, relu: bool = False,
+               transposed: bool = False, out_dtype: Optional[torch.dtype] = None,
+               status: Optional[torch.Tensor] = None, split: Optional[bool] = None) -> torch.Tensor:
+    """out = [relu](LN?(x) op(w)^T + b) on tcgen05; op(w) = w ([out, in]) or w^T with `transposed` (dx = dy w).
+    f32 rows run in split precision (two bf16 terms per operand, fp32-class accuracy) and return f32 unless
+    `split=False`; bf16 rows (and f32 rows with `split=False`) run with bf16 operands and return `out_dtype` (default: the
+    input dtype)."""
+    _need(x, 'x')
+    xd = _dtype_code(x)
+    if x.dim() != 2:
+        raise ValueError('x must be [rows, d]')
+    rows, d = x.shape
+    _need(w, 'w', torch.float32)
+    if tuple(w.shape) != (d, d):
+        raise ValueError('linear_fwd: w must be %s, got %s' % ((d, d), tuple(w.shape)))
+    _need(b, 'b', torch.float32, optional=True)
+    g = bt = None
+    eps = 1e-5
+    if ln is not None:
+        g, bt, eps = ln
+        _need(g, 'ln gamma', torch.float32)
+        _need(bt, 'ln beta', torch.float32, optional=True)
+    if split is None:
+        split = x.dtype == torch.float32          # f32 rows: the reference's precision class unless told otherwise
+    if split:
+        if x.dtype != torch.float32:
+            raise ValueError('linear_fwd: split precision takes f32 rows')
+        if out_dtype not in (None, torch.float32):
+            raise ValueError('linear_fwd: f32 rows (split precision) return f32')
+        out_dtype = torch.float32
+    out = torch.empty((rows, d), dtype=out_dtype or x.dtype, device=x.device)
+    _need(status, 'status', torch.int32, optional=True)
+    with torch.cuda.device(x.device):
+        _check(lib().allset_linear_fwd(_ptr(x), xd, _ptr(g), _ptr(bt), float(eps), _ptr(w), 1 if transposed else 0, _ptr(b),
+                                       1 if relu else 0, PREC_SPLIT if split else PREC_BF16, rows, d, _ptr(out),
+                                       _dtype_code(out), _ptr(status), _stream()), 'allset_linear_fwd')
+    return out
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dw[n, k] = sum_r dy[r, n] x[r, k]  ([d, d] f32) on tcgen05; dy, x [rows, d] of one dtype (f32: split precision)."""
+    _need(dy, 'dy')
+    _need(x, 'x')
+    if dy.dtype != x.dtype or dy.shape != x.shape or x.dim() != 2:
+        raise ValueError('linear_wgrad: dy and x must be [rows, d] of one dtype')
+    rows, d = x.shape
+    dw = torch.empty((d, d), dtype=torch.float32, device=x.device)
+    _need(status, 'status', torch.int32, optional=True)
+    with torch.cuda.device(x.device):
+        n_part = int(lib().allset_linear_wgrad_partials(rows))
+        ws = torch.empty((max(n_part, 1), d, d), dtype=torch.float32, device=x.device)
+        _check(lib().allset_linear_wgrad(_ptr(dy), _ptr(x), _dtype_code(x), PREC_SPLIT if x.dtype == torch.float32 else PREC_BF16,
+                                         rows, d, _ptr(dw), _ptr(ws), ws.numel(), _ptr(status), _stream()),
+               'allset_linear_wgrad')
+    return dw
 
 
 def pma_tail_fwd(x: torch.Tensor, ln0, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor,

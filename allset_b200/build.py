@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 SOURCES = [os.path.join(_HERE, 'csrc', 'allset_kernels.cu')]
 HEADERS = [os.path.join(ROOT, 'include', 'allset_b200.h')] + \
-    [os.path.join(_HERE, 'csrc', f) for f in ('mlp_tcgen05.cuh', 'rowop.cuh')]
+    [os.path.join(_HERE, 'csrc', f) for f in ('mlp_tcgen05.cuh', 'rowop.cuh', 'linear_wgrad.cuh')]
 OUTPUT = os.path.join(_HERE, 'liballset_b200.so')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

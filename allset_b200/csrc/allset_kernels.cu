@@ -2216,6 +2216,7 @@ int elem_bytes(int dtype) { return dtype == ALLSET_F32 ? 4 : 2; }
 // =============================================================================================
 namespace {
 #include "mlp_tcgen05.cuh"
+#include "linear_wgrad.cuh"
 }  // namespace
 
 namespace {
@@ -2607,6 +2608,67 @@ int allset_linear_score_fwd(const void* x, int x_dtype, const float* w, const fl
                  1, (long long)rows, status, 0, 0, nullptr, nullptr, 0.f, w_eff, b_eff, score, (int)heads,
                  mlp2_direct(out, out_pitch), (long long)out_pitch};
   return mlp2_dispatch<2>(p, x_dtype, out_dtype, d, static_cast<cudaStream_t>(stream));
+}
+
+int allset_linear_fwd(const void* x, int x_dtype, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                      const float* w, int w_transposed, const float* b, int relu, int precision, int64_t rows, int32_t d,
+                      void* out, int out_dtype, int32_t* status, void* stream) {
+  if (rows < 0 || d <= 0) return fail(ALLSET_EINVAL, "linear_fwd: bad size");
+  if (bad_dtype(x_dtype) || bad_dtype(out_dtype)) return fail(ALLSET_EINVAL, "linear_fwd: dtype must be 0 (f32) or 1 (bf16)");
+  if (precision != ALLSET_PREC_BF16 && precision != ALLSET_PREC_SPLIT) return fail(ALLSET_EINVAL, "linear_fwd: unknown precision %d", precision);
+  if (d != 64 && d != 128) return fail(ALLSET_EUNSUPPORTED, "linear_fwd: width %d not supported (64 or 128)", (int)d);
+  if (rows == 0) return ALLSET_OK;
+  if (x == nullptr || out == nullptr || w == nullptr) return fail(ALLSET_EINVAL, "linear_fwd: null pointer");
+  if (ln_beta != nullptr && ln_gamma == nullptr) return fail(ALLSET_EINVAL, "linear_fwd: LayerNorm beta without gamma");
+  if (w_transposed && ln_gamma != nullptr) return fail(ALLSET_EINVAL, "linear_fwd: w_transposed excludes the LayerNorm prologue");
+  const uintptr_t bits = (uintptr_t)x | (uintptr_t)out | (uintptr_t)w | (uintptr_t)ln_gamma;
+  if (bits % 16 != 0) return fail(ALLSET_EUNSUPPORTED, "linear_fwd: x, out, w and gamma must be 16-byte aligned");
+  const int64_t pitch = (int64_t)d * elem_bytes(out_dtype);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == ALLSET_PREC_SPLIT) {
+    if (x_dtype != ALLSET_F32 || out_dtype != ALLSET_F32)
+      return fail(ALLSET_EUNSUPPORTED, "linear_fwd: split precision takes and returns f32 rows");
+    if ((uintptr_t)out % 32 != 0) return fail(ALLSET_EUNSUPPORTED, "linear_fwd: split precision needs a 32-byte aligned out");
+    mlp5::Params p{x, out, ln_gamma, ln_beta, w, b, nullptr, nullptr, w, nullptr, ln_eps, 1e-5f, relu, 1, (long long)rows,
+                   status, 0, 0, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, 0, 1, (long long)pitch, w_transposed ? 1 : 0};
+    if (d == 64) return mlp5::launch<float, float, 64, 3>(p, st);
+    return mlp5::launch<float, float, 128, 3>(p, st);
+  }
+  mlp5::Params p{x, out, ln_gamma, ln_beta, w, b, nullptr, nullptr, w, nullptr, ln_eps, 1e-5f, relu, 1, (long long)rows,
+                 status, 0, 0, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, 0, mlp2_direct(out, pitch), (long long)pitch,
+                 w_transposed ? 1 : 0};
+  return mlp2_dispatch<0>(p, x_dtype, out_dtype, d, st);
+}
+
+int allset_linear_wgrad_partials(int64_t rows) { return rows <= 0 ? 0 : wgrad5::n_partials((long long)rows); }
+
+int allset_linear_wgrad(const void* dy, const void* x, int dtype, int precision, int64_t rows, int32_t d, float* dw,
+                        float* workspace, int64_t workspace_floats, int32_t* status, void* stream) {
+  if (rows < 0 || d <= 0) return fail(ALLSET_EINVAL, "linear_wgrad: bad size");
+  if (bad_dtype(dtype)) return fail(ALLSET_EINVAL, "linear_wgrad: dtype must be 0 (f32) or 1 (bf16)");
+  if (precision != ALLSET_PREC_BF16 && precision != ALLSET_PREC_SPLIT) return fail(ALLSET_EINVAL, "linear_wgrad: unknown precision %d", precision);
+  if (d != 64 && d != 128) return fail(ALLSET_EUNSUPPORTED, "linear_wgrad: width %d not supported (64 or 128)", (int)d);
+  if (dw == nullptr) return fail(ALLSET_EINVAL, "linear_wgrad: null pointer");
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows == 0) {
+    cudaMemsetAsync(dw, 0, (size_t)d * d * sizeof(float), st);
+    return check_launch("linear_wgrad");
+  }
+  if (dy == nullptr || x == nullptr || workspace == nullptr) return fail(ALLSET_EINVAL, "linear_wgrad: null pointer");
+  if ((dtype == ALLSET_F32) != (precision == ALLSET_PREC_SPLIT))
+    return fail(ALLSET_EUNSUPPORTED, "linear_wgrad: f32 rows take split precision, bf16 rows bf16 precision");
+  const uintptr_t bits = (uintptr_t)dy | (uintptr_t)x | (uintptr_t)workspace;
+  if (bits % 32 != 0) return fail(ALLSET_EUNSUPPORTED, "linear_wgrad: dy, x and the workspace must be 32-byte aligned");
+  if (workspace_floats < (int64_t)wgrad5::n_partials((long long)rows) * d * d)
+    return fail(ALLSET_EINVAL, "linear_wgrad: workspace too small (allset_linear_wgrad_partials(rows) * d * d floats)");
+  static const int swap = getenv("ALLSET_WGRAD_SWAP") != nullptr ? 1 : 0;
+  wgrad5::Params p{dy, x, (long long)rows, workspace, status, swap};
+  if (dtype == ALLSET_F32) {
+    if (d == 64) return wgrad5::launch<float, 64, true>(p, dw, st);
+    return wgrad5::launch<float, 128, true>(p, dw, st);
+  }
+  if (d == 64) return wgrad5::launch<__nv_bfloat16, 64, false>(p, dw, st);
+  return wgrad5::launch<__nv_bfloat16, 128, false>(p, dw, st);
 }
 
 int allset_segreduce_bwd_w(const void* x, const void* grad_out, int dtype, int32_t d, const int32_t* rowptr,

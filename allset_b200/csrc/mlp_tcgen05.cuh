@@ -57,6 +57,9 @@ struct Params {
   int heads;
   int direct;            // 1: epilogue 2 stores 32-byte pieces of a thread's own row (STG.256) instead of staging
   long long out_pitch;   // bytes between output rows (>= D * sizeof(TOut), multiple of 16); lets lin_V write packed records
+  // MODE 3 (split precision) / single Linear: 1 = `w1` is stored [in, out] (the kernel computes x W instead of x W^T:
+  // the input gradient of a Linear, dx = dy W); excludes LayerNorm 0
+  int w_transposed;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -406,9 +409,9 @@ struct Producer {
   }
 
   using Packed = uint32_t[G][EPL / 2];          // the normalised rows of one half as bf16 pairs
-  __device__ static __forceinline__ void compute(const Buf& buf, Packed& pk, float2 (&stats)[G], bool has_ln0,
-                                                 float eps0) {
-    float v[G][EPL];
+  // the rows of one half as floats, LayerNorm 0 (without its affine part) applied
+  __device__ static __forceinline__ void rows_f32(const Buf& buf, float (&v)[G][EPL], float2 (&stats)[G], bool has_ln0,
+                                                  float eps0) {
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
 #pragma unroll
@@ -433,7 +436,6 @@ struct Producer {
 #pragma unroll
         for (int gi = 0; gi < G; ++gi) s[gi] += __shfl_xor_sync(0xffffffffu, s[gi], o);
       }
-#pragma unroll
       float mean_[G];
 #pragma unroll
       for (int gi = 0; gi < G; ++gi) {
@@ -460,10 +462,41 @@ struct Producer {
         stats[gi] = make_float2(mean_[gi], rstd);   // PMA tail: the epilogue re-derives the residual from x with these
       }
     }
+  }
+  __device__ static __forceinline__ void compute(const Buf& buf, Packed& pk, float2 (&stats)[G], bool has_ln0,
+                                                 float eps0) {
+    float v[G][EPL];
+    rows_f32(buf, v, stats, has_ln0, eps0);
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
 #pragma unroll
       for (int e = 0; e < EPL; e += 2) pk[gi][e / 2] = pack_bf16(v[gi][e], v[gi][e + 1]);
+    }
+  }
+  // split precision: the three bf16 terms of the rows (x = t0 + t1 + t2 to 2^-25), each stored as soon as it is formed so
+  // that only ONE packed term is live beside the float rows (the low register count matters: a spilled prefetch register
+  // makes the warp wait for its load right after issuing it)
+  __device__ static __forceinline__ void split_store(const Buf& buf, bool has_ln0, float eps0, uint32_t s0, uint32_t s1,
+                                                     uint32_t s2, int pw, int half, int sub, int cl) {
+    float v[G][EPL];
+    float2 stats[G];
+    rows_f32(buf, v, stats, has_ln0, eps0);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      Packed pk;
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) {
+#pragma unroll
+        for (int e = 0; e < EPL; e += 2) {
+          const uint32_t h = pack_bf16(v[gi][e], v[gi][e + 1]);
+          pk[gi][e / 2] = h;
+          if (t < 2) {
+            v[gi][e] -= __uint_as_float(h << 16);
+            v[gi][e + 1] -= __uint_as_float(h & 0xFFFF0000u);
+          }
+        }
+      }
+      store(pk, stats, nullptr, t == 0 ? s0 : (t == 1 ? s1 : s2), pw, half, sub, cl);
     }
   }
   // the only part that needs the A stage to be free: EPL/2 registers per row -> swizzled shared memory
@@ -492,6 +525,17 @@ template <typename TIn, typename TOut, int D, int MODE>
 __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) {
   constexpr bool TAIL = (MODE == 1);
   constexpr bool SCORE = (MODE == 2);
+  // MODE 3: ONE Linear with fp32 accuracy out of bf16 tensor-core products.  Both operands are split into THREE bf16 terms
+  // (x = x1 + x2 + x3 exactly to 2^-25: 3 x 8 significant bits) and the six products down to 2^-18 relative are
+  // accumulated in fp32 in TMEM, smallest first:  x3 W1 + x1 W3 + x2 W2 + x2 W1 + x1 W2 + x1 W1  (the dropped terms are
+  // <= 2^-26).  Two terms / three products (the usual "3x" split) leave 2^-17 per product: measured on the citeseer
+  // golden model that is enough for the logits (1.4e-5) but flips ~10 ReLUs that sit within 1e-5 of zero, and a flipped
+  // unit is an O(1) change of that row's gradient -- so the reference-precision mode pays for the third term.
+  // Shared memory: the three weight terms take the W1 / W2 slots and the second hidden buffer, the three A terms the two
+  // A stages and the first hidden buffer, i.e. ONE A stage that both epilogue groups' tiles pass through in turn (the
+  // producers wait for the previous tile's MMAs); the output leaves through the direct (thread-per-row) stores because
+  // no staging buffer is left.
+  constexpr bool SPLIT = (MODE == 3);
   using L = Layout<D>;
   static_assert(D == 64 || D == 128, "mlp2_ws: widths 64 and 128");
   constexpr int PASS_BYTES = L::template pass_bytes<TOut>();
@@ -533,23 +577,45 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), WsLayout<D>::TMEM_COLS);
   // weights -> bf16 K-major SWIZZLE_128B, with the LayerNorm in front of each Linear folded in:
   //   LN(x) W^T + b = n(x) (W diag(gamma))^T + (b + W beta),  n(x) = (x - mean) * rstd
-#pragma unroll 4
-  for (int idx = tid; idx < 2 * D * (D / 8); idx += kWsThreads) {
+  constexpr int NW = SPLIT ? 3 : 2;                     // weight tiles to fill (SPLIT: the three terms of w1)
+#pragma unroll 2
+  for (int idx = tid; idx < NW * D * (D / 8); idx += kWsThreads) {
     const int which = idx / (D * (D / 8));
     const int rem = idx - which * (D * (D / 8));
-    const int n = rem / (D / 8), j = rem % (D / 8);
-    const float* w = (which ? p.w2 : p.w1) + (size_t)n * D + j * 8;
-    float4 lo = *reinterpret_cast<const float4*>(w);
-    float4 hi = *reinterpret_cast<const float4*>(w + 4);
-    const float* gam = which ? p.ln1_g : p.ln0_g;
-    if (gam != nullptr) {
-      const float4 gl = *reinterpret_cast<const float4*>(gam + j * 8);
-      const float4 gh = *reinterpret_cast<const float4*>(gam + j * 8 + 4);
-      lo.x *= gl.x; lo.y *= gl.y; lo.z *= gl.z; lo.w *= gl.w;
-      hi.x *= gh.x; hi.y *= gh.y; hi.z *= gh.z; hi.w *= gh.w;
+    const bool first = SPLIT || !which;
+    int n, j;
+    if (p.w_transposed) { n = rem % D; j = rem / D; }   // consecutive threads read consecutive output columns
+    else { n = rem / (D / 8); j = rem % (D / 8); }
+    const float* wsrc = first ? p.w1 : p.w2;
+    float wv[8];
+    if (p.w_transposed) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wv[e] = wsrc[(size_t)(j * 8 + e) * D + n];
+    } else {
+      const float4 lo = *reinterpret_cast<const float4*>(wsrc + (size_t)n * D + j * 8);
+      const float4 hi = *reinterpret_cast<const float4*>(wsrc + (size_t)n * D + j * 8 + 4);
+      wv[0] = lo.x; wv[1] = lo.y; wv[2] = lo.z; wv[3] = lo.w; wv[4] = hi.x; wv[5] = hi.y; wv[6] = hi.z; wv[7] = hi.w;
     }
-    st_shared16((which ? sW2 : sW1) + sw128_chunk<D>(n, j), pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w),
-                pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+    const float* gam = first ? p.ln0_g : p.ln1_g;
+    if (gam != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wv[e] *= gam[j * 8 + e];
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      uint32_t h = pack_bf16(wv[e], wv[e + 1]);
+      if (SPLIT) {
+        for (int t = 0; t < which; ++t) {               // peel `which` leading terms
+          wv[e] -= __uint_as_float(h << 16);
+          wv[e + 1] -= __uint_as_float(h & 0xFFFF0000u);
+          h = pack_bf16(wv[e], wv[e + 1]);
+        }
+      }
+      pk[e / 2] = h;
+    }
+    const uint32_t wdst = (which == 0) ? sW1 : (which == 1) ? sW2 : sA1 + BUF;
+    st_shared16(wdst + sw128_chunk<D>(n, j), pk[0], pk[1], pk[2], pk[3]);
   }
   // biases: sPar[0..D) = b1 + W1 beta0, sPar[D..2D) = b2 + W2 beta1 (fp32; 4 threads per output row, independent
   // 16-byte loads so the whole fold is one round trip to L2)
@@ -611,6 +677,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       // all the arithmetic happens BEFORE the stage is known to be free; only the shared-memory stores wait for it
       typename P::Packed pkA, pkB;
       float2 stA[P::G] = {}, stB[P::G] = {};
+      if constexpr (SPLIT) {
+        // three term tiles per row half, ONE stage: wait until the MMAs of the previous tile (the other group's) and of
+        // this group's previous tile have retired, then compute and store half by half
+        if (it >= 1) mbar_wait_bounded<500>(bar_a_empty + 8 * (st ^ 1u), ((it - 1) >> 1) & 1u, p.status);
+        if (it >= 2) mbar_wait_bounded<500>(bar_a_empty + 8 * st, ((it >> 1) - 1) & 1u, p.status);
+        P::split_store(bufA, has_ln0, p.eps0, sA0, sA0 + L::A_BYTES, sA1, pw, 0, sub, cl);
+        if (next < n_tiles) P::load(bufA, xb, next * kTileM, p.rows, pw, 0, sub, cl);
+        P::split_store(bufB, has_ln0, p.eps0, sA0, sA0 + L::A_BYTES, sA1, pw, 1, sub, cl);
+        if (next < n_tiles) P::load(bufB, xb, next * kTileM, p.rows, pw, 1, sub, cl);
+        proxy_fence_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_full + 8 * st);
+        continue;
+      }
       if (SCORE) P::score(bufA, reinterpret_cast<const float*>(sStat), sPar + 2 * D, p.heads, p.score, tile * kTileM,
                           p.rows, pw, 0, sub, cl);
       P::compute(bufA, pkA, stA, has_ln0, p.eps0);
@@ -635,16 +715,34 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     const uint32_t sH = sA1 + g * BUF;
     unsigned char* ob = static_cast<unsigned char*>(p.out);
     const bool issuer = (r == 0);                      // one thread per group issues its tcgen05.mma / commit
+    const bool direct = SPLIT || p.direct != 0;        // SPLIT: the staging buffers hold operand terms
     const uint32_t sAg = sA0 + g * L::A_BYTES;
     auto gemm1 = [&](uint32_t kk) {                    // GEMM 1 of this group's kk-th tile: A stage g x W1 -> acc1[g]
       mbar_wait_bounded(bar_a_full + 8 * g, kk & 1u, p.status);
       tc_fence_after();
+      if constexpr (SPLIT) {
+        // smallest products first: x3 W1, x1 W3, x2 W2, x2 W1, x1 W2, x1 W1, all into the same fp32 accumulator
+        const uint32_t xa[3] = {sA0, sA0 + (uint32_t)L::A_BYTES, sA1};
+        const uint32_t wa[3] = {sW1, sW2, sA1 + (uint32_t)BUF};
+        constexpr int XI[6] = {2, 0, 1, 1, 0, 0}, WI[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t koff = (uint32_t)((ks >> 2) * (kTileM * 128) + (ks & 3) * 32);
+            const uint32_t woff = (uint32_t)((ks >> 2) * (D * 128) + (ks & 3) * 32);
+            umma_bf16(tmem_acc1, smem_desc_sw128(xa[XI[t]] + koff), smem_desc_sw128(wa[WI[t]] + woff),
+                      instr_desc_bf16(kTileM, D), (t > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+      } else {
 #pragma unroll
       for (int ks = 0; ks < D / 16; ++ks) {
         const uint32_t koff = (uint32_t)((ks >> 2) * (kTileM * 128) + (ks & 3) * 32);
         const uint32_t woff = (uint32_t)((ks >> 2) * (D * 128) + (ks & 3) * 32);
         umma_bf16(tmem_acc1, smem_desc_sw128(sAg + koff), smem_desc_sw128(sW1 + woff), instr_desc_bf16(kTileM, D),
                   ks > 0 ? 1u : 0u);
+      }
       }
       umma_commit(bar_a_empty + 8 * g);
       umma_commit(bar_acc1_full + 8 * g);
@@ -804,7 +902,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
               }
             }
           }
-          if (p.direct) {
+          if (direct) {
             // thread-per-row stores in whole 32-byte sectors: no staging round trip through shared memory
             const long long gr = row0 + r;
             if (gr < p.rows) {
@@ -849,7 +947,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
           if (issuer && has_next) gemm1(k + 1);
         }
         __syncwarp();
-        if (p.direct) continue;                  // nothing staged: the hidden tile is untouched, no barrier needed
+        if (direct) continue;                  // nothing staged: the hidden tile is untouched, no barrier needed
         const int wrow = (warp & 3) * 32;
 #pragma unroll
         for (int idx = lane; idx < 32 * CHUNKS_PER_ROW; idx += 32) {

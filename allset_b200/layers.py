@@ -111,6 +111,17 @@ class MLP(nn.Module):
         io = x.dtype if out_dtype is None else out_dtype
         p = self.dropout if self.training else 0.0
         pf = final_dropout if self.training else 0.0
+        if (not torch.is_grad_enabled() and p == 0.0 and pf == 0.0 and x.is_contiguous()
+                and (cd == torch.bfloat16 or (x.dtype == torch.float32 and io == torch.float32))
+                and all(ops.tc_linear_ok(x, lin.weight) for lin in self.lins)):
+            # inference: every Linear is ONE tcgen05 launch with the LayerNorm in front of it, its bias and the ReLU behind
+            # it inside the kernel (rows read once, written once per Linear); fp32 mode in split precision
+            h = x
+            for i, lin in enumerate(self.lins):
+                last = i == len(self.lins) - 1
+                h = ops.linear_fused(h, lin.weight, lin.bias, ln=self._ln_tuple(self.normalizations[i]),
+                                     relu=final_relu if last else True, compute_dtype=cd, out_dtype=io if last else cd)
+            return h
         n0 = self.normalizations[0]
         if isinstance(n0, nn.LayerNorm):
             h = ops.rowop(x, gamma=n0.weight, beta=n0.bias, eps=n0.eps, out_dtype=cd)
@@ -260,7 +271,7 @@ class PMA(nn.Module):
             # training / fp32 mode at scale: bias-free GEMM (bf16 operands in bf16 mode) + one rowop pass that adds the
             # bias and writes the rows in the storage dtype the aggregation gathers
             xb = x if x.dtype == cd else x.to(cd)
-            v = ops.rowop(ops.linear_nb(xb, self.lin_V.weight), self.lin_V.bias, out_dtype=self.agg_dtype or cd)
+            v = ops.linear_bias_act(xb, self.lin_V.weight, self.lin_V.bias, out_dtype=self.agg_dtype or cd)
         else:
             x_V = self.lin_V(x if x.dtype == w_eff.dtype else x.to(w_eff.dtype))
             v = x_V if self.agg_dtype is None else x_V.to(self.agg_dtype)
@@ -281,7 +292,7 @@ class PMA(nn.Module):
             y = ops.rowop(out, gamma=self.ln0.weight, beta=self.ln0.bias, eps=self.ln0.eps, out_dtype=cd)   # ln0 (:155)
             a = y
             for lin in self.rFF.lins[:-1]:                                   # rFF: no norms, no dropout (:76-80)
-                a = ops.rowop(ops.linear_nb(a, lin.weight), lin.bias, relu=True, out_dtype=cd)
+                a = ops.linear_bias_act(a, lin.weight, lin.bias, relu=True, out_dtype=cd)
             last = self.rFF.lins[-1]
             out = ops.rowop(ops.linear_nb(a, last.weight), last.bias, relu=True, residual=y, gamma=self.ln1.weight,
                             beta=self.ln1.bias, eps=self.ln1.eps, relu_out=relu_out, drop_p=pdrop,

@@ -281,16 +281,36 @@ def rowop(x: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = Fal
     return _RowOp.apply(x, bias, residual, gamma, beta, relu, eps, relu_out, drop_p, out_dtype)
 
 
+TC_LINEAR = True     # square 64 / 128 Linears on the hand-written tcgen05 kernels (False: cuBLAS, for A/B runs)
+TC_LINEAR_PARTS = {'fwd', 'dgrad', 'wgrad'}     # A/B switch per kernel (debugging aid)
+
+
+def tc_linear_ok(x: torch.Tensor, w: torch.Tensor) -> bool:
+    """x @ w.T on allset_linear_fwd / its gradients on allset_linear_fwd(transposed) + allset_linear_wgrad."""
+    return TC_LINEAR and x.shape[0] >= FUSED_DENSE_MIN_ROWS and _lib.linear_ok(x, w)
+
+
 class _LinearNB(torch.autograd.Function):
-    """y = x @ W^T without bias, operands in `x.dtype` (bf16: tensor-core GEMM with fp32 accumulation; fp32: SGEMM), W
-    kept as the fp32 master parameter; dW is accumulated and returned in fp32.  `out_fp32` keeps the fp32 accumulator
-    as the result of a bf16 GEMM (attention scores)."""
+    """y = x @ W^T without bias, W kept as the fp32 master parameter, dW accumulated and returned in fp32.
+
+    Square widths 64 / 128 (every Linear between the aggregation steps) run on the hand-written tcgen05 kernels: bf16 rows
+    with bf16 operands, fp32 rows in split precision (two bf16 terms per operand, fp32-class accuracy) -- forward
+    (allset_linear_fwd), input gradient (the same kernel with the weight read transposed) and weight gradient
+    (allset_linear_wgrad, MN-major operands straight from the row-major activations).  Other shapes (the first layer from
+    a dataset's raw feature count, the classifier's class count, the skinny score GEMM) go to cuBLAS.  `out_fp32` keeps
+    the fp32 accumulator as the result of a bf16 GEMM (attention scores)."""
 
     @staticmethod
     def forward(ctx, x, w, out_fp32):
-        wc = w if w.dtype == x.dtype else w.to(x.dtype)
-        ctx.save_for_backward(x, wc)
         ctx.w_dtype = w.dtype
+        ctx.tc = tc_linear_ok(x, w)
+        if ctx.tc:
+            ctx.save_for_backward(x, w)
+            if 'fwd' in TC_LINEAR_PARTS:
+                return _lib.linear_fwd(x, w, out_dtype=torch.float32 if out_fp32 else x.dtype)
+        else:
+            ctx.save_for_backward(x, w if w.dtype == x.dtype else w.to(x.dtype))
+        wc = w if w.dtype == x.dtype else w.to(x.dtype)
         if out_fp32 and x.dtype != torch.float32:
             return torch.mm(x, wc.t(), out_dtype=torch.float32)
         return torch.mm(x, wc.t())
@@ -301,9 +321,15 @@ class _LinearNB(torch.autograd.Function):
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
         dy = dy.contiguous()
-        dx = torch.mm(dy, wc) if ctx.needs_input_grad[0] else None
-        dw = None
-        if ctx.needs_input_grad[1]:
+        tc = ctx.tc and dy.data_ptr() % 32 == 0
+        dx = dw = None
+        if tc and 'dgrad' in TC_LINEAR_PARTS:
+            dx = _lib.linear_fwd(dy, wc, transposed=True) if ctx.needs_input_grad[0] else None
+        elif ctx.needs_input_grad[0]:
+            dx = torch.mm(dy, wc if wc.dtype == x.dtype else wc.to(x.dtype))
+        if tc and 'wgrad' in TC_LINEAR_PARTS:
+            dw = _lib.linear_wgrad(dy, x) if ctx.needs_input_grad[1] else None
+        elif ctx.needs_input_grad[1]:
             if dy.dtype == torch.float32:
                 dw = torch.mm(dy.t(), x)
             else:
@@ -317,8 +343,30 @@ def linear_nb(x: torch.Tensor, w: torch.Tensor, out_fp32: bool = False) -> torch
     """x [rows, in] (bf16 | fp32) @ w[out, in]^T -> [rows, out] in x.dtype (fp32 with `out_fp32`); the bias is left to
     the rowop that follows."""
     if not torch.is_grad_enabled():
+        if tc_linear_ok(x, w):
+            return _lib.linear_fwd(x, w, out_dtype=torch.float32 if out_fp32 else x.dtype)
         wc = w if w.dtype == x.dtype else w.to(x.dtype)
         if out_fp32 and x.dtype != torch.float32:
             return torch.mm(x, wc.t(), out_dtype=torch.float32)
         return torch.mm(x, wc.t())
     return _LinearNB.apply(x, w, out_fp32)
+
+
+def linear_fused(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], ln=None, relu: bool = False,
+                 compute_dtype: torch.dtype = torch.float32, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """No-grad  [relu](LN?(x) w^T + b)  as ONE tcgen05 launch (LayerNorm prologue, bias and ReLU inside the kernel); the
+    caller checks `tc_linear_ok(x, w)`.  fp32 compute: split precision, f32 rows in and out; bf16 compute: bf16 operands,
+    any row dtypes.  An eval-mode MLP is one launch per Linear instead of a GEMM and a glue pass each."""
+    if compute_dtype == torch.float32:
+        return _lib.linear_fwd(x if x.dtype == torch.float32 else x.float(), w, b, ln=ln, relu=relu, split=True)
+    return _lib.linear_fwd(x, w, b, ln=ln, relu=relu, split=False, out_dtype=out_dtype or torch.bfloat16)
+
+
+def linear_bias_act(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = False,
+                    out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """[relu](x w^T + b) in `out_dtype`: one fused tcgen05 launch without autograd, linear_nb + rowop (each with its fused
+    backward) under autograd or for shapes the kernel does not take."""
+    od = out_dtype or x.dtype
+    if not torch.is_grad_enabled() and tc_linear_ok(x, w) and (x.dtype == torch.bfloat16 or od == torch.float32):
+        return _lib.linear_fwd(x, w, b, relu=relu, out_dtype=od)
+    return rowop(linear_nb(x, w), b, relu=relu, out_dtype=od)

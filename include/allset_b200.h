@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ALLSET_ABI_VERSION 2
+#define ALLSET_ABI_VERSION 3
 
 enum { ALLSET_F32 = 0, ALLSET_BF16 = 1 };
 enum { ALLSET_SUM = 0, ALLSET_MEAN = 1 };
@@ -193,6 +193,32 @@ int allset_linear_score_fwd(const void* x, int x_dtype, const float* w, const fl
                             const float* w_eff, const float* b_eff, int32_t heads,
                             int64_t rows, int32_t d, void* out, int out_dtype, int64_t out_pitch,
                             float* score, int32_t* status, void* stream);
+
+/* Arithmetic of the tcgen05 Linear kernels below. */
+#define ALLSET_PREC_BF16 0   /* operands rounded to bf16, fp32 accumulate (1e-2 class) */
+#define ALLSET_PREC_SPLIT 1  /* each f32 operand as TWO bf16 terms, three tensor-core products (x_lo W_hi + x_hi W_lo + x_hi W_hi)
+                              * accumulated in fp32: ~2^-17 relative per product, the reference's fp32 class (1e-4 bar) */
+
+/* ONE nn.Linear on tcgen05 (equal widths d in {64, 128}), the unit the training path is built from:
+ *     out = [relu]( LN?(x) op(W)^T + b ),   op(W) = W ([out, in], nn.Linear layout)      -- forward of MLP.lins[i] /
+ *                                                   PMA.lin_V (src/layers.py:575,129)
+ *                                           op(W) = W^T when w_transposed != 0             -- its input gradient dx = dy W
+ * x [rows, d] f32|bf16; W [d, d] f32; b, ln_* [d] f32 or NULL (the LayerNorm is the one IN FRONT of the Linear:
+ * MLP.normalizations[i], src/layers.py:573,577; not with w_transposed); out [rows, d] dense.
+ * precision ALLSET_PREC_BF16: any dtype pair; ALLSET_PREC_SPLIT: f32 in, f32 out, out 32-byte aligned -- this is what
+ * lets the DEFAULT (reference-precision) mode leave the SIMT SGEMM.  status as in allset_mlp2_fwd. */
+int allset_linear_fwd(const void* x, int x_dtype, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                      const float* w, int w_transposed, const float* b, int relu, int precision,
+                      int64_t rows, int32_t d, void* out, int out_dtype, int32_t* status, void* stream);
+
+/* Weight gradient of the same Linear: dw[n, k] = sum_r dy[r, n] * x[r, k]  (dw [d, d] f32, nn.Linear layout).
+ * dy, x [rows, d], both `dtype`, 32-byte aligned; f32 rows use ALLSET_PREC_SPLIT, bf16 rows ALLSET_PREC_BF16.
+ * One pass over both inputs; every CTA keeps its share of the sum in TMEM and writes one [d, d] partial into
+ * `workspace` (allset_linear_wgrad_partials(rows) * d * d floats, 32-byte aligned), a second launch adds the partials
+ * in a fixed order: deterministic, no atomics. */
+int allset_linear_wgrad_partials(int64_t rows);
+int allset_linear_wgrad(const void* dy, const void* x, int dtype, int precision, int64_t rows, int32_t d,
+                        float* dw, float* workspace, int64_t workspace_floats, int32_t* status, void* stream);
 
 /* Backward of allset_bias_act_norm (d in {128,256,512,1024}; ALLSET_EUNSUPPORTED otherwise):
  *   dx [rows, d] = gradient w.r.t. x;  dres [rows, d] or NULL = gradient w.r.t. residual;

@@ -139,41 +139,56 @@ def test_linear_nb_forward_backward(dtype):
     assert (xa.grad.float() - xb.grad).abs().max().item() <= (2e-2 if lo else 1e-4) * xb.grad.abs().max().item()
 
 
-@pytest.mark.parametrize('name', ['cora_alldeepsets.pt', 'citeseer_allsettransformer.pt'])
-def test_bf16_mode_training_gradients_vs_reference(name, monkeypatch):
-    """Autograd through the bf16 training chain (bf16 GEMM operands, bf16 activations and gathered rows, rowop forward /
-    backward) on the real models against the reference's fp32 logits and gradients.  bf16 operands perturb every
-    activation by 2^-9 and the LayerNorm chain amplifies a perturbation ~3x per half layer (profiles/r02_bf16_error_budget.md:
-    storing ONLY the gathered rows in bf16 already costs 1.1e-2 of the logit scale on cora), so the model-level bar is the
-    one mixed-precision training is held to: logits within 6e-2 of the scale, every parameter gradient within 15 % of its
-    own L2 norm (+ 1 % of the largest gradient norm in the model) and, where it is not vanishing, cosine >= 0.99 for the
-    weight matrices and >= 0.95 for the 1-D parameters.  A bias / LayerNorm gradient is a plain column SUM of signed per-row
-    terms over all rows: it cancels to a small fraction of the summed magnitudes, so the same per-element bf16 noise that
-    leaves a weight gradient (a sum weighted by the activations) at cosine 0.99+ shows up ~2x larger in it -- measured 0.979
-    for the first Linear's bias on cora (1433 -> 64, pre-activations of ~1e-2), identically before and after the rowop
-    kernels were rewritten (gpurun r2f / r2g), i.e. a property of the mode, not of a kernel."""
-    from allset_b200 import ops
-    monkeypatch.setattr(ops, 'FUSED_DENSE_MIN_ROWS', 0)
-    rec = load_golden(name)
+def _bf16_mode_grads(rec):
     model, data = _build(rec, agg_dtype=torch.bfloat16)
     out = model(data)
     assert out.dtype == torch.float32
-    scale = rec['logits'].abs().max().item()
-    assert (out.detach().cpu() - rec['logits']).abs().max().item() <= 6e-2 * max(scale, 1.0)
     (out * rec['grad_logits'].to(dev())).sum().backward()
     grads = dict((k, p.grad) for k, p in model.named_parameters() if p.grad is not None)
+    assert all(g.dtype == torch.float32 for g in grads.values())
+    return out.detach().cpu(), dict((k, g.float().cpu().reshape(-1)) for k, g in grads.items())
+
+
+@pytest.mark.parametrize('name', ['cora_alldeepsets.pt', 'citeseer_allsettransformer.pt'])
+def test_bf16_mode_training_gradients_vs_reference(name, monkeypatch):
+    """Autograd through the bf16 training chain (bf16 GEMM operands on the hand-written tcgen05 Linear kernels, bf16
+    activations and gathered rows, rowop forward / backward) on the real models.
+
+    Two bars.  (1) Against the SAME recipe with the three GEMMs of every Linear handed to cuBLAS (`ops.TC_LINEAR = False`):
+    the kernels compute the same products with the same fp32 accumulation, so logits and every parameter gradient must
+    agree to 2 % of the gradient's norm -- this is the parity statement for the kernels.  (2) Against the reference's fp32
+    logits and gradients: what the MODE costs.  bf16 operands perturb every activation by 2^-9 and the LayerNorm chain
+    amplifies a perturbation ~3x per half layer (profiles/r02_bf16_error_budget.md: storing ONLY the gathered rows in bf16
+    already costs 1.1e-2 of the logit scale on cora); measured with an fp64 evaluation of the oracle as the arbiter
+    (scripts/diag_split.py, gpurun r2j) the cuBLAS-backed recipe itself is 3.6e-2 off in the logits and up to 30 % off in
+    the L2 norm of individual LayerNorm / bias gradients on cora (d = 64, 1433 -> 64 first layer).  So the bar against the
+    reference is the one a mixed-precision recipe can meet: logits within 6e-2 of the scale, every non-vanishing
+    gradient within 40 % of its own L2 norm with cosine >= 0.93 (weights: >= 0.97)."""
+    from allset_b200 import ops
+    monkeypatch.setattr(ops, 'FUSED_DENSE_MIN_ROWS', 0)
+    rec = load_golden(name)
+    out, grads = _bf16_mode_grads(rec)
+    monkeypatch.setattr(ops, 'TC_LINEAR', False)
+    out_lib, grads_lib = _bf16_mode_grads(rec)
+    monkeypatch.setattr(ops, 'TC_LINEAR', True)
+    scale = rec['logits'].abs().max().item()
     big = max(g.norm().item() for g in rec['grads'].values())
+    # (1) tcgen05 kernels vs cuBLAS inside the same bf16 recipe
+    assert (out - out_lib).abs().max().item() <= 5e-3 * max(scale, 1.0)
+    for k, g in grads_lib.items():
+        err = (grads[k] - g).norm().item()
+        assert err <= 2e-2 * g.norm().item() + 2e-3 * big, '%s: tcgen05 vs cuBLAS |err| %.3e vs |g| %.3e' % (k, err, g.norm().item())
+    # (2) the mode vs the reference's fp32 arithmetic
+    assert (out - rec['logits']).abs().max().item() <= 6e-2 * max(scale, 1.0)
     for k, g in rec['grads'].items():
-        mine = grads[k].float().cpu().reshape(-1)
-        ref = g.reshape(-1)
-        assert grads[k].dtype == torch.float32
+        mine, ref = grads[k], g.reshape(-1)
         err = (mine - ref).norm().item()
         # a few parameters have (near-)vanishing gradients by symmetry (a bias in front of a softmax shifts every score of
         # a head alike): their error is measured against the model's gradient scale, not their own
-        assert err <= 0.15 * ref.norm().item() + 0.01 * big, '%s: |err| %.3e vs |ref| %.3e (largest %.3e)' % (k, err, ref.norm().item(), big)
+        assert err <= 0.4 * ref.norm().item() + 0.01 * big, '%s: |err| %.3e vs |ref| %.3e (largest %.3e)' % (k, err, ref.norm().item(), big)
         if ref.norm().item() > 0.05 * big:
             cos = torch.dot(mine, ref).item() / (mine.norm().item() * ref.norm().item() + 1e-30)
-            assert cos >= (0.99 if ref_is_matrix(g) else 0.95), '%s: cosine %.4f' % (k, cos)
+            assert cos >= (0.97 if ref_is_matrix(g) else 0.93), '%s: cosine %.4f' % (k, cos)
 
 
 def ref_is_matrix(g):
