@@ -473,30 +473,43 @@ struct Producer {
       for (int e = 0; e < EPL; e += 2) pk[gi][e / 2] = pack_bf16(v[gi][e], v[gi][e + 1]);
     }
   }
-  // split precision: the three bf16 terms of the rows (x = t0 + t1 + t2 to 2^-25), each stored as soon as it is formed so
-  // that only ONE packed term is live beside the float rows (the low register count matters: a spilled prefetch register
-  // makes the warp wait for its load right after issuing it)
-  __device__ static __forceinline__ void split_store(const Buf& buf, bool has_ln0, float eps0, uint32_t s0, uint32_t s1,
-                                                     uint32_t s2, int pw, int half, int sub, int cl) {
-    float v[G][EPL];
-    float2 stats[G];
-    rows_f32(buf, v, stats, has_ln0, eps0);
+  // split precision: the three bf16 terms (x = t0 + t1 + t2 to 2^-25) of the columns of this lane that fall into K block
+  // KB_ (64 columns) of its rows, each term stored as soon as it is formed (v is consumed: the residual is left in it)
+  template <int KBLK, int KB_>
+  __device__ static __forceinline__ void split_store_block(float (&v)[G][EPL], uint32_t s0, uint32_t s1, uint32_t s2,
+                                                           int pw, int half, int sub, int cl) {
+    constexpr int JB = CPL / KBLK;                       // chunks of this lane per K block
+    static_assert(CPL % KBLK == 0, "split_store_block: chunks per lane must split evenly over the K blocks");
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
-      Packed pk;
+      const uint32_t base = t == 0 ? s0 : (t == 1 ? s1 : s2);
 #pragma unroll
       for (int gi = 0; gi < G; ++gi) {
+        const int r = pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
 #pragma unroll
-        for (int e = 0; e < EPL; e += 2) {
-          const uint32_t h = pack_bf16(v[gi][e], v[gi][e + 1]);
-          pk[gi][e / 2] = h;
-          if (t < 2) {
-            v[gi][e] -= __uint_as_float(h << 16);
-            v[gi][e + 1] -= __uint_as_float(h & 0xFFFF0000u);
+        for (int jj = 0; jj < JB; ++jj) {
+          const int j = KB_ * JB + jj;
+          uint32_t w[EPC / 2];
+#pragma unroll
+          for (int e = 0; e < EPC; e += 2) {
+            float& a = v[gi][j * EPC + e];
+            float& b = v[gi][j * EPC + e + 1];
+            const uint32_t h = pack_bf16(a, b);
+            w[e / 2] = h;
+            if (t < 2) {
+              a -= __uint_as_float(h << 16);
+              b -= __uint_as_float(h & 0xFFFF0000u);
+            }
+          }
+          const int col = (cl + LPR * j) * EPC;
+          const uint32_t dst = base + sw128_chunk<kTileM>(r, col >> 3) + (uint32_t)((col & 7) * 2);
+          if constexpr (EPC == 4) {
+            st_shared8(dst, w[0], w[1]);
+          } else {
+            st_shared16(dst, w[0], w[1], w[2], w[3]);
           }
         }
       }
-      store(pk, stats, nullptr, t == 0 ? s0 : (t == 1 ? s1 : s2), pw, half, sub, cl);
     }
   }
   // the only part that needs the A stage to be free: EPL/2 registers per row -> swizzled shared memory
@@ -532,9 +545,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
   // golden model that is enough for the logits (1.4e-5) but flips ~10 ReLUs that sit within 1e-5 of zero, and a flipped
   // unit is an O(1) change of that row's gradient -- so the reference-precision mode pays for the third term.
   // Shared memory: the three weight terms take the W1 / W2 slots and the second hidden buffer, the three A terms the two
-  // A stages and the first hidden buffer, i.e. ONE A stage that both epilogue groups' tiles pass through in turn (the
-  // producers wait for the previous tile's MMAs); the output leaves through the direct (thread-per-row) stores because
-  // no staging buffer is left.
+  // A stages and the first hidden buffer, i.e. ONE tile's worth of A that both epilogue groups' tiles pass through in
+  // turn, refilled per 64-column K block while the tensor core works on the other block; the output leaves through the
+  // direct (thread-per-row) stores because no staging buffer is left.
   constexpr bool SPLIT = (MODE == 3);
   using L = Layout<D>;
   static_assert(D == 64 || D == 128, "mlp2_ws: widths 64 and 128");
@@ -570,7 +583,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       mbar_init(bar_a_full + 8 * b, kProdWarps);
       mbar_init(bar_a_empty + 8 * b, 1);
       mbar_init(bar_acc1_full + 8 * b, 1);
-      mbar_init(bar_acc2_full + 8 * b, 1);
+      mbar_init(bar_acc2_full + 8 * b, SPLIT ? kProdWarps : 1);   // SPLIT: "K block 1 filled" (see gemm1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -678,17 +691,34 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
       typename P::Packed pkA, pkB;
       float2 stA[P::G] = {}, stB[P::G] = {};
       if constexpr (SPLIT) {
-        // three term tiles per row half, ONE stage: wait until the MMAs of the previous tile (the other group's) and of
-        // this group's previous tile have retired, then compute and store half by half
-        if (it >= 1) mbar_wait_bounded<500>(bar_a_empty + 8 * (st ^ 1u), ((it - 1) >> 1) & 1u, p.status);
-        if (it >= 2) mbar_wait_bounded<500>(bar_a_empty + 8 * st, ((it >> 1) - 1) & 1u, p.status);
-        P::split_store(bufA, has_ln0, p.eps0, sA0, sA0 + L::A_BYTES, sA1, pw, 0, sub, cl);
-        if (next < n_tiles) P::load(bufA, xb, next * kTileM, p.rows, pw, 0, sub, cl);
-        P::split_store(bufB, has_ln0, p.eps0, sA0, sA0 + L::A_BYTES, sA1, pw, 1, sub, cl);
-        if (next < n_tiles) P::load(bufB, xb, next * kTileM, p.rows, pw, 1, sub, cl);
+        // Three term tiles, ONE tile's worth of shared memory, pipelined per K BLOCK (64 columns): block kb of all three
+        // tiles is refilled as soon as the MMAs of the previous tile that read it have retired (a_empty[kb]), while the
+        // tensor core still works on the other block.  a_empty is indexed by K block here (one phase per tile, waited on
+        // by the producers only); "filled" is signalled per (block, owning group): a_full[g] / acc2_full[g].
+        constexpr int KBLK = D / 64;
+        const uint32_t t0 = sA0, t1 = sA0 + L::A_BYTES, t2 = sA1;
+        float vA[P::G][P::EPL], vB[P::G][P::EPL];
+        float2 stx[P::G];
+        if (it >= 1) mbar_wait_bounded<200>(bar_a_empty, (it - 1) & 1u, p.status);
+        P::rows_f32(bufA, vA, stx, has_ln0, p.eps0);
+        P::template split_store_block<KBLK, 0>(vA, t0, t1, t2, pw, 0, sub, cl);
+        P::rows_f32(bufB, vB, stx, has_ln0, p.eps0);
+        P::template split_store_block<KBLK, 0>(vB, t0, t1, t2, pw, 1, sub, cl);
         proxy_fence_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a_full + 8 * st);
+        if (lane == 0) mbar_arrive(bar_a_full + 8 * st);   // st = it & 1 = the group that owns this tile
+        if (next < n_tiles) {                              // prefetch AFTER the first block: fewer live registers before it
+          P::load(bufA, xb, next * kTileM, p.rows, pw, 0, sub, cl);
+          P::load(bufB, xb, next * kTileM, p.rows, pw, 1, sub, cl);
+        }
+        if constexpr (KBLK == 2) {
+          if (it >= 1) mbar_wait_bounded<200>(bar_a_empty + 8, (it - 1) & 1u, p.status);
+          P::template split_store_block<KBLK, KBLK - 1>(vA, t0, t1, t2, pw, 0, sub, cl);
+          P::template split_store_block<KBLK, KBLK - 1>(vB, t0, t1, t2, pw, 1, sub, cl);
+          proxy_fence_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc2_full + 8 * st);
+        }
         continue;
       }
       if (SCORE) P::score(bufA, reinterpret_cast<const float*>(sStat), sPar + 2 * D, p.heads, p.score, tile * kTileM,
@@ -718,31 +748,43 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     const bool direct = SPLIT || p.direct != 0;        // SPLIT: the staging buffers hold operand terms
     const uint32_t sAg = sA0 + g * L::A_BYTES;
     auto gemm1 = [&](uint32_t kk) {                    // GEMM 1 of this group's kk-th tile: A stage g x W1 -> acc1[g]
-      mbar_wait_bounded(bar_a_full + 8 * g, kk & 1u, p.status);
-      tc_fence_after();
       if constexpr (SPLIT) {
-        // smallest products first: x3 W1, x1 W3, x2 W2, x2 W1, x1 W2, x1 W1, all into the same fp32 accumulator
+        // K block by K block (see the producers); per block the six products, smallest first:
+        // x3 W1, x1 W3, x2 W2, x2 W1, x1 W2, x1 W1, all into the same fp32 accumulator
+        constexpr int KBLK = D / 64;
         const uint32_t xa[3] = {sA0, sA0 + (uint32_t)L::A_BYTES, sA1};
         const uint32_t wa[3] = {sW1, sW2, sA1 + (uint32_t)BUF};
         constexpr int XI[6] = {2, 0, 1, 1, 0, 0}, WI[6] = {0, 2, 1, 0, 1, 0};
 #pragma unroll
-        for (int t = 0; t < 6; ++t) {
+        for (int kb = 0; kb < KBLK; ++kb) {
+          // "block kb of this group's kk-th tile is filled": one barrier per (block, group) -- the two issuers alternate
+          // tiles and may be early or late relative to each other, which a parity wait on a shared barrier cannot tell
+          // apart.  Block 1 borrows the acc2_full slots (unused by a single Linear).
+          mbar_wait_bounded((kb == 0 ? bar_a_full : bar_acc2_full) + 8 * g, kk & 1u, p.status);
+          tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks) {
-            const uint32_t koff = (uint32_t)((ks >> 2) * (kTileM * 128) + (ks & 3) * 32);
-            const uint32_t woff = (uint32_t)((ks >> 2) * (D * 128) + (ks & 3) * 32);
-            umma_bf16(tmem_acc1, smem_desc_sw128(xa[XI[t]] + koff), smem_desc_sw128(wa[WI[t]] + woff),
-                      instr_desc_bf16(kTileM, D), (t > 0 || ks > 0) ? 1u : 0u);
+          for (int t = 0; t < 6; ++t) {
+#pragma unroll
+            for (int ks = 4 * kb; ks < 4 * kb + 4; ++ks) {
+              const uint32_t koff = (uint32_t)((ks >> 2) * (kTileM * 128) + (ks & 3) * 32);
+              const uint32_t woff = (uint32_t)((ks >> 2) * (D * 128) + (ks & 3) * 32);
+              umma_bf16(tmem_acc1, smem_desc_sw128(xa[XI[t]] + koff), smem_desc_sw128(wa[WI[t]] + woff),
+                        instr_desc_bf16(kTileM, D), (kb > 0 || t > 0 || ks > 4 * kb) ? 1u : 0u);
+            }
           }
+          umma_commit(bar_a_empty + 8 * kb);
         }
-      } else {
+        umma_commit(bar_acc1_full + 8 * g);
+        return;
+      }
+      mbar_wait_bounded(bar_a_full + 8 * g, kk & 1u, p.status);
+      tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < D / 16; ++ks) {
         const uint32_t koff = (uint32_t)((ks >> 2) * (kTileM * 128) + (ks & 3) * 32);
         const uint32_t woff = (uint32_t)((ks >> 2) * (D * 128) + (ks & 3) * 32);
         umma_bf16(tmem_acc1, smem_desc_sw128(sAg + koff), smem_desc_sw128(sW1 + woff), instr_desc_bf16(kTileM, D),
                   ks > 0 ? 1u : 0u);
-      }
       }
       umma_commit(bar_a_empty + 8 * g);
       umma_commit(bar_acc1_full + 8 * g);

@@ -14,10 +14,15 @@ ei, tot = P.add_self_loops(v2e, n, m); norm = P.norm_construction(ei)
 x = synthetic.features(n, d, torch.float32, device='cuda:0')
 y = torch.randint(0, 10, (n,), device='cuda:0')
 limit = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+only = sys.argv[2] if len(sys.argv) > 2 else ''          # 'f32only' | 'bf16only' | 'deepsets' (short runs under ncu)
 for pma, heads in ((False, 1), (True, 8)):
     args = O.config_namespace(num_features=d, num_classes=10, MLP_hidden=d, Classifier_hidden=d, heads=heads,
                               All_num_layers=1, Classifier_num_layers=1, PMA=pma, aggregate='add')
+    if only == 'deepsets' and pma:
+        continue
     for agg in (None, torch.bfloat16):
+        if (only == 'f32only' and agg is not None) or (only == 'bf16only' and agg is None):
+            continue
         torch.manual_seed(0)
         model = allset_b200.SetGNN(args, agg_dtype=agg).to('cuda:0').train()
         opt = torch.optim.Adam(model.parameters(), lr=1e-3)

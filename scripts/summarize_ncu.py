@@ -1,5 +1,5 @@
 """Summarise an ncu report (.ncu-rep, read here with `ncu -i`) and a launch list into profiles/<name>.md|json.
-usage: python scripts/summarize_ncu.py <rep> <launches.csv|-> <out-prefix> [algorithmic-bytes-json]"""
+usage: python scripts/summarize_ncu.py <rep | raw-page.csv> <launches.csv|-> <out-prefix> [algorithmic-bytes-json]"""
 import csv, io, json, subprocess, sys
 
 KEYS = [
@@ -12,6 +12,7 @@ KEYS = [
     ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l2_throughput_pct'),
     ('sm__warps_active.avg.pct_of_peak_sustained_active', 'achieved_occupancy_pct'),
     ('sm__issue_active.avg.pct_of_peak_sustained_elapsed', 'issue_active_pct'),
+    ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor_pipe_active_pct'),
     ('launch__registers_per_thread', 'registers_per_thread'),
     ('launch__shared_mem_per_block_dynamic', 'dyn_smem_per_block'),
     ('launch__grid_size', 'grid'),
@@ -38,7 +39,10 @@ def to_ms(val, unit):
 
 def main():
     rep, launches, prefix = sys.argv[1], sys.argv[2], sys.argv[3]
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if rep.endswith('.csv'):      # `ncu -i <rep> --page raw --csv` already exported on the GPU box (reports > 64 MiB do not travel)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     out = {'report': rep, 'kernels': []}

@@ -32,7 +32,7 @@ def _status():
 
 
 @pytest.mark.parametrize('d', [64, 128])
-@pytest.mark.parametrize('rows', ROWS)
+@pytest.mark.parametrize('rows', ROWS + [300001])
 def test_linear_fwd_split_precision_vs_fp64(d, rows):
     from allset_b200 import _lib
     x, w, b = _mk(rows, d, 11 + d + rows)
