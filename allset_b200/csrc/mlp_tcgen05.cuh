@@ -335,6 +335,17 @@ struct Producer {
                                  : make_uint4(0, 0, 0, 0);
     }
   }
+  // L2 prefetch of a whole tile (128 dense rows = one contiguous block) by the 256 producer threads: the register
+  // prefetch reaches one tile ahead (32-64 KB in flight per SM, short of what HBM latency asks for), this one two tiles
+  // ahead at no register cost, so that the register loads of the next iteration hit L2.
+  __device__ static __forceinline__ void prefetch_l2(const unsigned char* xb, long long row0, long long rows, int ptid) {
+    if (row0 >= rows) return;
+    const long long nrows = (rows - row0) < kTileM ? (rows - row0) : kTileM;
+    const int lines = (int)((nrows * (long long)(D * sizeof(TIn)) + 127) >> 7);
+    const unsigned char* base = xb + (size_t)row0 * (D * sizeof(TIn));
+    for (int i = ptid; i < lines; i += kProdWarps * 32)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((size_t)i << 7)));
+  }
   // LayerNorm 0 WITHOUT its affine part (gamma / beta are folded into W1 / b1 at setup), the G row groups in lockstep.
   // PMA score of the rows of one half, fp32 on the CUDA cores: lane cl of a row holds EPL of its D elements; 8 heads at
   // a time are reduced over the 8 lanes of the row by a TRANSPOSED butterfly (4 + 2 + 1 shuffles: each step a lane keeps
@@ -685,6 +696,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     for (uint32_t it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t st = it & 1u;
       const long long next = tile + gridDim.x;
+      P::prefetch_l2(xb, (tile + 2LL * gridDim.x) * kTileM, p.rows, pw * 32 + lane);
       const uint32_t sAst = sA0 + st * L::A_BYTES;
       float2* stat = TAIL ? sStat + (st * 2 + ((it >> 1) & 1u)) * kTileM : nullptr;
       // all the arithmetic happens BEFORE the stage is known to be free; only the shared-memory stores wait for it
