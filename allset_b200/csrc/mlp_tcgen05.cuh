@@ -60,6 +60,7 @@ struct Params {
   // MODE 3 (split precision) / single Linear: 1 = `w1` is stored [in, out] (the kernel computes x W instead of x W^T:
   // the input gradient of a Linear, dx = dy W); excludes LayerNorm 0
   int w_transposed;
+  int no_l2_prefetch;    // debug / A-B: 1 = the producers do not prefetch two tiles ahead into L2
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -321,13 +322,20 @@ struct Producer {
   static constexpr int ROWS_PER_WARP = kTileM / kProdWarps;
   static constexpr int G = ROWS_PER_WARP / RPI / 2;     // row groups per half
   static_assert(CPL >= 1 && G == 2, "producer geometry");
+  // Row of the tile handled by (producer warp pw, half, row group gi, sub-row of the instruction): four consecutive rows
+  // per warp instruction.  (Tried: rows {0, 1, 4, 5} + 2 gi, which halves the bank conflicts of the 8-byte stores of fp32
+  // rows -- rows r and r ^ 4 land in opposite 64-byte halves of the 128-byte swizzle; measured neutral, +-2 %, on one box.)
+  __device__ static __forceinline__ int row_of(int pw, int half, int gi, int sub) {
+    return pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
+  }
+
   using Buf = uint4[G][CPL];
 
   __device__ static __forceinline__ void load(Buf& buf, const unsigned char* xb, long long row0, long long rows,
                                               int pw, int half, int sub, int cl) {
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
-      const int r = pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
+      const int r = row_of(pw, half, gi, sub);
       const long long gr = row0 + r;
 #pragma unroll
       for (int j = 0; j < CPL; ++j)
@@ -413,7 +421,7 @@ struct Producer {
         const float send = (cl & 1) ? b2[gi][0] : b2[gi][1];
         const float keep = (cl & 1) ? b2[gi][1] : b2[gi][0];
         const float total = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        const long long gr = row0 + pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
+        const long long gr = row0 + row_of(pw, half, gi, sub);
         if (gr < rows && hb + cl < H) out[gr * H + hb + cl] = total + sBe[hb + cl];
       }
     }
@@ -496,7 +504,7 @@ struct Producer {
       const uint32_t base = t == 0 ? s0 : (t == 1 ? s1 : s2);
 #pragma unroll
       for (int gi = 0; gi < G; ++gi) {
-        const int r = pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
+        const int r = row_of(pw, half, gi, sub);
 #pragma unroll
         for (int jj = 0; jj < JB; ++jj) {
           const int j = KB_ * JB + jj;
@@ -528,7 +536,7 @@ struct Producer {
                                                int pw, int half, int sub, int cl) {
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
-      const int r = pw * ROWS_PER_WARP + (half * G + gi) * RPI + sub;
+      const int r = row_of(pw, half, gi, sub);
       if (stat != nullptr && cl == 0) stat[r] = stats[gi];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
@@ -696,7 +704,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     for (uint32_t it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t st = it & 1u;
       const long long next = tile + gridDim.x;
-      P::prefetch_l2(xb, (tile + 2LL * gridDim.x) * kTileM, p.rows, pw * 32 + lane);
+      if (!p.no_l2_prefetch) P::prefetch_l2(xb, (tile + 2LL * gridDim.x) * kTileM, p.rows, pw * 32 + lane);
       const uint32_t sAst = sA0 + st * L::A_BYTES;
       float2* stat = TAIL ? sStat + (st * 2 + ((it >> 1) & 1u)) * kTileM : nullptr;
       // all the arithmetic happens BEFORE the stage is known to be free; only the shared-memory stores wait for it
@@ -1024,7 +1032,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
 }
 
 template <typename TIn, typename TOut, int D, int MODE>
-int launch(const Params& p, cudaStream_t st) {
+int launch(const Params& p_in, cudaStream_t st) {
+  static const int no_prefetch = getenv("ALLSET_MLP2_NO_L2_PREFETCH") != nullptr ? 1 : 0;
+  Params p = p_in;
+  p.no_l2_prefetch = no_prefetch;
   const long long n_tiles = (p.rows + kTileM - 1) / kTileM;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -640,7 +640,32 @@ def run_b200(a):
         mlp = {'kernel': 'mlp2_ws_kernel (tcgen05, bf16 operands): relu(LN -> Linear -> ReLU -> LN -> Linear) over X_v',
                'rows': Nv, 'ms': m_ms, 'bytes': nbytes, 'gbs': nbytes / (m_ms * 1e-3) / 1e9,
                'tflops': 4.0 * Nv * d * d / (m_ms * 1e-3) / 1e12, 'rows_per_s': Nv / (m_ms * 1e-3)}
-        del w1, w2
+        # the training path's Linear kernels on the same rows (tcgen05): forward / input gradient / weight gradient, in the
+        # bench dtype (bf16 operands) and for fp32 rows (three-term split precision, the reference's accuracy class)
+        def lin_ms(fn):
+            def step(marks):
+                if marks: marks[0].record()
+                fn()
+                if marks: marks[1].record()
+            n_it = max(5, a.steps // 5)
+            t_ms, _ = timed_steps(step, 1, n_it, a.warmup)
+            return t_ms / n_it
+
+        lin_rows = min(Nv, 4_000_000)                 # fp32 copies of the rows: keep the extra footprint at 4 GB
+        xr = x_rows[:lin_rows]
+        dyr = torch.randn(lin_rows, d, device=dev, generator=gw).to(o_dt)
+        linear = {'rows': lin_rows, 'kernels': 'allset_linear_fwd (mlp2_ws_kernel single-Linear modes) / allset_linear_wgrad (wgrad5::wgrad_kernel)'}
+        for tag, xx, dd in (('bf16' if o_dt == torch.bfloat16 else 'f32_split', xr, dyr),) + \
+                ((('f32_split', xr.float(), dyr.float()),) if o_dt == torch.bfloat16 else ()):
+            io_b = 2 * lin_rows * d * xx.element_size()
+            f_ms = lin_ms(lambda: _lib.linear_fwd(xx, w1))
+            g_ms = lin_ms(lambda: _lib.linear_fwd(dd, w1, transposed=True))
+            w_ms = lin_ms(lambda: _lib.linear_wgrad(dd, xx))
+            linear[tag] = {'fwd_ms': f_ms, 'dgrad_ms': g_ms, 'wgrad_ms': w_ms, 'bytes_per_launch': io_b,
+                           'fwd_gbs': io_b / (f_ms * 1e-3) / 1e9, 'dgrad_gbs': io_b / (g_ms * 1e-3) / 1e9,
+                           'wgrad_gbs': io_b / (w_ms * 1e-3) / 1e9}
+        mlp['linear'] = linear
+        del w1, w2, xr, dyr
 
     # ---- roofline of the dominant kernel (the segmented-reduce gather kernel; both directions launch it) --------
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')

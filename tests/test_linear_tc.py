@@ -164,3 +164,29 @@ def test_fp32_mode_mlp_eval_chain_matches_reference_arithmetic(monkeypatch):
         out = mlp(x, final_relu=True)
     assert out.dtype == torch.float32
     assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize('pma', [False, True])
+def test_fp32_mode_model_eval_on_tcgen05_matches_the_aten_path(pma, monkeypatch):
+    """Whole SetGNN forward in fp32 mode at a size where every square Linear runs in split precision on tcgen05 (MLP chain
+    with fused LayerNorm / bias / ReLU, PMA.lin_V and rFF through ops.linear_bias_act) against the same model with the
+    kernels switched off (cuBLAS SGEMM + glue): the fp32 bar, 1e-4 of the logit scale."""
+    import allset_oracle as O
+    from types import SimpleNamespace
+    from allset_b200 import ops, synthetic, preprocessing as P
+    import allset_b200
+    n, m, d = 30000, 6000, 128
+    v2e = synthetic.poisson_hypergraph(n, m, 8, seed=5, device=dev())
+    ei, tot = P.add_self_loops(v2e, n, m)
+    norm = P.norm_construction(ei)
+    x = synthetic.features(n, d, torch.float32, device=dev())
+    args = O.config_namespace(num_features=d, num_classes=7, MLP_hidden=d, Classifier_hidden=d, heads=8 if pma else 1,
+                              All_num_layers=2, Classifier_num_layers=1, PMA=pma, aggregate='add')
+    torch.manual_seed(0)
+    model = allset_b200.SetGNN(args).to(dev()).eval()
+    with torch.no_grad():
+        monkeypatch.setattr(ops, 'TC_LINEAR', False)
+        ref = model(SimpleNamespace(x=x, edge_index=ei.clone(), norm=norm))
+        monkeypatch.setattr(ops, 'TC_LINEAR', True)
+        out = model(SimpleNamespace(x=x, edge_index=ei.clone(), norm=norm))
+    assert (out - ref).abs().max().item() <= 1e-4 * max(ref.abs().max().item(), 1.0)
