@@ -1010,6 +1010,7 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
   for (int c = 0; c < CH; ++c) { m2[c] = -INFINITY; l[c] = 0.f; }
 #pragma unroll
   for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+  bool fresh = true;                            // no piece of the current segment accumulated yet (warp-uniform)
   int seg = 0, pos = kb;
   int cur_end = nseg > 0 ? __ldg(rp + 1) : INT32_MAX, nxt_end = __ldg(rp + min(2, max(nseg, 0)));
 
@@ -1060,6 +1061,7 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
     for (int c = 0; c < CH; ++c) { m2[c] = -INFINITY; l[c] = 0.f; }
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+    fresh = true;
     ++seg;
     cur_end = seg < nseg ? nxt_end : INT32_MAX;
     nxt_end = __ldg(rp + min(seg + 2, max(nseg, 0)));
@@ -1088,6 +1090,37 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
     float a2;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(scoreaddr + (uint32_t)hc[c] * 4u));
     return a2;
+  };
+
+  auto short_piece = [&](auto nc, int c, uint32_t prow, uint32_t psc) {
+    constexpr int N = decltype(nc)::value;
+    float a[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) a[k] = load_a2(psc + (uint32_t)k * SB, c);
+    float pm = a[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) pm = fmaxf(pm, a[k]);
+    float mn = pm, lc = 0.f;
+    if (!fresh) {                               // one rescale of the carried state
+      mn = fmaxf(m2[c], pm);
+      const float cf = ex2_approx(m2[c] - mn);
+      lc = l[c] * cf;
+#pragma unroll
+      for (int i = 0; i < EPC; i += 2) {
+        if (EPC >= 2) fmul2(acc[c * EPC + i], acc[c * EPC + i + 1], cf);
+        else acc[c * EPC + i] *= cf;
+      }
+    }
+    m2[c] = mn;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      uint32_t r0[4];
+      load_chunk(prow + (uint32_t)k * ROWB, c, r0);
+      const float p0 = ex2_approx(a[k] - mn);
+      lc += p0;
+      fma_chunk(c, r0, p0);
+    }
+    l[c] = lc;
   };
 
   const uint64_t pol_rows = l2_policy_evict_first(), pol_side = l2_policy_evict_last();
@@ -1146,29 +1179,21 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         if (plen <= kPmaOnlinePiece) {
-          // short piece (the E->V direction: ~5 rows per piece): ONE pass with an online max -- per row two ex2 and a
-          // rescale of the carried state, but none of the two-pass loop / remainder control overhead that made the
-          // kernel issue-bound on short segments (ncu: 4.2 G warp instructions = 70 per incidence, 82 % issue-active)
-          float m = m2[c], lc = l[c];
-#pragma unroll 1
-          for (int k = 0; k < plen; ++k) {
-            uint32_t r0[4];
-            load_chunk(prow + k * ROWB, c, r0);
-            const float a = load_a2(psc + k * SB, c);
-            const float mn = fmaxf(m, a);
-            const float cf = ex2_approx(m - mn);             // 2^-inf = 0 for the first row of a segment
-            const float p0 = ex2_approx(a - mn);
-            m = mn;
-            lc = fmaf(lc, cf, p0);
-#pragma unroll
-            for (int i = 0; i < EPC; i += 2) {
-              if (EPC >= 2) fmul2(acc[c * EPC + i], acc[c * EPC + i + 1], cf);
-              else acc[c * EPC + i] *= cf;
-            }
-            fma_chunk(c, r0, p0);
+          // short piece (the E->V direction: ~5 rows per piece): straight-line code per piece length -- the scores of the
+          // piece stay in registers between the max pass and the weight pass, one rescale of the carried state per piece
+          // (none at all for the first piece of a segment), no loop or remainder control.  History: two-pass loops unrolled
+          // by 4 / 2 were issue-bound on their control overhead (70 warp instructions per incidence); a single-pass online
+          // max (two ex2 and a rescale per ROW) brought that to 61; this form needs ~11 per row.
+          switch (plen) {
+            case 1: short_piece(std::integral_constant<int, 1>{}, c, prow, psc); break;
+            case 2: short_piece(std::integral_constant<int, 2>{}, c, prow, psc); break;
+            case 3: short_piece(std::integral_constant<int, 3>{}, c, prow, psc); break;
+            case 4: short_piece(std::integral_constant<int, 4>{}, c, prow, psc); break;
+            case 5: short_piece(std::integral_constant<int, 5>{}, c, prow, psc); break;
+            case 6: short_piece(std::integral_constant<int, 6>{}, c, prow, psc); break;
+            case 7: short_piece(std::integral_constant<int, 7>{}, c, prow, psc); break;
+            default: short_piece(std::integral_constant<int, 8>{}, c, prow, psc); break;
           }
-          m2[c] = m;
-          l[c] = lc;
           continue;
         }
         // pass 1: piece max
@@ -1214,6 +1239,7 @@ pma_stream_kernel(const T* __restrict__ v, const float* __restrict__ score, cons
       }
       r += plen;
       pos += plen;
+      fresh = false;
     }
     __syncwarp();
     if (ipos < ke) {
