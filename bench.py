@@ -402,32 +402,64 @@ def run_b200(a):
     ms_per_step = total_ms / a.steps
     value = Me / (ms_per_step * 1e-3)
     verified = None
+    verify_note = None
     if world > 1:
-        # every rank holds the full graph: recompute the pair unsharded and compare bit for bit (the per-segment
-        # summation order does not depend on the partition)
+        # every rank holds the full graph: recompute the pair unsharded and compare.  Segments shorter than the stream
+        # kernels' cut threshold (256 incidences) are summed in CSR order whatever the partition, so on a graph without
+        # longer ones the comparison is bit for bit.  A longer segment may be CUT at a chunk boundary, and chunk
+        # boundaries depend on the slice a rank reduces: its pieces are added in a different association, the row can
+        # differ by an ulp of the storage dtype, and so can everything gathered from it downstream -- then the check is
+        # exact equality on the rows of short hyperedges plus a rounding-level bound on all rows.
         replicate[0] = True
         sum_step(None)
         t, sgl = v2e.by_tgt, v2e.by_src
         ref_e = _lib.segreduce_fwd(x_v, t.rowptr, t.col, t.n_tgt, False, long_ids=t.long_ids, long_threshold=t.long_threshold)
         ref_v = _lib.segreduce_fwd(ref_e, sgl.rowptr, sgl.col, sgl.n_tgt, False, long_ids=sgl.long_ids, long_threshold=sgl.long_threshold)
+        len_e = (t.rowptr[1:] - t.rowptr[:-1])
+        cut_possible = bool((len_e >= 256).any()) or bool(((sgl.rowptr[1:] - sgl.rowptr[:-1]) >= 256).any())
+        ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -20
+
+        def close(a_, b_):
+            """|a - b| <= 4 ulp of the larger magnitude in the row (+ 4 ulp of the tensor scale for cancelling sums)"""
+            a_, b_ = a_.float(), b_.float()
+            bound = 4 * ulp * torch.maximum(a_.abs(), b_.abs()).amax(dim=1, keepdim=True) + 4 * ulp * b_.abs().max() * 1e-2
+            return bool(((a_ - b_).abs() <= bound).all())
+
+        def same(a_, b_, short_rows=None, what=''):
+            if not cut_possible:
+                return bool(torch.equal(a_, b_))
+            good = close(a_, b_)
+            if short_rows is not None and not bool(torch.equal(a_[short_rows], b_[short_rows])):
+                good = False
+            if not good:
+                diff = (a_.float() - b_.float()).abs()
+                rows_off = (diff.amax(dim=1) > 0)
+                sys.stderr.write('[rank %d] %s: %d rows differ, max |diff| %.4g at scale %.4g%s\n' % (
+                    rank, what, int(rows_off.sum()), float(diff.max()), float(b_.float().abs().max()),
+                    '' if short_rows is None else ', of them short-segment rows: %d' % int((rows_off & short_rows).sum())))
+            return good
+
         if selective_xv:
             # a rank holds its own vertex rows and the rows its hyperedge range gathers -- exactly what the next
             # layer's V->E reads: check those rows, then the next V->E itself
             need = torch.zeros(Nv, dtype=torch.bool, device=dev)
             need[sh.v_lo:sh.v_hi] = True
             need[sh.e_csr.col.long()] = True
-            ok = bool(torch.equal(plain(x_e), ref_e)) and bool(torch.equal(plain(x_v2)[need], ref_v[need]))
+            ok = same(plain(x_e), ref_e, len_e < 256, 'X_e') and same(plain(x_v2)[need], ref_v[need], None, 'X_v (needed rows)')
             nxt = torch.empty((sh.e_hi - sh.e_lo, d), dtype=dtype, device=dev)
             _lib.segreduce_fwd(plain(x_v2), sh.e_csr.rowptr, sh.e_csr.col, sh.e_csr.n_tgt, False, out=nxt)
             ref_nxt = _lib.segreduce_fwd(ref_v, t.rowptr, t.col, t.n_tgt, False)
-            ok = ok and bool(torch.equal(nxt, ref_nxt[sh.e_lo:sh.e_hi]))
+            ok = ok and same(nxt, ref_nxt[sh.e_lo:sh.e_hi], None, 'next V->E')
             del nxt, ref_nxt, need
         else:
-            ok = bool(torch.equal(plain(x_e), ref_e)) and bool(torch.equal(plain(x_v2), ref_v))
+            ok = same(plain(x_e), ref_e, len_e < 256, 'X_e') and same(plain(x_v2), ref_v, None, 'X_v')
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         verified = bool(flag.item())
-        del ref_e, ref_v
+        verify_note = ('bit for bit' if not cut_possible else
+                       'bit for bit on the rows of hyperedges shorter than 256 incidences, within 4 ulp of the storage dtype '
+                       'elsewhere (longer segments are cut at partition-dependent chunk boundaries)')
+        del ref_e, ref_v, len_e
         replicate[0] = a.replicate_xv
         if not verified:
             raise RuntimeError('sharded V->E/E->V result differs from the unsharded one')
@@ -726,7 +758,7 @@ def run_b200(a):
             'roofline': roofline,
             'cpu_baseline': cpu_baseline,
             'phases_ms': {'v2e': t_ve, 'exchange_x_e': t_ge, 'e2v': t_ev, 'exchange_x_v': t_gv},
-            'other_mode': other, 'sharded_equals_unsharded': verified,
+            'other_mode': other, 'sharded_equals_unsharded': verified, 'sharded_check': verify_note,
             'v2e_only': {'value': Me / ((v2e_plain_ms if v2e_plain_ms else t_ve) * 1e-3), 'unit': UNIT,
                          'ms': v2e_plain_ms if v2e_plain_ms else t_ve,
                          'note': 'the V->E segmented reduce alone, without the fused X_e stores to the peers (max over ranks)'},

@@ -202,3 +202,33 @@ def test_sharded_setgnn_two_gpus_forward_backward():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] for r in res), res
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+def test_slices_of_a_power_law_graph_match_the_whole_graph(dtype):
+    """What a rank computes on its slice of a graph WITH long hyperedges against the same rows of the unsharded launch.
+    Segments shorter than the stream kernels' cut threshold (256 incidences) are summed in CSR order whatever the slice:
+    bit for bit.  Longer ones may be cut at chunk boundaries, which depend on the slice: same value up to the association
+    of the pieces, i.e. within a few ulp of the storage dtype (this is the check bench.py applies on configs[4])."""
+    from allset_b200 import _lib, synthetic, sharding
+    import allset_b200
+    n, m, d = 1_500_000, 250_000, 128
+    ei = synthetic.powerlaw_hypergraph(n, m, 2, 4096, 2.0, seed=7, device=dev())
+    inc = allset_b200.Incidence.from_coo(ei[0], ei[1] - n, n_src=n, n_tgt=m)
+    t = inc.by_tgt
+    lens = (t.rowptr[1:] - t.rowptr[:-1])
+    assert int(lens.max()) >= 2048 and _lib.stream_eligible(dtype, d, m)
+    x = synthetic.features(n, d, dtype, seed=3, device=dev())
+    whole = _lib.segreduce_fwd(x, t.rowptr, t.col, m, False)
+    ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -20
+    for lo, hi in sharding.balanced_ranges(t.rowptr, 3, row_weight=1):
+        rp, col, _ = sharding.slice_csr(t.rowptr, t.col, lo, hi)
+        if not _lib.stream_eligible(dtype, d, hi - lo):
+            continue
+        part = _lib.segreduce_fwd(x, rp, col, hi - lo, False)
+        ref = whole[lo:hi]
+        short = lens[lo:hi] < 256
+        assert torch.equal(part[short], ref[short])
+        a, b = part.float(), ref.float()
+        bound = 4 * ulp * torch.maximum(a.abs(), b.abs()).amax(dim=1, keepdim=True) + 4e-2 * ulp * b.abs().max()
+        assert bool(((a - b).abs() <= bound).all())
