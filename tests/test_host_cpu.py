@@ -230,6 +230,18 @@ def test_tensor_core_paths_are_cuda_eval_bf16_only():
         assert not odd._tc_ok(x)                     # not square
 
 
+def test_tcgen05_linear_gating_is_cuda_square_only():
+    """ops.linear_nb / MLP._forward_chain hand a Linear to the tcgen05 kernels only for CUDA rows, square widths 64 / 128,
+    f32 master weights and at least FUSED_DENSE_MIN_ROWS rows (the module API itself refuses CPU tensors: test_no_cpu_fallback)."""
+    from allset_b200 import _lib, ops
+    x = torch.randn(9000, 128)
+    w = torch.randn(128, 128)
+    assert not _lib.linear_ok(x, w) and not ops.tc_linear_ok(x, w)          # CPU rows
+    assert _lib.LINEAR_WIDTHS == (64, 128) and (_lib.PREC_BF16, _lib.PREC_SPLIT) == (0, 1)
+    hdr = open(os.path.join(ROOT, 'include', 'allset_b200.h')).read()
+    assert '#define ALLSET_PREC_BF16 0' in hdr and '#define ALLSET_PREC_SPLIT 1' in hdr
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # Work split of the stream kernels (csrc/allset_kernels.cu: chunk_boundary / chunk_cut), restated in Python: the
 # invariants the decoupled look-back relies on.  A model check of the ALGORITHM (the device code is exercised on the GPU).
