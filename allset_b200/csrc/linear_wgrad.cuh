@@ -179,6 +179,18 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Params p) {
       const uint32_t s = it % kStages;
       const uint32_t stage = sStage + s * G::STAGE;
       const long long next = tile + gridDim.x;
+      {   // L2 prefetch two tiles ahead (the register prefetch reaches one tile = 32-64 KB per SM, short of HBM latency x rate)
+        const long long r0 = (tile + 2LL * gridDim.x) * kKT;
+        if (r0 < p.rows) {
+          const long long nrows = (p.rows - r0) < kKT ? (p.rows - r0) : kKT;
+          const int lines = (int)((nrows * (long long)(D * sizeof(T)) + 127) >> 7);
+          const size_t off = (size_t)r0 * (D * sizeof(T));
+          for (int i = pw * 32 + lane; i < lines; i += kProdWarps * 32) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const unsigned char*>(p.dy) + off + ((size_t)i << 7)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const unsigned char*>(p.x) + off + ((size_t)i << 7)));
+          }
+        }
+      }
       if (it >= kStages) mbar_wait_bounded<1000>(bar_empty + 8 * s, ((it / kStages) - 1) & 1u, p.status);
       store(bufY, 0, stage);
       if (next < n_tiles) load(bufY, yb, next);
