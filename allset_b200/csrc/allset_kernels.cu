@@ -2688,7 +2688,8 @@ int allset_linear_wgrad(const void* dy, const void* x, int dtype, int precision,
   if (workspace_floats < (int64_t)wgrad5::n_partials((long long)rows) * d * d)
     return fail(ALLSET_EINVAL, "linear_wgrad: workspace too small (allset_linear_wgrad_partials(rows) * d * d floats)");
   static const int swap = getenv("ALLSET_WGRAD_SWAP") != nullptr ? 1 : 0;
-  wgrad5::Params p{dy, x, (long long)rows, workspace, status, swap};
+  static const int ahead = getenv("ALLSET_WGRAD_L2_PREFETCH") != nullptr ? atoi(getenv("ALLSET_WGRAD_L2_PREFETCH")) : 2;
+  wgrad5::Params p{dy, x, (long long)rows, workspace, status, swap, ahead};
   if (dtype == ALLSET_F32) {
     if (d == 64) return wgrad5::launch<float, 64, true>(p, dw, st);
     return wgrad5::launch<float, 128, true>(p, dw, st);

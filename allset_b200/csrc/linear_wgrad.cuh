@@ -53,6 +53,7 @@ struct Params {
   float* partial;     // [gridDim.x, D, D]
   int* status;
   int swap_offsets;   // debug: exchange LBO and SBO in the descriptors
+  int l2_prefetch_ahead;   // tiles ahead the producers prefetch into L2 (0 = off)
 };
 
 // MN-major SWIZZLE_128B descriptor: start address >> 4, LBO (between 64-element column blocks) >> 4 in [16,30),
@@ -179,9 +180,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const Params p) {
       const uint32_t s = it % kStages;
       const uint32_t stage = sStage + s * G::STAGE;
       const long long next = tile + gridDim.x;
-      {   // L2 prefetch two tiles ahead (the register prefetch reaches one tile = 32-64 KB per SM, short of HBM latency x rate)
-        const long long r0 = (tile + 2LL * gridDim.x) * kKT;
-        if (r0 < p.rows) {
+      {   // L2 prefetch a few tiles ahead (the register prefetch reaches one tile = 32-64 KB per SM, short of HBM latency x rate)
+        const long long r0 = (tile + (long long)p.l2_prefetch_ahead * gridDim.x) * kKT;
+        if (p.l2_prefetch_ahead > 0 && r0 < p.rows) {
           const long long nrows = (p.rows - r0) < kKT ? (p.rows - r0) : kKT;
           const int lines = (int)((nrows * (long long)(D * sizeof(T)) + 127) >> 7);
           const size_t off = (size_t)r0 * (D * sizeof(T));

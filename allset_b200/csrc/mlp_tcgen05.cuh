@@ -60,7 +60,7 @@ struct Params {
   // MODE 3 (split precision) / single Linear: 1 = `w1` is stored [in, out] (the kernel computes x W instead of x W^T:
   // the input gradient of a Linear, dx = dy W); excludes LayerNorm 0
   int w_transposed;
-  int no_l2_prefetch;    // debug / A-B: 1 = the producers do not prefetch two tiles ahead into L2
+  int l2_prefetch_ahead; // tiles ahead the producers prefetch into L2 (0 = off; default 2, ALLSET_MLP2_L2_PREFETCH overrides)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -704,7 +704,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
     for (uint32_t it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t st = it & 1u;
       const long long next = tile + gridDim.x;
-      if (!p.no_l2_prefetch) P::prefetch_l2(xb, (tile + 2LL * gridDim.x) * kTileM, p.rows, pw * 32 + lane);
+      if (p.l2_prefetch_ahead > 0)
+        P::prefetch_l2(xb, (tile + (long long)p.l2_prefetch_ahead * gridDim.x) * kTileM, p.rows, pw * 32 + lane);
       const uint32_t sAst = sA0 + st * L::A_BYTES;
       float2* stat = TAIL ? sStat + (st * 2 + ((it >> 1) & 1u)) * kTileM : nullptr;
       // all the arithmetic happens BEFORE the stage is known to be free; only the shared-memory stores wait for it
@@ -1033,9 +1034,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp2_ws_kernel(const Params p) 
 
 template <typename TIn, typename TOut, int D, int MODE>
 int launch(const Params& p_in, cudaStream_t st) {
-  static const int no_prefetch = getenv("ALLSET_MLP2_NO_L2_PREFETCH") != nullptr ? 1 : 0;
+  static const int ahead = getenv("ALLSET_MLP2_L2_PREFETCH") != nullptr ? atoi(getenv("ALLSET_MLP2_L2_PREFETCH")) : 2;
   Params p = p_in;
-  p.no_l2_prefetch = no_prefetch;
+  p.l2_prefetch_ahead = ahead;
   const long long n_tiles = (p.rows + kTileM - 1) / kTileM;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

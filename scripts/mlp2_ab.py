@@ -31,6 +31,8 @@ for rows in (10_000_000, 1_000_000):
         xf = xb.float()
         res['mlp2_f32_f32_%dM' % (rows // 1_000_000)] = t(lambda: _lib.mlp2_fwd(xf, w1, bz, w2, bz, ln, ln, True, torch.float32))
         res['linear_split_%dM' % (rows // 1_000_000)] = t(lambda: _lib.linear_fwd(xf, w1))
+        res['wgrad_split_%dM' % (rows // 1_000_000)] = t(lambda: _lib.linear_wgrad(xf, xf))
+        res['wgrad_bf16_%dM' % (rows // 1_000_000)] = t(lambda: _lib.linear_wgrad(xb, xb))
         del xf
     del xb
 print(json.dumps(res), flush=True)
