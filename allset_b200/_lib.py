@@ -433,7 +433,7 @@ def linear_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = Non
                transposed: bool = False, out_dtype: Optional[torch.dtype] = None,
                status: Optional[torch.Tensor] = None, split: Optional[bool] = None) -> torch.Tensor:
     """out = [relu](LN?(x) op(w)^T + b) on tcgen05; op(w) = w ([out, in]) or w^T with `transposed` (dx = dy w).
-    f32 rows run in split precision (two bf16 terms per operand, fp32-class accuracy) and return f32 unless
+    f32 rows run in split precision (three bf16 terms per operand, six products: fp32 accuracy) and return f32 unless
     `split=False`; bf16 rows (and f32 rows with `split=False`) run with bf16 operands and return `out_dtype` (default: the
     input dtype)."""
     _need(x, 'x')

@@ -294,7 +294,8 @@ class _LinearNB(torch.autograd.Function):
     """y = x @ W^T without bias, W kept as the fp32 master parameter, dW accumulated and returned in fp32.
 
     Square widths 64 / 128 (every Linear between the aggregation steps) run on the hand-written tcgen05 kernels: bf16 rows
-    with bf16 operands, fp32 rows in split precision (two bf16 terms per operand, fp32-class accuracy) -- forward
+    with bf16 operands, fp32 rows in split precision (three bf16 terms per operand and six products for the forward and
+    the input gradient, two terms for the weight gradient: as close to fp64 as an fp32 SGEMM) -- forward
     (allset_linear_fwd), input gradient (the same kernel with the weight read transposed) and weight gradient
     (allset_linear_wgrad, MN-major operands straight from the row-major activations).  Other shapes (the first layer from
     a dataset's raw feature count, the classifier's class count, the skinny score GEMM) go to cuBLAS.  `out_fp32` keeps

@@ -196,8 +196,10 @@ int allset_linear_score_fwd(const void* x, int x_dtype, const float* w, const fl
 
 /* Arithmetic of the tcgen05 Linear kernels below. */
 #define ALLSET_PREC_BF16 0   /* operands rounded to bf16, fp32 accumulate (1e-2 class) */
-#define ALLSET_PREC_SPLIT 1  /* each f32 operand as TWO bf16 terms, three tensor-core products (x_lo W_hi + x_hi W_lo + x_hi W_hi)
-                              * accumulated in fp32: ~2^-17 relative per product, the reference's fp32 class (1e-4 bar) */
+#define ALLSET_PREC_SPLIT 1  /* f32 operands cut into bf16 terms whose products are accumulated in fp32 in TMEM: THREE terms and the
+                              * six products down to 2^-18 for allset_linear_fwd (as close to fp64 as an fp32 SGEMM: 1e-6 of the
+                              * output scale; two terms leave 2^-17 per product, which flips ReLUs that sit within 1e-5 of zero),
+                              * TWO terms / three products for allset_linear_wgrad (a sum over all rows averages the 2^-17 errors) */
 
 /* ONE nn.Linear on tcgen05 (equal widths d in {64, 128}), the unit the training path is built from:
  *     out = [relu]( LN?(x) op(W)^T + b ),   op(W) = W ([out, in], nn.Linear layout)      -- forward of MLP.lins[i] /
