@@ -249,3 +249,30 @@ def config_namespace(**kw) -> SimpleNamespace:
              Classifier_hidden=64, Classifier_num_layers=2, num_classes=None)
     d.update(kw)
     return SimpleNamespace(**d)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Split-precision Linear (test infrastructure for allset_linear_fwd / allset_linear_wgrad, csrc/mlp_tcgen05.cuh MODE 3 and
+# csrc/linear_wgrad.cuh): the ARITHMETIC the tensor-core kernels perform, restated on the CPU.  The reference computes
+# `x @ W.t()` in fp32 (nn.Linear, reference src/layers.py:575); the kernels cut both operands into bf16 terms, whose
+# pairwise products are exact in fp32, and accumulate the products in fp32.
+# ----------------------------------------------------------------------------------------------------------------------
+def bf16_terms(x: Tensor, n_terms: int) -> List[Tensor]:
+    """x (fp32) as n_terms bf16-representable fp32 tensors: t0 = bf16(x), t1 = bf16(x - t0), ... (round to nearest even)."""
+    terms, rest = [], x.float()
+    for _ in range(n_terms):
+        t = rest.to(torch.bfloat16).float()
+        terms.append(t)
+        rest = rest - t
+    return terms
+
+
+def linear_split(x: Tensor, w: Tensor, n_terms: int = 3) -> Tensor:
+    """x @ w.t() from bf16 terms: all products x_i w_j with i + j < n_terms (n_terms = 3: the six products of
+    allset_linear_fwd; n_terms = 2: the three of the usual "3x" split), smallest first, fp32 accumulation."""
+    xs, ws = bf16_terms(x, n_terms), bf16_terms(w, n_terms)
+    pairs = sorted(((i, j) for i in range(n_terms) for j in range(n_terms) if i + j < n_terms), key=lambda p: -(p[0] + p[1]))
+    acc = torch.zeros(x.shape[0], w.shape[0], dtype=torch.float32)
+    for i, j in pairs:
+        acc = acc + xs[i] @ ws[j].t()
+    return acc
