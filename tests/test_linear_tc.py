@@ -190,3 +190,16 @@ def test_fp32_mode_model_eval_on_tcgen05_matches_the_aten_path(pma, monkeypatch)
         monkeypatch.setattr(ops, 'TC_LINEAR', True)
         out = model(SimpleNamespace(x=x, edge_index=ei.clone(), norm=norm))
     assert (out - ref).abs().max().item() <= 1e-4 * max(ref.abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize('d', [64, 128])
+def test_linear_fwd_split_vs_the_oracle_restatement(d):
+    """The kernel against the CPU restatement of its own arithmetic (oracle/allset_oracle.py::linear_split: three bf16 terms
+    per operand, six exact products, fp32 accumulation): same terms, same products, only the order of the fp32 additions
+    differs -- 1e-6 of the scale (the two are 2e-7 and 4e-7 away from fp64 themselves)."""
+    import allset_oracle as O
+    from allset_b200 import _lib
+    x, w, b = _mk(3000, d, 77 + d)
+    out = _lib.linear_fwd(x, w)
+    ref = O.linear_split(x.cpu(), w.cpu(), 3)
+    assert (out.cpu() - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
